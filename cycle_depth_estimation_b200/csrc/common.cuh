@@ -1,0 +1,54 @@
+// Host-side helpers shared by the translation units of libcdb200.so: error reporting, CUDA checks,
+// TMA tensor-map construction (driver entry point resolved at run time, so the library has no
+// link-time dependency on libcuda and loads on a machine without a driver).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cdb200.h"
+
+namespace cdb {
+
+// Thread-local message for cdb_last_error().
+char* error_buffer();
+int fail(int status, const char* fmt, ...);
+
+#define CDB_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (void)cudaGetLastError(); /* clear the non-sticky error state */                      \
+      return ::cdb::fail(CDB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                               \
+    }                                                                                       \
+  } while (0)
+
+#define CDB_REQUIRE(cond, status, ...)                  \
+  do {                                                  \
+    if (!(cond)) return ::cdb::fail(status, __VA_ARGS__); \
+  } while (0)
+
+// Device-side abort flag (set when a bounded mbarrier wait times out).
+int* device_abort_flag_ptr();
+
+// Encodes a tiled tensor map with 128-byte swizzle. dims/strides are given innermost first;
+// strides[i] (bytes) is the stride of dimension i+1 (dimension 0 is contiguous).
+int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
+
+int sm_count();
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+inline int floor_div(int a, int b) {
+  int q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+inline int pos_mod(int a, int b) { return a - floor_div(a, b) * b; }
+
+}  // namespace cdb

@@ -1,0 +1,522 @@
+// K1/K2 — implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05), sm_100a only.
+//
+// GEMM view:  D[m, n] = sum_k A[m, k] * B[n, k]
+//   m : 128 output pixels of one tile  (tile_n images x tile_h rows x tile_w columns)
+//   n : output channels (one tile of bn <= 256)
+//   k : (filter tap, 64-channel chunk) pairs — one pipeline stage per pair
+// A is never materialised: for every tap the TMA engine fetches the shifted NHWC window
+// {64 ch, tile_w, tile_h, tile_n} of the input straight into 128B-swizzled shared memory, where it
+// is exactly the K-major operand tcgen05.mma expects; out-of-range coordinates are zero-filled by the
+// TMA unit, which implements zero padding. Stride-2 and transposed convolutions are expressed through
+// parity views of the input / output, so the main loop is the same for all of them.
+//
+// Warp roles (256 threads, persistent over tiles):
+//   warp 0   TMA producer (one lane)        warp 1   tcgen05.mma issuer (one lane)
+//   warp 2   TMEM allocator                 warps 4-7  epilogue: tcgen05.ld -> bias/act -> global
+// Accumulators are double buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cdb {
+
+constexpr int kMaxTaps = 64;
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
+
+struct IgemmTap {
+  int16_t map, dh, dw, pad_;
+  int32_t wk;
+};
+
+struct IgemmParams {
+  int32_t n_taps, k_chunks;
+  int32_t tile_w, tile_h, tile_n;
+  int32_t tiles_w, tiles_h, tiles_n;
+  int32_t n_tiles_n;
+  int32_t dom_n, dom_h, dom_w;
+  int32_t cout, cstore, bn;
+  int32_t out_dtype, act;
+  float slope;
+  int32_t stages;
+  int32_t stats_on;
+  const float* bias;
+  void* out;
+  int64_t o_sn, o_sh, o_sw, o_sc;
+  float* stats;
+  int* abort_flag;
+  IgemmTap taps[kMaxTaps];
+};
+
+struct IgemmMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case CDB_ACT_RELU: return v > 0.f ? v : 0.f;
+    case CDB_ACT_LEAKY: return v > 0.f ? v : v * slope;
+    case CDB_ACT_TANH: return tanhf(v);
+    case CDB_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ int abort_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  const int k_blocks = p.n_taps * p.k_chunks;
+
+  if (threadIdx.x == 0) {
+    abort_smem = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&maps.b);
+    prefetch_tmap(&maps.a[0]);
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  volatile int* abort_flag = &abort_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles_n;
+        int m_tile = tile / p.n_tiles_n;
+        const int tw = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int tn = m_tile / p.tiles_h;
+        const int q0 = tw * p.tile_w, p0 = th * p.tile_h, img0 = tn * p.tile_n;
+        const int n0 = n_tile * p.bn;
+        for (int t = 0; t < p.n_taps && ok; ++t) {
+          const IgemmTap tap = p.taps[t];
+          const CUtensorMap* amap = &maps.a[tap.map];
+          for (int c = 0; c < p.k_chunks; ++c) {
+            if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u, abort_flag)) {
+              ok = false;
+              break;
+            }
+            const uint32_t full = smem_u32(&bar_full[stage]);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            mbar_arrive_expect_tx(full, stage_bytes);
+            tma_load_4d(amap, full, sa, c * 64, q0 + tap.dw, p0 + tap.dh, img0);
+            tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * 64, n0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        const uint32_t tphase = (local >> 1) & 1u;
+        if (!mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          if (!mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag)) {
+            ok = false;
+            break;
+          }
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (ok) umma_commit(smem_u32(&bar_tfull[buf]));
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int r_w = row % p.tile_w;
+    const int r_h = (row / p.tile_w) % p.tile_h;
+    const int r_n = row / (p.tile_w * p.tile_h);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int buf = local & 1;
+      const uint32_t tphase = (local >> 1) & 1u;
+      if (!mbar_wait(smem_u32(&bar_tfull[buf]), tphase, abort_flag)) break;
+      tc_fence_after();
+      const int n_tile = tile % p.n_tiles_n;
+      int m_tile = tile / p.n_tiles_n;
+      const int tw = m_tile % p.tiles_w;
+      m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int tn = m_tile / p.tiles_h;
+      const int q = tw * p.tile_w + r_w, pp = th * p.tile_h + r_h, img = tn * p.tile_n + r_n;
+      const bool valid = (q < p.dom_w) && (pp < p.dom_h) && (img < p.dom_n);
+      const int n0 = n_tile * p.bn;
+      const int64_t obase = img * p.o_sn + pp * p.o_sh + q * p.o_sw;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>(buf) * 256u;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        if (n0 + c0 >= p.cstore) break;  // uniform across the CTA
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int ch = n0 + c0 + j;
+          float x = __uint_as_float(v[j]);
+          if (p.bias != nullptr && ch < p.cout) x += __ldg(p.bias + ch);
+          x = apply_act(x, p.act, p.slope);
+          f[j] = ch < p.cout ? x : 0.f;
+        }
+        if (p.stats_on) {
+          // per-(image, channel) sum and sum of squares of the fp32 accumulators of this tile
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float s1 = valid ? f[j] : 0.f;
+            float s2 = s1 * s1;
+            if (p.tile_n == 1) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              }
+              const int ch = n0 + c0 + j;
+              if (lane == 0 && ch < p.cout && (tn * p.tile_n) < p.dom_n) {
+                atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.cout + ch) * 2, s1);
+                atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.cout + ch) * 2 + 1, s2);
+              }
+            } else {
+              const int ch = n0 + c0 + j;
+              if (valid && ch < p.cout) {
+                atomicAdd(p.stats + (static_cast<int64_t>(img) * p.cout + ch) * 2, s1);
+                atomicAdd(p.stats + (static_cast<int64_t>(img) * p.cout + ch) * 2 + 1, s2);
+              }
+            }
+          }
+        }
+        if (valid) {
+          if (p.out_dtype == CDB_BF16 && p.o_sc == 1) {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + obase + n0 + c0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (n0 + c0 + h * 8 < p.cstore) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[h * 8 + 0], f[h * 8 + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[h * 8 + 2], f[h * 8 + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[h * 8 + 4], f[h * 8 + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[h * 8 + 6], f[h * 8 + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                *reinterpret_cast<uint4*>(o + h * 8) = pk;
+              }
+            }
+          } else if (p.out_dtype == CDB_BF16) {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + obase;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = n0 + c0 + j;
+              if (ch < p.cstore) o[ch * p.o_sc] = __float2bfloat16(f[j]);
+            }
+          } else {
+            float* o = static_cast<float*>(p.out) + obase;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = n0 + c0 + j;
+              if (ch < p.cstore) o[ch * p.o_sc] = f[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && abort_smem && p.abort_flag) atomicExch(p.abort_flag, 1);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Host side: geometry -> tap tables, TMA maps, launches
+// -------------------------------------------------------------------------------------------------
+static void choose_tile(int dom_n, int dom_h, int dom_w, int* tw, int* th, int* tn) {
+  int w = 1;
+  while (w < dom_w && w < 128) w <<= 1;
+  int h = 1;
+  while (h < dom_h && h * w < 128) h <<= 1;
+  int n = 128 / (w * h);
+  *tw = w;
+  *th = h;
+  *tn = n;
+  (void)dom_n;
+}
+
+struct SrcView {
+  void* ptr;
+  int64_t dims[4];     // c, w, h, n
+  int64_t strides[3];  // w, h, n strides in elements
+};
+
+static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, int w_rows_pad,
+                        int w_ktotal, IgemmParams& prm, cudaStream_t stream) {
+  IgemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const uint32_t abox[4] = {64u, (uint32_t)prm.tile_w, (uint32_t)prm.tile_h, (uint32_t)prm.tile_n};
+  for (int i = 0; i < 4; ++i) {
+    const SrcView& v = views[i < n_views ? i : 0];
+    uint64_t dims[4] = {(uint64_t)v.dims[0], (uint64_t)v.dims[1], (uint64_t)v.dims[2], (uint64_t)v.dims[3]};
+    uint64_t str[3] = {(uint64_t)v.strides[0] * 2, (uint64_t)v.strides[1] * 2, (uint64_t)v.strides[2] * 2};
+    for (int d = 0; d < 4; ++d)
+      if (dims[d] == 0) dims[d] = 1;
+    int rc = make_tmap(&maps.a[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, dims, str, abox);
+    if (rc != CDB_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)w_ktotal, (uint64_t)w_rows_pad};
+    uint64_t str[1] = {(uint64_t)w_ktotal * 2};
+    uint32_t box[2] = {64u, (uint32_t)prm.bn};
+    int rc = make_tmap(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, str, box);
+    if (rc != CDB_OK) return rc;
+  }
+  const int stage_bytes = kABytes + prm.bn * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  prm.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  const int total = prm.tiles_n * prm.tiles_h * prm.tiles_w * prm.n_tiles_n;
+  int grid = total < sm_count() ? total : sm_count();
+  if (grid < 1) return CDB_OK;
+  prm.abort_flag = device_abort_flag_ptr();
+  igemm_kernel<<<grid, 256, smem, stream>>>(maps, prm);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+static int check_act(const CdbAct* x, const char* name) {
+  CDB_REQUIRE(x && x->ptr, CDB_ERR_BAD_DESC, "%s: null tensor", name);
+  CDB_REQUIRE(x->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "%s: only bf16 activations are supported", name);
+  CDB_REQUIRE(x->c % 8 == 0 && x->sw % 8 == 0 && x->sh % 8 == 0 && x->sn % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0,
+              CDB_ERR_ALIGNMENT, "%s: channels/strides must be multiples of 8 elements and ptr 16B aligned", name);
+  return CDB_OK;
+}
+
+}  // namespace cdb
+
+using namespace cdb;
+
+extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
+                              int32_t w_rows_pad, int32_t w_kpad, const CdbOut* y,
+                              const CdbEpilogue* ep, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(g && x && y && wpacked, CDB_ERR_BAD_DESC, "conv2d_fwd: null argument");
+  int rc = check_act(x, "conv2d_fwd x");
+  if (rc) return rc;
+  CDB_REQUIRE(g->stride == 1 || g->stride == 2, CDB_ERR_UNSUPPORTED, "conv2d_fwd: stride %d", g->stride);
+  CDB_REQUIRE(g->dil >= 1 && (g->dil == 1 || g->stride == 1), CDB_ERR_UNSUPPORTED, "conv2d_fwd: dilation with stride");
+  CDB_REQUIRE(y->c >= 1 && y->cstore >= y->c, CDB_ERR_BAD_DESC, "conv2d_fwd: bad output channels");
+  CDB_REQUIRE(w_rows_pad % 16 == 0 && w_rows_pad >= y->c && w_kpad % 64 == 0, CDB_ERR_BAD_DESC,
+              "conv2d_fwd: packed weight geometry");
+  if (y->dtype == CDB_BF16 && y->sc == 1)
+    CDB_REQUIRE(y->sn % 8 == 0 && y->sh % 8 == 0 && y->sw % 8 == 0 && y->cstore % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0,
+                CDB_ERR_ALIGNMENT, "conv2d_fwd: bf16 NHWC output must be 16B aligned per pixel");
+  const int st = g->stride;
+  const int n_real_taps = g->rowpack ? g->r : g->r * g->s;
+  CDB_REQUIRE(n_real_taps <= kMaxTaps, CDB_ERR_UNSUPPORTED, "conv2d_fwd: too many taps");
+
+  IgemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.cout = y->c;
+  prm.cstore = y->cstore;
+  prm.bn = w_rows_pad < 256 ? w_rows_pad : 256;
+  prm.n_tiles_n = ceil_div(w_rows_pad, prm.bn);
+  prm.out_dtype = y->dtype;
+  prm.act = ep ? ep->act : CDB_ACT_NONE;
+  prm.slope = ep ? ep->slope : 0.f;
+  prm.bias = ep ? ep->bias : nullptr;
+  prm.stats = ep ? ep->stats : nullptr;
+  prm.stats_on = prm.stats != nullptr;
+  prm.k_chunks = w_kpad / 64;
+  prm.dom_n = y->n;
+
+  if (!g->transposed) {
+    // ---------------- direct convolution: parity views of the input for stride 2
+    SrcView views[4];
+    int n_views = st * st;
+    if (g->rowpack) {
+      CDB_REQUIRE(g->pad_w == 0 && g->s * g->rowpack <= 64 && (g->rowpack == 8 || g->rowpack == 16) &&
+                      x->c == g->rowpack && w_kpad == 64,
+                  CDB_ERR_BAD_DESC, "conv2d_fwd: rowpack geometry");
+      const int span = 64 / g->rowpack;  // pixels covered by one K block
+      CDB_REQUIRE(x->w >= st * (y->w - 1) + span, CDB_ERR_BAD_DESC,
+                  "conv2d_fwd: rowpack input needs w >= %d (has %d)", st * (y->w - 1) + span, x->w);
+      n_views = st;
+      for (int a = 0; a < st; ++a) {
+        views[a].ptr = static_cast<__nv_bfloat16*>(x->ptr) + a * x->sh;
+        views[a].dims[0] = 64;
+        views[a].dims[1] = (x->w - span) / st + 1;
+        views[a].dims[2] = (x->h - a + st - 1) / st;
+        views[a].dims[3] = x->n;
+        views[a].strides[0] = x->sw * st;
+        views[a].strides[1] = x->sh * st;
+        views[a].strides[2] = x->sn;
+      }
+      prm.n_taps = g->r;
+      for (int r = 0; r < g->r; ++r) {
+        const int ih = r * g->dil - g->pad_h;
+        const int a = pos_mod(ih, st);
+        prm.taps[r].map = (int16_t)a;
+        prm.taps[r].dh = (int16_t)((ih - a) / st);
+        prm.taps[r].dw = 0;
+        prm.taps[r].wk = r * 64;
+      }
+    } else {
+      for (int a = 0; a < st; ++a)
+        for (int b = 0; b < st; ++b) {
+          SrcView& v = views[a * st + b];
+          v.ptr = static_cast<__nv_bfloat16*>(x->ptr) + a * x->sh + b * x->sw;
+          v.dims[0] = x->c;
+          v.dims[1] = (x->w - b + st - 1) / st;
+          v.dims[2] = (x->h - a + st - 1) / st;
+          v.dims[3] = x->n;
+          v.strides[0] = x->sw * st;
+          v.strides[1] = x->sh * st;
+          v.strides[2] = x->sn;
+        }
+      prm.n_taps = g->r * g->s;
+      for (int r = 0; r < g->r; ++r)
+        for (int s = 0; s < g->s; ++s) {
+          const int ih = r * g->dil - g->pad_h, iw = s * g->dil - g->pad_w;
+          const int a = pos_mod(ih, st), b = pos_mod(iw, st);
+          IgemmTap& t = prm.taps[r * g->s + s];
+          t.map = (int16_t)(a * st + b);
+          t.dh = (int16_t)((ih - a) / st);
+          t.dw = (int16_t)((iw - b) / st);
+          t.wk = (r * g->s + s) * w_kpad;
+        }
+    }
+    prm.dom_h = y->h;
+    prm.dom_w = y->w;
+    choose_tile(y->n, y->h, y->w, &prm.tile_w, &prm.tile_h, &prm.tile_n);
+    prm.tiles_w = ceil_div(y->w, prm.tile_w);
+    prm.tiles_h = ceil_div(y->h, prm.tile_h);
+    prm.tiles_n = ceil_div(y->n, prm.tile_n);
+    prm.out = y->ptr;
+    prm.o_sn = y->sn;
+    prm.o_sh = y->sh;
+    prm.o_sw = y->sw;
+    prm.o_sc = y->sc;
+    const int ktotal = (g->rowpack ? g->r : g->r * g->s) * w_kpad;
+    return launch_igemm(views, n_views, wpacked, w_rows_pad, ktotal, prm, stream);
+  }
+
+  // ---------------- transposed convolution: one launch per output parity class
+  CDB_REQUIRE(!g->rowpack, CDB_ERR_UNSUPPORTED, "conv2d_fwd: rowpack with transposed");
+  SrcView view;
+  view.ptr = x->ptr;
+  view.dims[0] = x->c;
+  view.dims[1] = x->w;
+  view.dims[2] = x->h;
+  view.dims[3] = x->n;
+  view.strides[0] = x->sw;
+  view.strides[1] = x->sh;
+  view.strides[2] = x->sn;
+  const int ktotal = g->r * g->s * w_kpad;
+  const size_t esz = y->dtype == CDB_BF16 ? 2 : 4;
+  for (int a = 0; a < st; ++a)
+    for (int b = 0; b < st; ++b) {
+      const int dom_h = (y->h - a + st - 1) / st, dom_w = (y->w - b + st - 1) / st;
+      if (dom_h <= 0 || dom_w <= 0) continue;
+      IgemmParams q = prm;
+      int nt = 0;
+      for (int r = 0; r < g->r; ++r) {
+        const int ih = a + g->pad_h - r * g->dil;
+        if (pos_mod(ih, st) != 0) continue;
+        for (int s = 0; s < g->s; ++s) {
+          const int iw = b + g->pad_w - s * g->dil;
+          if (pos_mod(iw, st) != 0) continue;
+          IgemmTap& t = q.taps[nt++];
+          t.map = 0;
+          t.dh = (int16_t)(ih / st);
+          t.dw = (int16_t)(iw / st);
+          t.wk = (r * g->s + s) * w_kpad;
+        }
+      }
+      q.n_taps = nt;
+      q.dom_h = dom_h;
+      q.dom_w = dom_w;
+      choose_tile(y->n, dom_h, dom_w, &q.tile_w, &q.tile_h, &q.tile_n);
+      q.tiles_w = ceil_div(dom_w, q.tile_w);
+      q.tiles_h = ceil_div(dom_h, q.tile_h);
+      q.tiles_n = ceil_div(y->n, q.tile_n);
+      q.out = static_cast<char*>(y->ptr) + (a * y->sh + b * y->sw) * (int64_t)esz;
+      q.o_sn = y->sn;
+      q.o_sh = y->sh * st;
+      q.o_sw = y->sw * st;
+      q.o_sc = y->sc;
+      if (nt == 0) return fail(CDB_ERR_UNSUPPORTED, "conv2d_fwd: transposed parity class without taps");
+      rc = launch_igemm(&view, 1, wpacked, w_rows_pad, ktotal, q, stream);
+      if (rc) return rc;
+    }
+  return CDB_OK;
+}

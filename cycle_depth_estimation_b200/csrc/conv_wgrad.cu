@@ -1,0 +1,487 @@
+// K3 — convolution weight gradient on tcgen05, plus the weight (re)packing kernels.
+//
+//   out[tap][cS][cG] = sum_{n,p,q} S[n,p,q,cS] * G[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, cG]
+// S is the "small" tensor whose pixels are iterated (dy for Conv2d, x for ConvTranspose2d), G the
+// shifted one (x for Conv2d, dy for ConvTranspose2d); the result maps to W4[d0 = cS][d1 = cG][r][s]
+// in both cases. The reduction runs over pixels, which is the SLOW axis of NHWC, so both operands
+// reach the tensor core MN-major: a TMA box {64 ch, tile_w, tile_h, tile_n} of 64 pixels lands as
+// 64 rows (k) x 128 B (64 channels, mn) in 128B-swizzled shared memory.
+//   M (128 rows of TMEM) = channels of one operand, N (<= 256 columns) = channels of the other,
+//   K = 64 pixels per pipeline stage, split-K over pixel tiles across CTAs (fp32 partials in a
+//   caller-provided workspace, reduced deterministically by the finalize kernel).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace cdb {
+
+constexpr int kWgMaxTaps = 64;
+constexpr int kWgMaxStages = 8;
+constexpr int kChunkBytes = 64 * 128;  // 64 pixels x 64 channels bf16
+
+struct WgTap {
+  int16_t map, dh, dw, pad_;
+};
+
+struct WgParams {
+  int32_t n_taps;
+  int32_t tile_w, tile_h, tile_n;     // 64 pixels per K block
+  int32_t tiles_w, tiles_h, tiles_n;  // pixel tiles over the S domain
+  int32_t m_tiles, n_tiles, bn;       // bn multiple of 64
+  int32_t splits, k_tiles_per_split;
+  int32_t shift_on_a;                 // 1: the tap shift applies to the M-side operand
+  int32_t stages;
+  int32_t mpad, npad;
+  float* ws;                          // [splits][taps][mpad][npad]
+  int* abort_flag;
+  WgTap taps[kWgMaxTaps];
+};
+
+struct WgMaps {
+  CUtensorMap fixed;     // S views: single map
+  CUtensorMap shift[4];  // G parity views
+};
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kWgMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kWgMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull[2];
+  __shared__ __align__(8) uint64_t bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ int abort_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = 2u * kChunkBytes;
+  const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / 64u;
+  const uint32_t stage_bytes = a_bytes + b_chunks * kChunkBytes;
+  const int total_items = p.n_taps * p.m_tiles * p.n_tiles * p.splits;
+  const int k_tiles_total = p.tiles_n * p.tiles_h * p.tiles_w;
+
+  if (threadIdx.x == 0) {
+    abort_smem = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_tfull[b]), 1);
+      mbar_init(smem_u32(&bar_tempty[b]), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  volatile int* abort_flag = &abort_smem;
+
+  // item -> (split, tap, m_tile, n_tile); split fastest so that the CTAs of one wave share operands
+  auto decode = [&](int item, int& split, int& tap, int& mt, int& nt) {
+    split = item % p.splits;
+    item /= p.splits;
+    nt = item % p.n_tiles;
+    item /= p.n_tiles;
+    mt = item % p.m_tiles;
+    tap = item / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+        int split, tap, mt, nt;
+        decode(item, split, tap, mt, nt);
+        const WgTap tp = p.taps[tap];
+        const CUtensorMap* amap = p.shift_on_a ? &maps.shift[tp.map] : &maps.fixed;
+        const CUtensorMap* bmap = p.shift_on_a ? &maps.fixed : &maps.shift[tp.map];
+        const int a_dh = p.shift_on_a ? tp.dh : 0, a_dw = p.shift_on_a ? tp.dw : 0;
+        const int b_dh = p.shift_on_a ? 0 : tp.dh, b_dw = p.shift_on_a ? 0 : tp.dw;
+        const int kt0 = split * p.k_tiles_per_split;
+        int kt1 = kt0 + p.k_tiles_per_split;
+        if (kt1 > k_tiles_total) kt1 = k_tiles_total;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          int t = kt;
+          const int tw = t % p.tiles_w;
+          t /= p.tiles_w;
+          const int th = t % p.tiles_h;
+          const int tn = t / p.tiles_h;
+          const int q0 = tw * p.tile_w, p0 = th * p.tile_h, img0 = tn * p.tile_n;
+          if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u, abort_flag)) {
+            ok = false;
+            break;
+          }
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_arrive_expect_tx(full, stage_bytes);
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * 64, q0 + a_dw, p0 + a_dh, img0);
+          for (uint32_t j = 0; j < b_chunks; ++j)
+            tma_load_4d(bmap, full, sa + a_bytes + j * kChunkBytes, nt * p.bn + j * 64, q0 + b_dw,
+                        p0 + b_dh, img0);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn));
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      bool ok = true;
+      for (int item = blockIdx.x; item < total_items && ok; item += gridDim.x, ++local) {
+        int split, tap, mt, nt;
+        decode(item, split, tap, mt, nt);
+        const int kt0 = split * p.k_tiles_per_split;
+        int kt1 = kt0 + p.k_tiles_per_split;
+        if (kt1 > k_tiles_total) kt1 = k_tiles_total;
+        const int buf = local & 1;
+        const uint32_t tphase = (local >> 1) & 1u;
+        if (!mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag)) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
+        for (int kt = kt0; kt < kt1; ++kt) {
+          if (!mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag)) {
+            ok = false;
+            break;
+          }
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 k-rows.
+          const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
+            umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&bar_empty[stage]));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (ok) umma_commit(smem_u32(&bar_tfull[buf]));
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int local = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
+      int split, tap, mt, nt;
+      decode(item, split, tap, mt, nt);
+      const int kt0 = split * p.k_tiles_per_split;
+      const bool empty_split = kt0 >= k_tiles_total;
+      const int buf = local & 1;
+      const uint32_t tphase = (local >> 1) & 1u;
+      if (!mbar_wait(smem_u32(&bar_tfull[buf]), tphase, abort_flag)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>(buf) * 256u;
+      float* dst = p.ws + ((static_cast<int64_t>(split) * p.n_taps + tap) * p.mpad + mt * 128 + row) * p.npad +
+                   nt * p.bn;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 o;
+          o.x = empty_split ? 0.f : __uint_as_float(v[j]);
+          o.y = empty_split ? 0.f : __uint_as_float(v[j + 1]);
+          o.z = empty_split ? 0.f : __uint_as_float(v[j + 2]);
+          o.w = empty_split ? 0.f : __uint_as_float(v[j + 3]);
+          *reinterpret_cast<float4*>(dst + c0 + j) = o;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_tempty[buf]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && abort_smem && p.abort_flag) atomicExch(p.abort_flag, 1);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Sums the split-K partials and scatters them into the fp32 filter gradient W4[d0][d1][R][S].
+// m_is_d0: the M side of the GEMM holds d0 (else d1). rowpack: tap = r, the d1-side index is
+// s*rowpack + ch.
+__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int d0, int d1,
+                                      int R, int S, int n_taps, int splits, int mpad, int npad,
+                                      int m_is_d0, int rowpack, int accumulate) {
+  const int64_t total = static_cast<int64_t>(d0) * d1 * R * S;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t t = idx;
+    const int s = t % S;
+    t /= S;
+    const int r = t % R;
+    t /= R;
+    const int i1 = t % d1;
+    const int i0 = t / d1;
+    int tap, cS = i0, cG = i1;
+    if (rowpack) {
+      tap = r;
+      cG = s * rowpack + i1;
+    } else {
+      tap = r * S + s;
+    }
+    const int m = m_is_d0 ? cS : cG;
+    const int n = m_is_d0 ? cG : cS;
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp)
+      acc += ws[((static_cast<int64_t>(sp) * n_taps + tap) * mpad + m) * npad + n];
+    dw[idx] = accumulate ? dw[idx] + acc : acc;
+  }
+}
+
+// fp32 W4[d0][d1][R][S] -> bf16 packed[rows_pad][taps*kpad] (see cdb_pack_conv_weight).
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
+                                   int d1, int R, int S, int rows_are_dim0, int rowpack, int rows,
+                                   int kdim, int rows_pad, int kpad, int n_taps) {
+  const int64_t ktotal = static_cast<int64_t>(n_taps) * kpad;
+  const int64_t total = static_cast<int64_t>(rows_pad) * ktotal;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = idx / ktotal;
+    const int kk = idx % ktotal;
+    const int tap = kk / kpad;
+    int k = kk % kpad;
+    int r, s;
+    bool ok = row < rows;
+    if (rowpack) {
+      r = tap;
+      s = k / rowpack;
+      k = k % rowpack;
+      ok = ok && s < S && k < kdim;
+    } else {
+      r = tap / S;
+      s = tap % S;
+      ok = ok && k < kdim;
+    }
+    float v = 0.f;
+    if (ok) {
+      const int i0 = rows_are_dim0 ? row : k;
+      const int i1 = rows_are_dim0 ? k : row;
+      v = w[((static_cast<int64_t>(i0) * d1 + i1) * R + r) * S + s];
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+struct WgPlan {
+  int m_is_s;  // M side = S tensor
+  int cM, cN, mpad, npad, bn, m_tiles, n_tiles;
+  int tile_w, tile_h, tile_n, tiles_w, tiles_h, tiles_n, k_tiles, splits, k_per_split, n_taps;
+};
+
+static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g_act, WgPlan* pl) {
+  const int cS = s_act->c;
+  const int cG = g->rowpack ? 64 : g_act->c;
+  auto cost = [](int cm, int cn) { return (int64_t)round_up(cm, 128) * round_up(cn, 64); };
+  pl->m_is_s = cost(cS, cG) <= cost(cG, cS) ? 1 : 0;
+  pl->cM = pl->m_is_s ? cS : cG;
+  pl->cN = pl->m_is_s ? cG : cS;
+  pl->mpad = round_up(pl->cM, 128);
+  pl->m_tiles = pl->mpad / 128;
+  const int n64 = round_up(pl->cN, 64);
+  pl->bn = n64 < 256 ? n64 : 256;
+  pl->n_tiles = ceil_div(n64, pl->bn);
+  pl->npad = pl->n_tiles * pl->bn;
+  // 64-pixel K tiles over the S domain
+  int w = 1;
+  while (w < s_act->w && w < 64) w <<= 1;
+  int h = 1;
+  while (h < s_act->h && h * w < 64) h <<= 1;
+  pl->tile_w = w;
+  pl->tile_h = h;
+  pl->tile_n = 64 / (w * h);
+  pl->tiles_w = ceil_div(s_act->w, w);
+  pl->tiles_h = ceil_div(s_act->h, h);
+  pl->tiles_n = ceil_div(s_act->n, pl->tile_n);
+  pl->k_tiles = pl->tiles_w * pl->tiles_h * pl->tiles_n;
+  pl->n_taps = g->rowpack ? g->r : g->r * g->s;
+  const int items = pl->n_taps * pl->m_tiles * pl->n_tiles;
+  int splits = (2 * sm_count()) / (items > 0 ? items : 1);
+  if (splits < 1) splits = 1;
+  int max_splits = pl->k_tiles / 8;
+  if (max_splits < 1) max_splits = 1;
+  if (splits > max_splits) splits = max_splits;
+  pl->k_per_split = ceil_div(pl->k_tiles, splits);
+  pl->splits = ceil_div(pl->k_tiles, pl->k_per_split);
+  return CDB_OK;
+}
+
+}  // namespace cdb
+
+using namespace cdb;
+
+extern "C" int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
+                                    int32_t rows_are_dim0, int32_t rowpack, void* out,
+                                    cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(w4 && out, CDB_ERR_BAD_DESC, "pack_conv_weight: null argument");
+  const int rows = rows_are_dim0 ? d0 : d1;
+  const int kdim = rows_are_dim0 ? d1 : d0;
+  const int rows_pad = round_up(rows, 16);
+  int kpad, n_taps;
+  if (rowpack) {
+    CDB_REQUIRE(s * rowpack <= 64 && kdim <= rowpack, CDB_ERR_BAD_DESC, "pack_conv_weight: rowpack geometry");
+    kpad = 64;
+    n_taps = r;
+  } else {
+    kpad = round_up(kdim, 64);
+    n_taps = r * s;
+  }
+  const int64_t total = (int64_t)rows_pad * n_taps * kpad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w4, static_cast<__nv_bfloat16*>(out), d0, d1, r, s,
+                                                 rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad, n_taps);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+static void wgrad_roles(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, const CdbAct** s_act,
+                        const CdbAct** g_act) {
+  if (g->transposed) {
+    *s_act = x;
+    *g_act = dy;
+  } else {
+    *s_act = dy;
+    *g_act = x;
+  }
+}
+
+extern "C" size_t cdb_conv2d_wgrad_workspace(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy) {
+  if (!g || !x || !dy) return 0;
+  const CdbAct *s_act, *g_act;
+  wgrad_roles(g, x, dy, &s_act, &g_act);
+  WgPlan pl;
+  plan_wgrad(g, s_act, g_act, &pl);
+  return (size_t)pl.splits * pl.n_taps * pl.mpad * pl.npad * sizeof(float);
+}
+
+extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, float* dw4,
+                                int32_t d0, int32_t d1, int32_t accumulate, void* workspace,
+                                size_t ws_bytes, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(g && x && dy && dw4 && workspace, CDB_ERR_BAD_DESC, "conv2d_wgrad: null argument");
+  CDB_REQUIRE(x->dtype == CDB_BF16 && dy->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: bf16 only");
+  CDB_REQUIRE(g->stride == 1 || g->stride == 2, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: stride %d", g->stride);
+  CDB_REQUIRE(!(g->rowpack && g->transposed), CDB_ERR_UNSUPPORTED, "conv2d_wgrad: rowpack with transposed");
+  const CdbAct *s_act, *g_act;
+  wgrad_roles(g, x, dy, &s_act, &g_act);
+  WgPlan pl;
+  plan_wgrad(g, s_act, g_act, &pl);
+  const size_t need = (size_t)pl.splits * pl.n_taps * pl.mpad * pl.npad * sizeof(float);
+  CDB_REQUIRE(ws_bytes >= need, CDB_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < %zu", ws_bytes, need);
+  CDB_REQUIRE(pl.n_taps <= kWgMaxTaps, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: too many taps");
+  const int st = g->stride;
+
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const uint32_t box[4] = {64u, (uint32_t)pl.tile_w, (uint32_t)pl.tile_h, (uint32_t)pl.tile_n};
+  {
+    uint64_t dims[4] = {(uint64_t)s_act->c, (uint64_t)s_act->w, (uint64_t)s_act->h, (uint64_t)s_act->n};
+    uint64_t str[3] = {(uint64_t)s_act->sw * 2, (uint64_t)s_act->sh * 2, (uint64_t)s_act->sn * 2};
+    int rc = make_tmap(&maps.fixed, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s_act->ptr, dims, str, box);
+    if (rc) return rc;
+  }
+  WgParams prm;
+  memset(&prm, 0, sizeof(prm));
+  if (g->rowpack) {
+    const int span = 64 / g->rowpack;
+    for (int a = 0; a < 4; ++a) {
+      const int aa = a < st ? a : 0;
+      uint64_t dims[4] = {64, (uint64_t)((g_act->w - span) / st + 1), (uint64_t)((g_act->h - aa + st - 1) / st),
+                          (uint64_t)g_act->n};
+      uint64_t str[3] = {(uint64_t)g_act->sw * st * 2, (uint64_t)g_act->sh * st * 2, (uint64_t)g_act->sn * 2};
+      int rc = make_tmap(&maps.shift[a], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                         static_cast<__nv_bfloat16*>(g_act->ptr) + aa * g_act->sh, dims, str, box);
+      if (rc) return rc;
+    }
+    for (int r = 0; r < g->r; ++r) {
+      const int ih = r * g->dil - g->pad_h;
+      const int a = pos_mod(ih, st);
+      prm.taps[r].map = (int16_t)a;
+      prm.taps[r].dh = (int16_t)((ih - a) / st);
+      prm.taps[r].dw = 0;
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) {
+      const int a = (i < st * st) ? i / st : 0, b = (i < st * st) ? i % st : 0;
+      uint64_t dims[4] = {(uint64_t)g_act->c, (uint64_t)((g_act->w - b + st - 1) / st),
+                          (uint64_t)((g_act->h - a + st - 1) / st), (uint64_t)g_act->n};
+      for (int d = 0; d < 4; ++d)
+        if (dims[d] == 0) dims[d] = 1;
+      uint64_t str[3] = {(uint64_t)g_act->sw * st * 2, (uint64_t)g_act->sh * st * 2, (uint64_t)g_act->sn * 2};
+      int rc = make_tmap(&maps.shift[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                         static_cast<__nv_bfloat16*>(g_act->ptr) + a * g_act->sh + b * g_act->sw, dims, str, box);
+      if (rc) return rc;
+    }
+    for (int r = 0; r < g->r; ++r)
+      for (int s = 0; s < g->s; ++s) {
+        const int ih = r * g->dil - g->pad_h, iw = s * g->dil - g->pad_w;
+        const int a = pos_mod(ih, st), b = pos_mod(iw, st);
+        WgTap& t = prm.taps[r * g->s + s];
+        t.map = (int16_t)(a * st + b);
+        t.dh = (int16_t)((ih - a) / st);
+        t.dw = (int16_t)((iw - b) / st);
+      }
+  }
+  prm.n_taps = pl.n_taps;
+  prm.tile_w = pl.tile_w;
+  prm.tile_h = pl.tile_h;
+  prm.tile_n = pl.tile_n;
+  prm.tiles_w = pl.tiles_w;
+  prm.tiles_h = pl.tiles_h;
+  prm.tiles_n = pl.tiles_n;
+  prm.m_tiles = pl.m_tiles;
+  prm.n_tiles = pl.n_tiles;
+  prm.bn = pl.bn;
+  prm.splits = pl.splits;
+  prm.k_tiles_per_split = pl.k_per_split;
+  prm.shift_on_a = pl.m_is_s ? 0 : 1;
+  prm.mpad = pl.mpad;
+  prm.npad = pl.npad;
+  prm.ws = static_cast<float*>(workspace);
+  prm.abort_flag = device_abort_flag_ptr();
+  const int stage_bytes = 2 * kChunkBytes + (pl.bn / 64) * kChunkBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  prm.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static size_t smem_attr = 0;
+  if (smem > smem_attr) {
+    CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  const int items = pl.n_taps * pl.m_tiles * pl.n_tiles * pl.splits;
+  int grid = items < sm_count() ? items : sm_count();
+  wgrad_kernel<<<grid, 256, smem, stream>>>(maps, prm);
+  CDB_CUDA_OK(cudaGetLastError());
+
+  const int64_t total = (int64_t)d0 * d1 * g->r * g->s;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  // W4[d0 = cS][d1 = cG]: the M side holds d0 when M is the S tensor.
+  wgrad_finalize_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), dw4, d0, d1, g->r,
+                                                    g->s, pl.n_taps, pl.splits, pl.mpad, pl.npad, pl.m_is_s,
+                                                    g->rowpack, accumulate);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}

@@ -1,0 +1,123 @@
+/*
+ * cdb200.h — C ABI of libcdb200.so, the B200 (sm_100a) kernel library behind the drop-in
+ * replacements for the dense-convolution hot path of JosephineRabbit/cycle_depth_estimation.
+ *
+ * The reference has no native layer: every entry point below replaces the ATen/cuDNN call that a
+ * torch.nn module of the reference reaches (reference file:line given per function).  All pointers
+ * are DEVICE pointers owned by the caller unless stated otherwise; the library never allocates,
+ * frees or keeps device memory, launches only on the stream it is given, never synchronises and is
+ * CUDA-graph capturable.  Every function returns 0 on success or a negative CdbStatus and records a
+ * message retrievable with cdb_last_error() (thread local).
+ *
+ * Activations are NHWC ("channels last"), channel stride 1, bf16 (dtype 0) or fp32 (dtype 1);
+ * stored channel counts are multiples of 8 so that every pixel starts on a 16-byte boundary.
+ */
+#ifndef CDB200_H_
+#define CDB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cdbStream_t; /* a cudaStream_t / CUstream */
+
+typedef enum CdbStatus {
+  CDB_OK = 0,
+  CDB_ERR_BAD_DESC = -1,
+  CDB_ERR_UNSUPPORTED = -2,
+  CDB_ERR_ALIGNMENT = -3,
+  CDB_ERR_WORKSPACE = -4,
+  CDB_ERR_CUDA = -5,
+  CDB_ERR_DEVICE_ABORT = -6
+} CdbStatus;
+
+enum { CDB_BF16 = 0, CDB_F32 = 1 };
+enum { CDB_ACT_NONE = 0, CDB_ACT_RELU = 1, CDB_ACT_LEAKY = 2, CDB_ACT_TANH = 3, CDB_ACT_SIGMOID = 4 };
+enum { CDB_NORM_NONE = 0, CDB_NORM_INSTANCE = 1, CDB_NORM_BATCH = 2 };
+enum { CDB_PAD_ZERO = 0, CDB_PAD_REFLECT = 1 };
+
+/* NHWC activation view. c = stored channels (multiple of 8); strides in elements. */
+typedef struct CdbAct {
+  void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+  int32_t dtype;
+  int32_t reserved;
+} CdbAct;
+
+/* Strided output of a convolution: element (n,p,q,ch) goes to ptr[n*sn + p*sh + q*sw + ch*sc].
+ * c = number of real output channels; cstore >= c = channels written (the extra ones get 0), used
+ * to keep channel-padded NHWC buffers clean.  With sc == 1 and dtype bf16 stores are 16-byte
+ * vectors (ptr, sn, sh, sw must then be multiples of 8 elements). */
+typedef struct CdbOut {
+  void* ptr;
+  int32_t n, h, w, c;
+  int32_t cstore;
+  int32_t dtype;
+  int64_t sn, sh, sw, sc;
+} CdbOut;
+
+/* Convolution geometry.  Forward semantics on the STORED tensors (out-of-range x reads 0):
+ *   transposed == 0:  y[n,p,q,o] = sum_{r,s,i} x[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, i] * W[o,i,r,s]
+ *   transposed == 1:  y[n,p,q,o] = sum_{r,s,i : (p+pad_h-r*dil) % stride == 0 ...}
+ *                                   x[n, (p+pad_h-r*dil)/stride, (q+pad_w-s*dil)/stride, i] * W[o,i,r,s]
+ * where W is the PACKED operand (see cdb_pack_conv_weight); a materialised (reflect/zero) padding
+ * is expressed by passing the padded buffer as x with pad_* = 0.
+ * rowpack != 0 selects the small-channel image layers: x stores `rowpack` (8 or 16) channels per
+ * pixel and one K block covers a whole filter row (s = 0..S-1) of one r; requires transposed == 0,
+ * pad_w == 0 (materialised), S*rowpack <= 64 and x.w >= stride*(y.w-1) + 64/rowpack. */
+typedef struct CdbConvGeom {
+  int32_t r, s;
+  int32_t stride;
+  int32_t pad_h, pad_w;
+  int32_t dil;
+  int32_t transposed;
+  int32_t rowpack;
+} CdbConvGeom;
+
+typedef struct CdbEpilogue {
+  const float* bias; /* [c] or NULL */
+  int32_t act;
+  float slope;
+  float* stats;      /* optional [n][c][2] fp32 (sum, sum of squares) accumulated with atomics, or NULL */
+  int64_t reserved;
+} CdbEpilogue;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int cdb_version(void);
+const char* cdb_last_error(void);
+/* Reads-and-clears the device-side abort flag raised when a kernel's bounded mbarrier wait timed out. */
+int cdb_device_abort_flag(void);
+
+/* ---- K1/K2: tcgen05 implicit-GEMM convolution ----------------------------------------------
+ * Replaces aten.convolution reached from nn.Conv2d / nn.ConvTranspose2d
+ * (models/networks.py:158,166,178,185,214,229,277,285-301,331-356; new_multi/networks5_ds.py
+ * passim) and, with the dgrad packing of the weights, the data-gradient half of
+ * aten.convolution_backward.  wpacked: bf16 [rows_pad][taps*kpad] from cdb_pack_conv_weight. */
+int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, int32_t w_rows_pad,
+                   int32_t w_kpad, const CdbOut* y, const CdbEpilogue* ep, cdbStream_t stream);
+
+/* Packs an fp32 4-D filter W4[d0][d1][R][S] (Conv2d: OIHW, ConvTranspose2d: IOHW) into the bf16
+ * GEMM B operand [rows_pad][taps*kpad]:  packed[row][tap*kpad + k] = W4[row][k][r][s] when
+ * rows_are_dim0, else W4[k][row][r][s]; tap = r*S+s (rowpack: tap = r, k = s*rowpack + ch, kpad 64).
+ * rows_pad = round_up(rows,16), kpad = round_up(k,64).  out must hold rows_pad*taps*kpad bf16. */
+int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
+                         int32_t rows_are_dim0, int32_t rowpack, void* out, cdbStream_t stream);
+
+/* ---- K3: weight gradient -------------------------------------------------------------------
+ * Replaces the filter-gradient half of aten.convolution_backward.
+ *   dW4[d0][d1][r][s] (+)= sum_{n,p,q} dy[n,p,q,o] * x[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, i]
+ * with (o,i) = (d0,d1) for Conv2d and x/dy swapped roles for ConvTranspose2d (g->transposed).
+ * workspace: cdb_conv2d_wgrad_workspace() bytes of fp32 split-K partials. */
+size_t cdb_conv2d_wgrad_workspace(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy);
+int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, float* dw4,
+                     int32_t d0, int32_t d1, int32_t accumulate, void* workspace, size_t ws_bytes,
+                     cdbStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDB200_H_ */

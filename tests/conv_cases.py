@@ -1,0 +1,175 @@
+"""Convolution parity cases shared by tests/test_conv_gpu.py and tools/gpu_probe.py.
+
+Each case builds seeded inputs, runs the tcgen05 path through the C ABI and compares with a plain
+PyTorch fp32 evaluation of the same convolution on the SAME bf16-rounded operands, so the only
+differences are accumulation order and the rounding of the stored result.
+Tolerances (relative L2): bf16 outputs 4e-3 (one rounding, 2^-9), fp32 outputs 2e-5.
+"""
+import torch
+import torch.nn.functional as F
+
+from cycle_depth_estimation_b200 import ops
+
+TOL_BF16 = 4e-3
+TOL_F32 = 2e-5
+
+
+def rel_l2(a, b):
+    a = a.double()
+    b = b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).to(torch.bfloat16)
+
+
+def nhwc(x_nchw, cstore=None):
+    """NCHW (any float) -> contiguous NHWC bf16 with channels zero-padded to cstore."""
+    n, c, h, w = x_nchw.shape
+    cs = cstore or ops.round_up(c, 8)
+    out = torch.zeros((n, h, w, cs), dtype=torch.bfloat16, device=x_nchw.device)
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1)
+    return out
+
+
+def conv_fwd_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=False, out_pad=0,
+                  out_mode="nhwc", bias=False, act=ops.ACT_NONE, stats=False, seed=0):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = _rand((n, cin, h, w), gen)
+    if transposed:
+        w4 = _rand((cin, cout, k, k), gen, 0.05)
+        ref = F.conv_transpose2d(x.float(), w4.float(), None, stride, pad, out_pad, 1, dil)
+    else:
+        w4 = _rand((cout, cin, k, k), gen, 0.05)
+        ref = F.conv2d(x.float(), w4.float(), None, stride, pad, dil)
+    b = None
+    if bias:
+        b = torch.randn(cout, generator=gen, device="cuda")
+        ref = ref + b.view(1, -1, 1, 1)
+    if act == ops.ACT_RELU:
+        ref = torch.relu(ref)
+    elif act == ops.ACT_LEAKY:
+        ref = F.leaky_relu(ref, 0.2)
+    elif act == ops.ACT_TANH:
+        ref = torch.tanh(ref)
+    p, q = ref.shape[2], ref.shape[3]
+    xs = nhwc(x)
+    wp, rows_pad, kpad = ops.pack_conv_weight(w4.float().contiguous(), rows_are_dim0=not transposed)
+    g = ops.geom(k, k, stride, pad, pad, dil, transposed)
+    st = torch.zeros((n, cout, 2), dtype=torch.float32, device="cuda") if stats else None
+    if out_mode == "nhwc":
+        cs = ops.round_up(cout, 8)
+        y = torch.full((n, p, q, cs), float("nan"), dtype=torch.bfloat16, device="cuda")
+        ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nhwc(y, cout), b, act, 0.2, st)
+        got = y[..., :cout].permute(0, 3, 1, 2).float()
+        tol = TOL_BF16
+        pad_ok = bool((y[..., cout:] == 0).all()) if cs > cout else True
+    else:
+        y = torch.full((n, cout, p, q), float("nan"), dtype=torch.float32, device="cuda")
+        ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nchw(y), b, act, 0.2, st)
+        got = y
+        tol = TOL_F32
+        pad_ok = True
+    torch.cuda.synchronize()
+    err = rel_l2(got, ref)
+    res = {"err": err, "tol": tol, "ok": err <= tol and pad_ok and bool(torch.isfinite(got).all())}
+    if stats:
+        s_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1)
+        res["stats_err"] = rel_l2(st, s_ref)
+        res["ok"] = res["ok"] and res["stats_err"] < 1e-3
+    return res
+
+
+def conv_rowpack_case(n, cin, cout, h, w, k, stride, rowpack, seed=0):
+    """Image-input layers: x holds `rowpack` channels per pixel, padding materialised by the caller."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = _rand((n, cin, h, w), gen)  # already padded image
+    w4 = _rand((cout, cin, k, k), gen, 0.05)
+    ref = F.conv2d(x.float(), w4.float(), None, stride, 0, 1)
+    p, q = ref.shape[2], ref.shape[3]
+    span = 64 // rowpack
+    wneed = max(w, stride * (q - 1) + span)
+    xs = torch.zeros((n, h, wneed, rowpack), dtype=torch.bfloat16, device="cuda")
+    xs[:, :, :w, :cin] = x.permute(0, 2, 3, 1)
+    wp, rows_pad, kpad = ops.pack_conv_weight(w4.float().contiguous(), True, rowpack)
+    g = ops.geom(k, k, stride, 0, 0, 1, False, rowpack)
+    cs = ops.round_up(cout, 8)
+    y = torch.full((n, p, q, cs), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nhwc(y, cout))
+    torch.cuda.synchronize()
+    got = y[..., :cout].permute(0, 3, 1, 2).float()
+    err = rel_l2(got, ref)
+    return {"err": err, "tol": TOL_BF16, "ok": err <= TOL_BF16}
+
+
+def conv_wgrad_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=False, out_pad=0,
+                    rowpack=0, accumulate=False, seed=0):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = _rand((n, cin, h, w), gen)
+    xf = x.float().requires_grad_(False)
+    if transposed:
+        w4 = torch.zeros((cin, cout, k, k), device="cuda", requires_grad=True)
+        y = F.conv_transpose2d(xf, w4, None, stride, pad, out_pad, 1, dil)
+    else:
+        w4 = torch.zeros((cout, cin, k, k), device="cuda", requires_grad=True)
+        y = F.conv2d(xf, w4, None, stride, pad, dil)
+    dy = _rand(tuple(y.shape), gen, 0.1)
+    y.backward(dy.float())
+    ref = w4.grad
+    if rowpack:
+        span = 64 // rowpack
+        q = y.shape[3]
+        wneed = max(w, stride * (q - 1) + span)
+        xs = torch.zeros((n, h, wneed, rowpack), dtype=torch.bfloat16, device="cuda")
+        xs[:, :, :w, :cin] = x.permute(0, 2, 3, 1)
+    else:
+        xs = nhwc(x)
+    dys = nhwc(dy)
+    g = ops.geom(k, k, stride, pad, pad, dil, transposed, rowpack)
+    base = torch.randn(ref.shape, generator=gen, device="cuda") if accumulate else torch.zeros_like(ref)
+    dw = base.clone()
+    ops.conv2d_wgrad(g, xs, dys, dw, accumulate)
+    torch.cuda.synchronize()
+    err = rel_l2(dw - base if accumulate else dw, ref)
+    return {"err": err, "tol": 1e-3, "ok": err <= 1e-3}
+
+
+FWD_CASES = {
+    # name: kwargs
+    "gemm_1x1_c64_n16": dict(n=1, cin=64, cout=16, h=8, w=16, k=1),
+    "gemm_1x1_c128_n256": dict(n=2, cin=128, cout=256, h=16, w=32, k=1),
+    "gemm_1x1_c64_n512": dict(n=1, cin=64, cout=512, h=16, w=16, k=1),
+    "conv3x3_zero_pad_256": dict(n=2, cin=256, cout=256, h=64, w=64, k=3, pad=1),
+    "conv3x3_prepadded_stats": dict(n=2, cin=128, cout=128, h=34, w=34, k=3, stats=True),
+    "conv3x3_s2_64_128": dict(n=2, cin=64, cout=128, h=32, w=32, k=3, stride=2, pad=1),
+    "conv4x4_s2_patchgan": dict(n=2, cin=64, cout=128, h=64, w=64, k=4, stride=2, pad=1, bias=True, act=ops.ACT_LEAKY),
+    "conv4x4_s1_31": dict(n=2, cin=256, cout=512, h=32, w=32, k=4, pad=1),
+    "conv4x4_s1_cout1": dict(n=2, cin=512, cout=1, h=31, w=31, k=4, pad=1, bias=True, out_mode="nchw"),
+    "conv3x3_dil2": dict(n=1, cin=64, cout=64, h=12, w=40, k=3, pad=2, dil=2),
+    "conv7x7_cout3_tanh_nchw": dict(n=1, cin=64, cout=3, h=70, w=70, k=7, bias=True, act=ops.ACT_TANH, out_mode="nchw"),
+    "conv_cin8": dict(n=1, cin=8, cout=64, h=16, w=16, k=3, pad=1),
+    "conv_small_spatial_batchtile": dict(n=16, cin=512, cout=512, h=2, w=2, k=4, stride=2, pad=1),
+    "convT3x3_s2": dict(n=2, cin=256, cout=128, h=16, w=16, k=3, stride=2, pad=1, transposed=True, out_pad=1),
+    "convT4x4_s2": dict(n=2, cin=128, cout=64, h=8, w=8, k=4, stride=2, pad=1, transposed=True),
+    "convT4x4_s2_from1x1": dict(n=4, cin=512, cout=512, h=1, w=1, k=4, stride=2, pad=1, transposed=True),
+    "dgrad_like_3x3_pad2": dict(n=1, cin=256, cout=256, h=64, w=64, k=3, pad=2),
+}
+
+ROWPACK_CASES = {
+    "rowpack8_7x7": dict(n=2, cin=3, cout=64, h=70, w=70, k=7, stride=1, rowpack=8),
+    "rowpack16_4x4_s2": dict(n=2, cin=3, cout=64, h=66, w=66, k=4, stride=2, rowpack=16),
+    "rowpack16_4x4_s2_cin6": dict(n=1, cin=6, cout=64, h=34, w=34, k=4, stride=2, rowpack=16),
+}
+
+WGRAD_CASES = {
+    "wgrad_3x3_256": dict(n=2, cin=256, cout=256, h=34, w=34, k=3),
+    "wgrad_3x3_pad1_128_64": dict(n=2, cin=128, cout=64, h=32, w=32, k=3, pad=1, accumulate=True),
+    "wgrad_3x3_s2": dict(n=2, cin=64, cout=128, h=32, w=32, k=3, stride=2, pad=1),
+    "wgrad_4x4_s2": dict(n=2, cin=64, cout=128, h=32, w=32, k=4, stride=2, pad=1),
+    "wgrad_4x4_s1_cout1": dict(n=2, cin=512, cout=1, h=31, w=31, k=4, pad=1),
+    "wgrad_convT3x3_s2": dict(n=2, cin=256, cout=128, h=16, w=16, k=3, stride=2, pad=1, transposed=True, out_pad=1),
+    "wgrad_7x7_cout3": dict(n=1, cin=64, cout=3, h=38, w=38, k=7),
+    "wgrad_rowpack8_7x7": dict(n=2, cin=3, cout=64, h=38, w=38, k=7, rowpack=8),
+    "wgrad_rowpack16_4x4_s2": dict(n=2, cin=3, cout=64, h=34, w=34, k=4, stride=2, rowpack=16),
+}
