@@ -33,6 +33,14 @@ class CdbEpilogue(C.Structure):
                 ("reserved", C.c_int64)]
 
 
+class CdbNormDesc(C.Structure):
+    _fields_ = [("norm", C.c_int32), ("act", C.c_int32), ("slope", C.c_float), ("eps", C.c_float),
+                ("channels", C.c_int32), ("pad", C.c_int32), ("use_running", C.c_int32),
+                ("update_running", C.c_int32), ("momentum", C.c_float), ("reserved", C.c_int32),
+                ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -50,6 +58,7 @@ def lib():
     L.cdb_last_error.restype = C.c_char_p
     L.cdb_device_abort_flag.restype = C.c_int
     L.cdb_conv2d_wgrad_workspace.restype = C.c_size_t
+    L.cdb_depth_metrics_workspace.restype = C.c_size_t
     _lib = L
     return L
 

@@ -1,0 +1,307 @@
+// Layout conversion at the module boundary (NCHW fp32 <-> NHWC bf16), the fused GAN / L1 / BCE
+// losses (forward scalar and gradient in one pass) and a multi-tensor-free fused Adam step.
+#include "common.cuh"
+
+namespace cdb {
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (warp == 0) {
+    r = lane < (blockDim.x >> 5) ? smem[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in warp 0
+}
+
+// src NCHW fp32 (strided) -> interior of an NHWC bf16 buffer with `cs` stored channels; channels
+// >= c are zero; a reflect halo of `pad` pixels is mirrored. With act_out != nullptr the value is
+// multiplied by the derivative of `act` evaluated from the activation OUTPUT (backward of a final
+// tanh / sigmoid / leaky layer).
+struct ToNhwcParams {
+  const float* src;
+  const float* act_out;
+  int64_t s_n, s_c, s_h, s_w;
+  __nv_bfloat16* out;
+  int64_t o_n, o_h, o_w;
+  int N, C, H, W, cs, pad, act;
+  float slope;
+};
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(ToNhwcParams p) {
+  const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = idx % p.W;
+    const int h = (idx / p.W) % p.H;
+    const int n = idx / (static_cast<int64_t>(p.W) * p.H);
+    const int64_t sbase = n * p.s_n + h * p.s_h + w * p.s_w;
+    __nv_bfloat16* ob = p.out + n * p.o_n;
+    for (int c0 = 0; c0 < p.cs; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float v = 0.f;
+        if (c < p.C) {
+          v = p.src[sbase + c * p.s_c];
+          if (p.act_out != nullptr) {
+            const float o = p.act_out[sbase + c * p.s_c];
+            if (p.act == CDB_ACT_TANH) v *= (1.f - o * o);
+            else if (p.act == CDB_ACT_SIGMOID) v *= o * (1.f - o);
+            else if (p.act == CDB_ACT_LEAKY) v *= (o > 0.f ? 1.f : p.slope);
+            else if (p.act == CDB_ACT_RELU) v *= (o > 0.f ? 1.f : 0.f);
+          }
+        }
+        f[j] = v;
+      }
+      uint4 pk;
+      __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      int hh[3], ww[3];
+      int nh = 0, nw = 0;
+      hh[nh++] = h;
+      ww[nw++] = w;
+      if (p.pad > 0) {
+        if (h >= 1 && h <= p.pad) hh[nh++] = -h;
+        if (h <= p.H - 2 && h >= p.H - 1 - p.pad) hh[nh++] = 2 * (p.H - 1) - h;
+        if (w >= 1 && w <= p.pad) ww[nw++] = -w;
+        if (w <= p.W - 2 && w >= p.W - 1 - p.pad) ww[nw++] = 2 * (p.W - 1) - w;
+      }
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b)
+          *reinterpret_cast<uint4*>(ob + hh[a] * p.o_h + ww[b] * p.o_w + c0) = pk;
+    }
+  }
+}
+
+// dst[n,c,h,w] (+)= sum of the reflect images of (h,w) in src [N,C,H+2p,W+2p] (fp32 NCHW).
+__global__ void reflect_fold_nchw_kernel(const float* __restrict__ src, float* __restrict__ dst, int NC, int H,
+                                         int W, int pad, int accumulate) {
+  const int64_t total = static_cast<int64_t>(NC) * H * W;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int w = idx % W;
+    const int h = (idx / W) % H;
+    const int64_t nc = idx / (static_cast<int64_t>(W) * H);
+    int hh[3], ww[3];
+    int nh = 0, nw = 0;
+    hh[nh++] = h;
+    ww[nw++] = w;
+    if (h >= 1 && h <= pad) hh[nh++] = -h;
+    if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
+    if (w >= 1 && w <= pad) ww[nw++] = -w;
+    if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
+    float acc = 0.f;
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b) acc += src[(nc * Hp + hh[a] + pad) * Wp + ww[b] + pad];
+    dst[idx] = accumulate ? dst[idx] + acc : acc;
+  }
+}
+
+// db[c] = sum_{n,h,w} g[n,c,h,w] * act'(out[n,c,h,w])  — bias gradient of a final conv (+ activation)
+// layer taken from the fp32 NCHW tensors, one block per channel.
+__global__ void __launch_bounds__(256)
+bias_grad_nchw_kernel(const float* __restrict__ g, const float* __restrict__ act_out, int act, float slope, int N,
+                      int C, int64_t HW, float* __restrict__ db) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const int64_t base = (static_cast<int64_t>(n) * C + c) * HW;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+      float v = g[base + i];
+      if (act_out != nullptr) {
+        const float o = act_out[base + i];
+        if (act == CDB_ACT_TANH) v *= (1.f - o * o);
+        else if (act == CDB_ACT_SIGMOID) v *= o * (1.f - o);
+        else if (act == CDB_ACT_LEAKY) v *= (o > 0.f ? 1.f : slope);
+        else if (act == CDB_ACT_RELU) v *= (o > 0.f ? 1.f : 0.f);
+      }
+      acc += v;
+    }
+  }
+  const float r = block_reduce_sum(acc, red);
+  if (threadIdx.x == 0) db[c] = r;
+}
+
+// ---- losses: loss_acc += weight * mean(f(x)); grad = weight * f'(x) / numel -----------------------
+enum { kLossMse = 0, kLossL1 = 1, kLossBce = 2 };
+
+template <int kKind>
+__global__ void __launch_bounds__(256)
+loss_kernel(const float* __restrict__ x, const float* __restrict__ y, float target, int64_t numel, float weight,
+            float* __restrict__ loss_acc, float* __restrict__ grad) {
+  __shared__ float red[32];
+  const float inv_n = 1.f / static_cast<float>(numel);
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float a = x[i];
+    const float t = y != nullptr ? y[i] : target;
+    float l, g;
+    if (kKind == kLossMse) {
+      const float d = a - t;
+      l = d * d;
+      g = 2.f * d;
+    } else if (kKind == kLossL1) {
+      const float d = a - t;
+      l = fabsf(d);
+      g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else {
+      // torch.nn.BCELoss: log terms clamped at -100; backward divides by max((1-a)*a, 1e-12)
+      const float la = fmaxf(logf(a), -100.f), l1a = fmaxf(logf(1.f - a), -100.f);
+      l = -(t * la + (1.f - t) * l1a);
+      g = (a - t) / fmaxf((1.f - a) * a, 1e-12f);
+    }
+    acc += l;
+    if (grad != nullptr) grad[i] = weight * inv_n * g;
+  }
+  const float r = block_reduce_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_acc, weight * inv_n * r);
+}
+
+// out[i] = a[i] * (*scalar)   (chain rule with the incoming scalar gradient)
+__global__ void scale_by_scalar_kernel(const float* __restrict__ a, const float* __restrict__ scalar,
+                                       float* __restrict__ out, int64_t numel) {
+  const float s = *scalar;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = a[i] * s;
+}
+
+// Adam (torch.optim.Adam semantics, no amsgrad, no weight decay): one launch per parameter tensor.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t numel, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt) {
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);  // lerp, as torch does
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+static int grid_for(int64_t n, int per_thread = 4) {
+  int64_t b = (n + 256 * per_thread - 1) / (256 * per_thread);
+  const int cap = sm_count() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace cdb
+
+using namespace cdb;
+
+extern "C" int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t h, int32_t w, int64_t s_n,
+                                int64_t s_c, int64_t s_h, int64_t s_w, const float* act_out, int32_t act,
+                                float slope, const CdbAct* out, int32_t pad, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(src && out && out->ptr, CDB_ERR_BAD_DESC, "nchw_to_nhwc: null argument");
+  CDB_REQUIRE(out->dtype == CDB_BF16 && out->c % 8 == 0 && out->c >= c, CDB_ERR_BAD_DESC, "nchw_to_nhwc: out channels");
+  CDB_REQUIRE(out->n == n && out->h == h && out->w == w, CDB_ERR_BAD_DESC, "nchw_to_nhwc: out must be the interior view");
+  CDB_REQUIRE(out->sn % 8 == 0 && out->sh % 8 == 0 && out->sw % 8 == 0 && (reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0,
+              CDB_ERR_ALIGNMENT, "nchw_to_nhwc: alignment");
+  CDB_REQUIRE(pad >= 0 && pad < h && pad < w, CDB_ERR_BAD_DESC, "nchw_to_nhwc: pad");
+  ToNhwcParams p;
+  p.src = src;
+  p.act_out = act_out;
+  p.s_n = s_n;
+  p.s_c = s_c;
+  p.s_h = s_h;
+  p.s_w = s_w;
+  p.out = static_cast<__nv_bfloat16*>(out->ptr);
+  p.o_n = out->sn;
+  p.o_h = out->sh;
+  p.o_w = out->sw;
+  p.N = n;
+  p.C = c;
+  p.H = h;
+  p.W = w;
+  p.cs = out->c;
+  p.pad = pad;
+  p.act = act;
+  p.slope = slope;
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * h * w, 1), 256, 0, stream>>>(p);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_reflect_fold_nchw(const float* src, float* dst, int32_t nc, int32_t h, int32_t w,
+                                     int32_t pad, int32_t accumulate, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(src && dst && pad >= 0 && pad < h && pad < w, CDB_ERR_BAD_DESC, "reflect_fold_nchw: bad argument");
+  reflect_fold_nchw_kernel<<<grid_for((int64_t)nc * h * w, 1), 256, 0, stream>>>(src, dst, nc, h, w, pad, accumulate);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_bias_grad_nchw(const float* g, const float* act_out, int32_t act, float slope, int32_t n,
+                                  int32_t c, int64_t hw, float* db, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(g && db && n > 0 && c > 0 && hw > 0, CDB_ERR_BAD_DESC, "bias_grad_nchw: bad argument");
+  bias_grad_nchw_kernel<<<c, 256, 0, stream>>>(g, act_out, act, slope, n, c, hw, db);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_loss_mse_const(const float* x, int64_t numel, float target, float weight, float* loss_acc,
+                                  float* grad, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(x && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_mse_const: bad argument");
+  loss_kernel<kLossMse><<<grid_for(numel), 256, 0, stream>>>(x, nullptr, target, numel, weight, loss_acc, grad);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_loss_bce_const(const float* x, int64_t numel, float target, float weight, float* loss_acc,
+                                  float* grad, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(x && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_bce_const: bad argument");
+  loss_kernel<kLossBce><<<grid_for(numel), 256, 0, stream>>>(x, nullptr, target, numel, weight, loss_acc, grad);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_loss_l1(const float* a, const float* b, int64_t numel, float weight, float* loss_acc,
+                           float* grad_a, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(a && b && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_l1: bad argument");
+  loss_kernel<kLossL1><<<grid_for(numel), 256, 0, stream>>>(a, b, 0.f, numel, weight, loss_acc, grad_a);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_scale_by_scalar(const float* a, const float* scalar, float* out, int64_t numel,
+                                   cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(a && scalar && out && numel > 0, CDB_ERR_BAD_DESC, "scale_by_scalar: bad argument");
+  scale_by_scalar_kernel<<<grid_for(numel), 256, 0, stream>>>(a, scalar, out, numel);
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}
+
+extern "C" int cdb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                             float lr, float beta1, float beta2, float eps, int32_t step, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, CDB_ERR_BAD_DESC, "adam_step: bad argument");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(numel), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
+                                                   (float)bc1, (float)sqrt(bc2));
+  CDB_CUDA_OK(cudaGetLastError());
+  return CDB_OK;
+}

@@ -385,6 +385,20 @@ extern "C" int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_im
   return CDB_OK;
 }
 
+static int fill_common(const CdbNormDesc* d, const CdbAct* y, int* C) {
+  CDB_REQUIRE(d->channels >= 1 && round_up(d->channels, 8) <= y->c, CDB_ERR_BAD_DESC,
+              "norm: channels %d do not fit the stored %d", d->channels, y->c);
+  CDB_REQUIRE(d->pad >= 0 && d->pad < y->h && d->pad < y->w, CDB_ERR_BAD_DESC, "norm: pad too large");
+  CDB_REQUIRE(d->norm == CDB_NORM_NONE || d->use_running || d->stats, CDB_ERR_BAD_DESC, "norm: stats missing");
+  CDB_REQUIRE(!d->use_running || (d->running_mean && d->running_var), CDB_ERR_BAD_DESC, "norm: running stats missing");
+  *C = d->channels;
+  return CDB_OK;
+}
+
+static float inv_count_of(const CdbNormDesc* d, const CdbAct* y) {
+  return 1.f / (d->norm == CDB_NORM_INSTANCE ? (float)(y->h * y->w) : (float)((int64_t)y->n * y->h * y->w));
+}
+
 extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const CdbAct* residual,
                                 const CdbAct* out, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -393,24 +407,24 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   if (rc) return rc;
   rc = check_view(out, "norm_act_fwd out");
   if (rc) return rc;
-  if (residual && residual->ptr) {
+  const bool has_res = residual && residual->ptr;
+  if (has_res) {
     rc = check_view(residual, "norm_act_fwd residual");
     if (rc) return rc;
   }
   CDB_REQUIRE(out->n == y->n && out->h == y->h && out->w == y->w, CDB_ERR_BAD_DESC,
               "norm_act_fwd: out must be the interior view with the shape of y");
-  CDB_REQUIRE(d->pad >= 0 && d->pad < y->h && d->pad < y->w, CDB_ERR_BAD_DESC, "norm_act_fwd: pad too large");
-  CDB_REQUIRE(d->norm == CDB_NORM_NONE || d->use_running || d->stats, CDB_ERR_BAD_DESC, "norm_act_fwd: stats missing");
   NormFwdParams p;
   memset(&p, 0, sizeof(p));
+  rc = fill_common(d, y, &p.C);
+  if (rc) return rc;
   p.y = view_of(y);
   p.out = view_of(out);
-  p.has_res = residual && residual->ptr;
-  if (p.has_res) p.res = view_of(residual);
+  p.has_res = has_res;
+  if (has_res) p.res = view_of(residual);
   p.H = y->h;
   p.W = y->w;
-  p.C = round_up(d->channels, 8) <= y->c ? round_up(d->channels, 8) : y->c;
-  const Mapping m = mapping_for(p.C);
+  const Mapping m = mapping_for(round_up(p.C, 8));
   p.vt = m.vt;
   p.norm = d->norm;
   p.act = d->act;
@@ -418,27 +432,15 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.eps = d->eps;
   p.pad = d->pad;
   p.per_image = d->norm == CDB_NORM_INSTANCE;
-  p.inv_count = 1.f / (d->norm == CDB_NORM_INSTANCE ? (float)(y->h * y->w) : (float)((int64_t)y->n * y->h * y->w));
+  p.inv_count = inv_count_of(d, y);
   p.use_running = d->use_running;
   p.stats = d->stats;
   p.gamma = d->gamma;
   p.beta = d->beta;
   p.running_mean = d->running_mean;
   p.running_var = d->running_var;
-  // note: p.C counts stored channels; coefficient lookups are bounded by the real channel count
-  NormFwdParams q = p;
-  q.C = p.C;
   const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
   dim3 grid(chunks, y->n, m.cv_tiles);
-  // real-channel bound for stats/gamma/beta indexing
-  q.C = p.C;
-  NormFwdParams launch = q;
-  launch.C = p.C;
-  // The kernels bound parameter reads by C; pass the real channel count through `norm_coeffs` by
-  // clamping here: padded channels of y are exact zeros and stay zero (scale*0 + shift must be 0).
-  launch.C = d->channels;
-  // stored-vector bound: a separate field keeps vector iteration over the padded channel count
-  (void)launch;
   norm_act_fwd_kernel<<<grid, 256, 0, stream>>>(p);
   CDB_CUDA_OK(cudaGetLastError());
   if (d->norm == CDB_NORM_BATCH && !d->use_running && d->update_running && d->running_mean && d->running_var) {
@@ -447,5 +449,64 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
                                                                       d->running_mean, d->running_var);
     CDB_CUDA_OK(cudaGetLastError());
   }
+  return CDB_OK;
+}
+
+extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const CdbAct* dout, const CdbAct* dskip,
+                                float* bstats, const CdbAct* dy, const CdbAct* gsum, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(d, CDB_ERR_BAD_DESC, "norm_act_bwd: null desc");
+  int rc = check_view(y, "norm_act_bwd y");
+  if (rc) return rc;
+  rc = check_view(dy, "norm_act_bwd dy");
+  if (rc) return rc;
+  const bool has_dout = dout && dout->ptr, has_dskip = dskip && dskip->ptr, has_gsum = gsum && gsum->ptr;
+  CDB_REQUIRE(has_dout || has_dskip, CDB_ERR_BAD_DESC, "norm_act_bwd: no incoming gradient");
+  if (has_dout && (rc = check_view(dout, "norm_act_bwd dout"))) return rc;
+  if (has_dskip && (rc = check_view(dskip, "norm_act_bwd dskip"))) return rc;
+  if (has_gsum && (rc = check_view(gsum, "norm_act_bwd gsum"))) return rc;
+  CDB_REQUIRE(d->act == CDB_ACT_NONE || d->act == CDB_ACT_RELU || d->act == CDB_ACT_LEAKY, CDB_ERR_UNSUPPORTED,
+              "norm_act_bwd: activation %d", d->act);
+  NormBwdParams p;
+  memset(&p, 0, sizeof(p));
+  rc = fill_common(d, y, &p.C);
+  if (rc) return rc;
+  const bool need_reduce = d->norm != CDB_NORM_NONE && !d->use_running;
+  CDB_REQUIRE(!need_reduce || bstats, CDB_ERR_BAD_DESC, "norm_act_bwd: bstats missing");
+  p.y = view_of(y);
+  p.dy = view_of(dy);
+  p.has_dout = has_dout;
+  p.has_dskip = has_dskip;
+  p.write_gsum = has_gsum;
+  if (has_dout) p.dout = view_of(dout);
+  if (has_dskip) p.dskip = view_of(dskip);
+  if (has_gsum) p.gsum = view_of(gsum);
+  p.H = y->h;
+  p.W = y->w;
+  const Mapping m = mapping_for(round_up(p.C, 8));
+  p.vt = m.vt;
+  p.norm = d->norm;
+  p.act = d->act;
+  p.slope = d->slope;
+  p.eps = d->eps;
+  p.pad = d->pad;
+  p.per_image = d->norm == CDB_NORM_INSTANCE;
+  p.inv_count = inv_count_of(d, y);
+  p.use_running = d->use_running;
+  p.stats = d->stats;
+  p.gamma = d->gamma;
+  p.beta = d->beta;
+  p.running_mean = d->running_mean;
+  p.running_var = d->running_var;
+  p.bstats = bstats;
+  const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
+  dim3 grid(chunks, y->n, m.cv_tiles);
+  if (need_reduce || (bstats && d->norm == CDB_NORM_NONE)) {
+    // norm none + bstats: the reduction yields the bias gradient (sum of ga) in component 0
+    norm_act_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+    CDB_CUDA_OK(cudaGetLastError());
+  }
+  norm_act_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  CDB_CUDA_OK(cudaGetLastError());
   return CDB_OK;
 }

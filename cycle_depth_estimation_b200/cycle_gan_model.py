@@ -1,0 +1,227 @@
+"""The CycleGAN training step of the reference (``models/cycle_gan_model.py:46-160``) on the B200
+networks: G_A / G_B ResNet generators, D_A / D_B PatchGANs, LSGAN + L1 cycle + identity losses, two
+ImagePools, Adam(lr, (beta1, 0.999)) for G and for D, and the fork's schedule of FOUR discriminator
+updates per generator update (:151).
+
+``CycleGANModel`` mirrors the reference class (``initialize(opt)``, ``set_input``, ``forward``,
+``backward_G``, ``backward_D_A/B``, ``optimize_parameters(train_or_test)``, ``get_current_losses``) but
+does not inherit the reference's BaseModel, whose glue is broken as shipped (SURVEY B-12).  With
+``world_size > 1`` (one process per GPU) gradients are averaged with a bucketed NCCL all-reduce before
+each optimizer step and the pools are replicated (all-gather of the fakes) so that every rank draws the
+same ``random`` sequence over the global batch, as the single-process reference would.
+"""
+import itertools
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+
+from . import losses, networks, ops
+from .image_pool import ImagePool
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps=1e-8) semantics on the cdb_adam_step kernel (one launch per
+    parameter tensor). Keeps ``param_groups`` / ``zero_grad`` / ``step`` so schedulers and the step glue
+    work unchanged."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.param_groups = [{'params': list(params), 'lr': lr, 'betas': betas, 'eps': eps, 'initial_lr': lr}]
+        self.state = {}
+        self.defaults = {'lr': lr, 'betas': betas, 'eps': eps}
+
+    def zero_grad(self, set_to_none=True):
+        for g in self.param_groups:
+            for p in g['params']:
+                if set_to_none:
+                    p.grad = None
+                elif p.grad is not None:
+                    p.grad.zero_()
+
+    @torch.no_grad()
+    def step(self):
+        for g in self.param_groups:
+            b1, b2 = g['betas']
+            for p in g['params']:
+                if p.grad is None:
+                    continue
+                st = self.state.get(p)
+                if st is None:
+                    st = {'step': 0, 'exp_avg': torch.zeros_like(p), 'exp_avg_sq': torch.zeros_like(p)}
+                    self.state[p] = st
+                st['step'] += 1
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                ops.adam_step(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'], st['step'])
+                # the kernel writes through raw pointers, which autograd's version counter cannot
+                # see; the packed-weight cache also keys on this explicit counter
+                p._cdb_version = getattr(p, '_cdb_version', 0) + 1
+
+
+class GradBuckets:
+    """Bucketed gradient all-reduce (average) over NCCL: gradients are flattened into ~25 MB fp32
+    buckets in reverse parameter order, each bucket is reduced with one collective on a side stream."""
+
+    def __init__(self, params, bucket_bytes=25 << 20):
+        self.params = [p for p in params]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+
+    def all_reduce(self):
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        world = dist.get_world_size()
+        works = []
+        for bucket in self.buckets:
+            grads = [p.grad for p in bucket if p.grad is not None]
+            if not grads:
+                continue
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, grads))
+        for work, flat, grads in works:
+            work.wait()
+            flat.div_(world)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
+
+class CycleGANModel:
+    def name(self):
+        return 'CycleGANModel'
+
+    def initialize(self, opt):
+        """opt: namespace with the fields of models/checkpoints/app2orange_cycle/opt.txt that the
+        reference reads at models/cycle_gan_model.py:32-69 (input_nc, output_nc, ngf, ndf, netG, netD,
+        n_layers_D, norm, no_dropout, init_type, init_gain, no_lsgan, pool_size, lr, beta1, lambda_A,
+        lambda_B, lambda_identity, isTrain) plus ``device``."""
+        self.opt = opt
+        self.isTrain = opt.isTrain
+        self.device = torch.device(getattr(opt, 'device', 'cuda'))
+        gpu_ids = [self.device]
+        self.loss_names = ['D_A', 'G_A', 'cycle_A', 'idt_A', 'D_B', 'G_B', 'cycle_B', 'idt_B']
+        self.model_names = ['G_A', 'G_B', 'D_A', 'D_B'] if self.isTrain else ['G_A', 'G_B']
+        self.netG_A = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.norm, not opt.no_dropout,
+                                        opt.init_type, opt.init_gain, gpu_ids)
+        self.netG_B = networks.define_G(opt.output_nc, opt.input_nc, opt.ngf, opt.netG, opt.norm, not opt.no_dropout,
+                                        opt.init_type, opt.init_gain, gpu_ids)
+        if self.isTrain:
+            use_sigmoid = opt.no_lsgan
+            self.netD_A = networks.define_D(opt.output_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, use_sigmoid,
+                                            opt.init_type, opt.init_gain, gpu_ids)
+            self.netD_B = networks.define_D(opt.input_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, use_sigmoid,
+                                            opt.init_type, opt.init_gain, gpu_ids)
+            self.fake_A_pool = ImagePool(opt.pool_size)
+            self.fake_B_pool = ImagePool(opt.pool_size)
+            self.criterionGAN = networks.GANLoss(use_lsgan=not opt.no_lsgan).to(self.device)
+            self.criterionCycle = losses.L1Loss()
+            self.criterionIdt = losses.L1Loss()
+            self.build_optimizers()
+
+    def build_optimizers(self):
+        opt = self.opt
+        adam = FusedAdam if getattr(opt, 'fused_adam', True) else torch.optim.Adam
+        self.optimizer_G = adam(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()),
+                                lr=opt.lr, betas=(opt.beta1, 0.999))
+        self.optimizer_D = adam(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()),
+                                lr=opt.lr, betas=(opt.beta1, 0.999))
+        self.optimizers = [self.optimizer_G, self.optimizer_D]
+        self._buckets_G = GradBuckets(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()))
+        self._buckets_D = GradBuckets(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()))
+
+    def set_input(self, input):
+        self.real_A = input['img_source'].to(self.device, non_blocking=True)
+        self.real_B = input['img_target'].to(self.device, non_blocking=True)
+
+    def set_requires_grad(self, nets, requires_grad=False):
+        if not isinstance(nets, list):
+            nets = [nets]
+        for net in nets:
+            if net is not None:
+                for param in net.parameters():
+                    param.requires_grad = requires_grad
+
+    def forward(self):
+        self.fake_B = self.netG_A(self.real_A)
+        self.rec_A = self.netG_B(self.fake_B)
+        self.fake_A = self.netG_B(self.real_B)
+        self.rec_B = self.netG_A(self.fake_A)
+
+    def _pool_query(self, pool, fake):
+        """Replicated pool under data parallelism: all ranks see the global batch in rank-major order
+        and replay the identical random stream; each rank keeps its own slice of the result."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world, rank = dist.get_world_size(), dist.get_rank()
+            gathered = [torch.empty_like(fake) for _ in range(world)]
+            dist.all_gather(gathered, fake.detach().contiguous())
+            out = pool.query(torch.cat(gathered, 0))
+            b = fake.shape[0]
+            return out[rank * b:(rank + 1) * b]
+        return pool.query(fake)
+
+    def backward_D_basic(self, netD, real, fake):
+        loss_D_real = self.criterionGAN(netD(real), True)
+        loss_D_fake = self.criterionGAN(netD(fake), False)
+        return (loss_D_real + loss_D_fake) * 0.5
+
+    def backward_D_A(self):
+        fake_B = self._pool_query(self.fake_B_pool, self.fake_B)
+        self.loss_D_A = self.backward_D_basic(self.netD_A, self.real_B, fake_B)
+        return self.loss_D_A
+
+    def backward_D_B(self):
+        fake_A = self._pool_query(self.fake_A_pool, self.fake_A)
+        self.loss_D_B = self.backward_D_basic(self.netD_B, self.real_A, fake_A)
+        return self.loss_D_B
+
+    def backward_G(self):
+        lambda_idt, lambda_A, lambda_B = self.opt.lambda_identity, self.opt.lambda_A, self.opt.lambda_B
+        if lambda_idt > 0:
+            self.idt_A = self.netG_A(self.real_B)
+            self.loss_idt_A = self.criterionIdt(self.idt_A, self.real_B) * lambda_B * lambda_idt
+            self.idt_B = self.netG_B(self.real_A)
+            self.loss_idt_B = self.criterionIdt(self.idt_B, self.real_A) * lambda_A * lambda_idt
+        else:
+            self.loss_idt_A = 0
+            self.loss_idt_B = 0
+        self.loss_G_A = self.criterionGAN(self.netD_A(self.fake_B), True)
+        self.loss_G_B = self.criterionGAN(self.netD_B(self.fake_A), True)
+        self.loss_cycle_A = self.criterionCycle(self.rec_A, self.real_A) * lambda_A
+        self.loss_cycle_B = self.criterionCycle(self.rec_B, self.real_B) * lambda_B
+        self.loss_G = (self.loss_G_A + self.loss_G_B + self.loss_cycle_A + self.loss_cycle_B + self.loss_idt_A
+                       + self.loss_idt_B)
+        return self.loss_G
+
+    def optimize_parameters(self, train_or_test='train'):
+        train = train_or_test == 'train'
+        self.forward()
+        self.set_requires_grad([self.netD_A, self.netD_B], False)
+        self.optimizer_G.zero_grad()
+        self.loss_G = self.backward_G()
+        if train:
+            self.loss_G.backward()
+            self._buckets_G.all_reduce()
+            self.optimizer_G.step()
+        for _ in range(4):
+            self.set_requires_grad([self.netD_A, self.netD_B], True)
+            self.optimizer_D.zero_grad()
+            self.loss_D_A = self.backward_D_A()
+            self.loss_D_B = self.backward_D_B()
+            if train:
+                self.loss_D_A.backward()
+                self.loss_D_B.backward()
+                self._buckets_D.all_reduce()
+                self.optimizer_D.step()
+
+    def get_current_losses(self):
+        out = OrderedDict()
+        for name in self.loss_names:
+            out[name] = float(getattr(self, 'loss_' + name))
+        return out

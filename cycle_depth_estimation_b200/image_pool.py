@@ -1,0 +1,46 @@
+"""Drop-in for the reference's ``util/image_pool.py``.
+
+Same decisions, in the same order, from the same Python ``random`` stream as the reference
+(util/image_pool.py:12-32): fill the pool first, then with probability 1/2 return a random stored image
+and store the new one.  The images live in ONE preallocated device tensor [pool_size, C, H, W] and the
+returned batch is written in place, so a query is index bookkeeping on the host plus slice copies on the
+device — no per-image unsqueeze / clone / cat.  ``trace`` records the decisions for the parity tests.
+"""
+import random
+
+import torch
+
+
+class ImagePool():
+    def __init__(self, pool_size):
+        self.pool_size = pool_size
+        if self.pool_size > 0:
+            self.num_imgs = 0
+            self.images = None      # [pool_size, C, H, W], allocated at the first query
+            self.trace = []
+
+    def query(self, images):
+        if self.pool_size == 0:
+            return images
+        images = images.detach()
+        if self.images is None:
+            self.images = torch.empty((self.pool_size,) + tuple(images.shape[1:]), dtype=images.dtype,
+                                      device=images.device)
+        out = torch.empty_like(images)
+        for i in range(images.shape[0]):
+            if self.num_imgs < self.pool_size:
+                self.images[self.num_imgs].copy_(images[i])
+                out[i].copy_(images[i])
+                self.trace.append(('fill', self.num_imgs))
+                self.num_imgs = self.num_imgs + 1
+            else:
+                p = random.uniform(0, 1)
+                if p > 0.5:
+                    random_id = random.randint(0, self.pool_size - 1)  # inclusive, as in the reference
+                    out[i].copy_(self.images[random_id])
+                    self.images[random_id].copy_(images[i])
+                    self.trace.append(('swap', random_id))
+                else:
+                    out[i].copy_(images[i])
+                    self.trace.append(('pass', -1))
+        return out

@@ -1,0 +1,309 @@
+"""Drop-in replacement for the reference's ``models/networks.py``.
+
+Same public names, constructor signatures, module tree and ``state_dict`` keys as the reference
+(models/networks.py:12-389), so ``cycle_gan_model.py`` / ``pix2pix_model.py`` / ``test_model.py`` can
+import this module instead.  The leaf modules are the stock ``torch.nn`` classes used purely as
+parameter holders; ``forward`` of every network runs the fused B200 engine (``engine.py``) — no
+cuDNN, no CPU path.
+"""
+import functools
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+from torch.optim import lr_scheduler
+
+from . import engine, losses
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers (models/networks.py:12-70)
+# ------------------------------------------------------------------------------------------------
+def get_norm_layer(norm_type='instance'):
+    """models/networks.py:12-22."""
+    table = {
+        'batch': lambda: functools.partial(nn.BatchNorm2d, affine=True),
+        'instance': lambda: functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=False),
+        'none': lambda: None,
+    }
+    if norm_type not in table:
+        raise NotImplementedError('normalization layer [%s] is not found' % norm_type)
+    return table[norm_type]()
+
+
+def get_scheduler(optimizer, opt):
+    """models/networks.py:24-38 (the lambda rule is hard-wired to 1 - max(0, epoch-10)/30 there)."""
+    policy = opt.lr_policy
+    if policy == 'lambda':
+        return lr_scheduler.LambdaLR(optimizer, lr_lambda=lambda epoch: 1.0 - max(0, epoch - 10) / float(30))
+    if policy == 'step':
+        return lr_scheduler.StepLR(optimizer, step_size=opt.lr_decay_iters, gamma=0.1)
+    if policy == 'plateau':
+        return lr_scheduler.ReduceLROnPlateau(optimizer, mode='min', factor=0.2, threshold=0.01, patience=5)
+    if policy == 'cosine':
+        return lr_scheduler.CosineAnnealingLR(optimizer, T_max=opt.niter, eta_min=0)
+    # the reference RETURNS (does not raise) the exception object here (models/networks.py:37)
+    return NotImplementedError('learning rate policy [%s] is not implemented', policy)
+
+
+def init_weights(net, init_type='normal', gain=0.02):
+    """models/networks.py:40-61: N(0, gain) (or xavier/kaiming/orthogonal) on Conv*/Linear weights,
+    zero biases, BatchNorm2d weight ~ N(1, gain)."""
+    fillers = {
+        'normal': lambda w: init.normal_(w, 0.0, gain),
+        'xavier': lambda w: init.xavier_normal_(w, gain=gain),
+        'kaiming': lambda w: init.kaiming_normal_(w, a=0, mode='fan_in'),
+        'orthogonal': lambda w: init.orthogonal_(w, gain=gain),
+    }
+
+    def visit(m):
+        name = type(m).__name__
+        if hasattr(m, 'weight') and ('Conv' in name or 'Linear' in name):
+            if init_type not in fillers:
+                raise NotImplementedError('initialization method [%s] is not implemented' % init_type)
+            fillers[init_type](m.weight.data)
+            if getattr(m, 'bias', None) is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif 'BatchNorm2d' in name:
+            init.normal_(m.weight.data, 1.0, gain)
+            init.constant_(m.bias.data, 0.0)
+
+    print('initialize network with %s' % init_type)
+    net.apply(visit)
+    engine.invalidate_packed_weights()  # the fills above write through .data
+
+
+def init_net(net, init_type='normal', init_gain=0.02, gpu_ids=[]):
+    """models/networks.py:63-70: moves to gpu_ids[0] (IndexError on an empty list, as there)."""
+    net.to(gpu_ids[0])
+    init_weights(net, init_type, gain=init_gain)
+    return net
+
+
+def define_G(input_nc, output_nc, ngf, netG, norm='batch', use_dropout=False, init_type='normal',
+             init_gain=0.02, gpu_ids=[]):
+    """models/networks.py:73-91."""
+    norm_layer = get_norm_layer(norm_type=norm)
+    if netG in ('resnet_9blocks', 'resnet_6blocks'):
+        net = ResnetGenerator(input_nc, output_nc, ngf, norm_layer=norm_layer, use_dropout=use_dropout,
+                              n_blocks=9 if netG == 'resnet_9blocks' else 6)
+    elif netG in ('unet_128', 'unet_256'):
+        net = UnetGenerator(input_nc, output_nc, 7 if netG == 'unet_128' else 8, ngf, norm_layer=norm_layer,
+                            use_dropout=use_dropout)
+    else:
+        raise NotImplementedError('Generator model name [%s] is not recognized' % netG)
+    return init_net(net, init_type, init_gain, gpu_ids)
+
+
+def define_D(input_nc, ndf, netD, n_layers_D=3, norm='batch', use_sigmoid=False, init_type='normal',
+             init_gain=0.02, gpu_ids=[]):
+    """models/networks.py:94-107 ('basic' ignores n_layers_D there, and so does this)."""
+    norm_layer = get_norm_layer(norm_type=norm)
+    if netD == 'basic':
+        net = NLayerDiscriminator(input_nc, ndf, n_layers=3, norm_layer=norm_layer, use_sigmoid=use_sigmoid)
+    elif netD == 'pixel':
+        net = PixelDiscriminator(input_nc, ndf, norm_layer=norm_layer, use_sigmoid=use_sigmoid)
+    else:
+        raise NotImplementedError('Discriminator model name [%s] is not recognized' % netD)
+    return init_net(net, init_type, init_gain, gpu_ids)
+
+
+def _bias_follows_instance_norm(norm_layer):
+    """use_bias rule of models/networks.py:152-155."""
+    target = norm_layer.func if type(norm_layer) == functools.partial else norm_layer
+    return target == nn.InstanceNorm2d
+
+
+# ------------------------------------------------------------------------------------------------
+# GANLoss (models/networks.py:119-138)
+# ------------------------------------------------------------------------------------------------
+class GANLoss(nn.Module):
+    """LSGAN (MSE) or vanilla (BCE) loss against a constant label. The label buffers stay in the
+    state_dict as in the reference; the loss itself is one fused kernel (forward value + gradient)."""
+
+    def __init__(self, use_lsgan=True, target_real_label=1.0, target_fake_label=0.0):
+        super(GANLoss, self).__init__()
+        self.register_buffer('real_label', torch.tensor(target_real_label))
+        self.register_buffer('fake_label', torch.tensor(target_fake_label))
+        self.use_lsgan = use_lsgan
+        self._labels = (float(target_real_label), float(target_fake_label))
+
+    def get_target_tensor(self, input, target_is_real):
+        return (self.real_label if target_is_real else self.fake_label).expand_as(input)
+
+    def __call__(self, input, target_is_real):
+        label = self._labels[0] if target_is_real else self._labels[1]
+        if self.use_lsgan:
+            return losses.mse_const(input, label)
+        return losses.bce_const(input, label)
+
+
+# ------------------------------------------------------------------------------------------------
+# networks
+# ------------------------------------------------------------------------------------------------
+class _FusedNet(nn.Module):
+    """Base of the drop-in networks: compiles `self._body()` once and runs it on the engine."""
+
+    def _body(self):
+        raise NotImplementedError
+
+    def _plan(self):
+        plan = self.__dict__.get('_cdb_plan')
+        if plan is None:
+            stages, final = engine.compile_chain(list(self._body().children()))
+            plan = engine.Plan(stages, final)
+            self.__dict__['_cdb_plan'] = plan
+        return plan
+
+    def forward(self, input):
+        return engine.run_network(self, self._plan(), input)
+
+
+class ResnetGenerator(_FusedNet):
+    """models/networks.py:145-191: c7s1-ngf, two stride-2 downsamplings, n_blocks residual blocks, two
+    transposed-conv upsamplings, c7s1-output_nc, tanh."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False, n_blocks=6,
+                 padding_type='reflect'):
+        assert (n_blocks >= 0)
+        super(ResnetGenerator, self).__init__()
+        self.input_nc, self.output_nc, self.ngf = input_nc, output_nc, ngf
+        use_bias = _bias_follows_instance_norm(norm_layer)
+        layers = [nn.ReflectionPad2d(3), nn.Conv2d(input_nc, ngf, kernel_size=7, padding=0, bias=use_bias),
+                  norm_layer(ngf), nn.ReLU(True)]
+        ch = ngf
+        for _ in range(2):  # downsampling
+            layers += [nn.Conv2d(ch, ch * 2, kernel_size=3, stride=2, padding=1, bias=use_bias),
+                       norm_layer(ch * 2), nn.ReLU(True)]
+            ch *= 2
+        layers += [ResnetBlock(ch, padding_type=padding_type, norm_layer=norm_layer, use_dropout=use_dropout,
+                               use_bias=use_bias) for _ in range(n_blocks)]
+        for _ in range(2):  # upsampling
+            layers += [nn.ConvTranspose2d(ch, ch // 2, kernel_size=3, stride=2, padding=1, output_padding=1,
+                                          bias=use_bias),
+                       norm_layer(ch // 2), nn.ReLU(True)]
+            ch //= 2
+        layers += [nn.ReflectionPad2d(3), nn.Conv2d(ngf, output_nc, kernel_size=7, padding=0), nn.Tanh()]
+        self.model = nn.Sequential(*layers)
+
+    def _body(self):
+        return self.model
+
+
+class ResnetBlock(nn.Module):
+    """models/networks.py:195-236: x + conv_block(x) with conv_block = pad-conv-norm-relu-[dropout]-pad-conv-norm."""
+
+    def __init__(self, dim, padding_type, norm_layer, use_dropout, use_bias):
+        super(ResnetBlock, self).__init__()
+        self.conv_block = self.build_conv_block(dim, padding_type, norm_layer, use_dropout, use_bias)
+
+    def build_conv_block(self, dim, padding_type, norm_layer, use_dropout, use_bias):
+        def padded_conv():
+            if padding_type == 'reflect':
+                return [nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=use_bias)]
+            if padding_type == 'replicate':
+                return [nn.ReplicationPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=use_bias)]
+            if padding_type == 'zero':
+                return [nn.Conv2d(dim, dim, kernel_size=3, padding=1, bias=use_bias)]
+            raise NotImplementedError('padding [%s] is not implemented' % padding_type)
+
+        block = padded_conv() + [norm_layer(dim), nn.ReLU(True)]
+        if use_dropout:
+            block += [nn.Dropout(0.5)]
+        block += padded_conv() + [norm_layer(dim)]
+        return nn.Sequential(*block)
+
+    def forward(self, x):
+        # only reached when a block is used outside a fused network
+        raise RuntimeError("ResnetBlock runs as part of a fused cdb200 network (ResnetGenerator.forward)")
+
+
+class NLayerDiscriminator(_FusedNet):
+    """models/networks.py:320-364: the 70x70 PatchGAN."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False):
+        super(NLayerDiscriminator, self).__init__()
+        use_bias = _bias_follows_instance_norm(norm_layer)
+        kw, padw = 4, 1
+        seq = [nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), nn.LeakyReLU(0.2, True)]
+        mult = 1
+        for n in range(1, n_layers + 1):
+            prev, mult = mult, min(2 ** n, 8)
+            stride = 2 if n < n_layers else 1
+            seq += [nn.Conv2d(ndf * prev, ndf * mult, kernel_size=kw, stride=stride, padding=padw, bias=use_bias),
+                    norm_layer(ndf * mult), nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(ndf * mult, 1, kernel_size=kw, stride=1, padding=padw)]
+        if use_sigmoid:
+            seq += [nn.Sigmoid()]
+        self.model = nn.Sequential(*seq)
+
+    def _body(self):
+        return self.model
+
+
+class PixelDiscriminator(_FusedNet):
+    """models/networks.py:367-389: three 1x1 convolutions."""
+
+    def __init__(self, input_nc, ndf=64, norm_layer=nn.BatchNorm2d, use_sigmoid=False):
+        super(PixelDiscriminator, self).__init__()
+        use_bias = _bias_follows_instance_norm(norm_layer)
+        net = [nn.Conv2d(input_nc, ndf, kernel_size=1, stride=1, padding=0), nn.LeakyReLU(0.2, True),
+               nn.Conv2d(ndf, ndf * 2, kernel_size=1, stride=1, padding=0, bias=use_bias), norm_layer(ndf * 2),
+               nn.LeakyReLU(0.2, True), nn.Conv2d(ndf * 2, 1, kernel_size=1, stride=1, padding=0, bias=use_bias)]
+        if use_sigmoid:
+            net.append(nn.Sigmoid())
+        self.net = nn.Sequential(*net)
+
+    def _body(self):
+        return self.net
+
+
+class UnetGenerator(nn.Module):
+    """models/networks.py:243-260. Module tree / state_dict identical; execution on the fused engine is
+    not wired yet for the skip-connection topology (raises, never falls back)."""
+
+    def __init__(self, input_nc, output_nc, num_downs, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super(UnetGenerator, self).__init__()
+        block = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=None, norm_layer=norm_layer,
+                                        innermost=True)
+        for _ in range(num_downs - 5):
+            block = UnetSkipConnectionBlock(ngf * 8, ngf * 8, input_nc=None, submodule=block,
+                                            norm_layer=norm_layer, use_dropout=use_dropout)
+        for outer, inner in ((ngf * 4, ngf * 8), (ngf * 2, ngf * 4), (ngf, ngf * 2)):
+            block = UnetSkipConnectionBlock(outer, inner, input_nc=None, submodule=block, norm_layer=norm_layer)
+        self.model = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=block, outermost=True,
+                                             norm_layer=norm_layer)
+
+    def forward(self, input):
+        raise NotImplementedError("cdb200: UnetGenerator execution is not implemented yet (no fallback path)")
+
+
+class UnetSkipConnectionBlock(nn.Module):
+    """models/networks.py:266-316 (parameter layout only, see UnetGenerator)."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc=None, submodule=None, outermost=False, innermost=False,
+                 norm_layer=nn.BatchNorm2d, use_dropout=False):
+        super(UnetSkipConnectionBlock, self).__init__()
+        self.outermost = outermost
+        self.innermost = innermost
+        use_bias = _bias_follows_instance_norm(norm_layer)
+        if input_nc is None:
+            input_nc = outer_nc
+        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+        downrelu, uprelu = nn.LeakyReLU(0.2, True), nn.ReLU(True)
+        downnorm, upnorm = norm_layer(inner_nc), norm_layer(outer_nc)
+        if outermost:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            model = [downconv, submodule, uprelu, upconv, nn.Tanh()]
+        elif innermost:
+            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            model = [downrelu, downconv, uprelu, upconv, upnorm]
+        else:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=use_bias)
+            model = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
+            if use_dropout:
+                model += [nn.Dropout(0.5)]
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):
+        raise NotImplementedError("cdb200: UnetSkipConnectionBlock runs only inside a fused UnetGenerator")

@@ -115,3 +115,133 @@ def conv2d_wgrad(g, x, dy, dw4, accumulate=False):
     check(L.cdb_conv2d_wgrad(C.byref(g), C.byref(xv), C.byref(dyv), C.c_void_p(dw4.data_ptr()), dw4.shape[0],
                              dw4.shape[1], 1 if accumulate else 0, C.c_void_p(ws.data_ptr()),
                              C.c_size_t(ws.numel()), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# norm / activation / layout / losses / optimiser / metrics
+# ---------------------------------------------------------------------------------------------
+from ._lib import CdbNormDesc, NORM_BATCH, NORM_INSTANCE, NORM_NONE  # noqa: E402
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def norm_desc(norm, act, slope, eps, channels, pad, stats=None, gamma=None, beta=None, running_mean=None,
+              running_var=None, use_running=False, update_running=False, momentum=0.1):
+    return CdbNormDesc(norm, act, slope, eps, channels, pad, 1 if use_running else 0, 1 if update_running else 0,
+                       momentum, 0, stats.data_ptr() if stats is not None else None,
+                       gamma.data_ptr() if gamma is not None else None,
+                       beta.data_ptr() if beta is not None else None,
+                       running_mean.data_ptr() if running_mean is not None else None,
+                       running_var.data_ptr() if running_var is not None else None)
+
+
+def channel_stats(y, c_real, per_image, stats):
+    _require_cuda(y, stats)
+    yv = act_view(y)
+    check(_lib.lib().cdb_channel_stats(C.byref(yv), c_real, 1 if per_image else 0, _p(stats), _stream()))
+
+
+def norm_act_fwd(desc, y, out, residual=None):
+    _require_cuda(y, out)
+    yv, ov = act_view(y), act_view(out)
+    rv = act_view(residual) if residual is not None else None
+    check(_lib.lib().cdb_norm_act_fwd(C.byref(desc), C.byref(yv), C.byref(rv) if rv is not None else None,
+                                      C.byref(ov), _stream()))
+
+
+def norm_act_bwd(desc, y, dy, dout=None, dskip=None, bstats=None, gsum=None):
+    _require_cuda(y, dy)
+    yv, dyv = act_view(y), act_view(dy)
+    dov = act_view(dout) if dout is not None else None
+    dsv = act_view(dskip) if dskip is not None else None
+    gv = act_view(gsum) if gsum is not None else None
+    check(_lib.lib().cdb_norm_act_bwd(C.byref(desc), C.byref(yv), C.byref(dov) if dov is not None else None,
+                                      C.byref(dsv) if dsv is not None else None, _p(bstats), C.byref(dyv),
+                                      C.byref(gv) if gv is not None else None, _stream()))
+
+
+def nchw_to_nhwc(src, out_interior, pad=0, act_out=None, act=ACT_NONE, slope=0.0):
+    """src fp32 [N,C,H,W] (any strides) -> bf16 NHWC interior view (+ reflect halo of pad)."""
+    _require_cuda(src, out_interior)
+    assert src.dtype == torch.float32 and src.dim() == 4
+    if act_out is not None:
+        assert act_out.dtype == torch.float32 and act_out.stride() == src.stride()
+    n, c, h, w = src.shape
+    ov = act_view(out_interior)
+    check(_lib.lib().cdb_nchw_to_nhwc(_p(src), n, c, h, w, C.c_int64(src.stride(0)), C.c_int64(src.stride(1)),
+                                      C.c_int64(src.stride(2)), C.c_int64(src.stride(3)), _p(act_out), act,
+                                      C.c_float(slope), C.byref(ov), pad, _stream()))
+
+
+def reflect_fold_nchw(src, dst, pad, accumulate=False):
+    _require_cuda(src, dst)
+    assert src.is_contiguous() and dst.is_contiguous() and src.dtype == torch.float32 and dst.dtype == torch.float32
+    n, c, h, w = dst.shape
+    check(_lib.lib().cdb_reflect_fold_nchw(_p(src), _p(dst), n * c, h, w, pad, 1 if accumulate else 0, _stream()))
+
+
+def bias_grad_nchw(g, act_out, act, slope, db):
+    _require_cuda(g, db)
+    assert g.is_contiguous() and g.dtype == torch.float32 and (act_out is None or act_out.is_contiguous())
+    n, c, h, w = g.shape
+    check(_lib.lib().cdb_bias_grad_nchw(_p(g), _p(act_out), act, C.c_float(slope), n, c, C.c_int64(h * w), _p(db),
+                                        _stream()))
+
+
+def loss_mse_const(x, target, weight, loss_acc, grad=None):
+    _require_cuda(x, loss_acc)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    check(_lib.lib().cdb_loss_mse_const(_p(x), C.c_int64(x.numel()), C.c_float(target), C.c_float(weight),
+                                        _p(loss_acc), _p(grad), _stream()))
+
+
+def loss_bce_const(x, target, weight, loss_acc, grad=None):
+    _require_cuda(x, loss_acc)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    check(_lib.lib().cdb_loss_bce_const(_p(x), C.c_int64(x.numel()), C.c_float(target), C.c_float(weight),
+                                        _p(loss_acc), _p(grad), _stream()))
+
+
+def loss_l1(a, b, weight, loss_acc, grad_a=None):
+    _require_cuda(a, b, loss_acc)
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+    assert a.shape == b.shape
+    check(_lib.lib().cdb_loss_l1(_p(a), _p(b), C.c_int64(a.numel()), C.c_float(weight), _p(loss_acc), _p(grad_a),
+                                 _stream()))
+
+
+def scale_by_scalar(a, scalar, out=None):
+    _require_cuda(a, scalar)
+    assert a.is_contiguous() and a.dtype == torch.float32 and scalar.dtype == torch.float32
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib().cdb_scale_by_scalar(_p(a), _p(scalar), _p(out), C.c_int64(a.numel()), _stream()))
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.is_contiguous() and t.dtype == torch.float32
+    check(_lib.lib().cdb_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), C.c_int64(param.numel()),
+                                   C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps), int(step),
+                                   _stream()))
+
+
+def depth_metrics(gt, pred):
+    """gt, pred: uint8 CUDA tensors [n_img, h, w] (contiguous). Returns float64 [n_img, 8]:
+    abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, masked-pixel count."""
+    _require_cuda(gt, pred)
+    assert gt.dtype == torch.uint8 and pred.dtype == torch.uint8 and gt.shape == pred.shape and gt.dim() == 3
+    assert gt.is_contiguous() and pred.is_contiguous()
+    n, h, w = gt.shape
+    L = _lib.lib()
+    need = L.cdb_depth_metrics_workspace(n)
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=gt.device)
+    off = (-ws.data_ptr()) % 256
+    out = torch.empty((n, 8), dtype=torch.float64, device=gt.device)
+    check(L.cdb_depth_metrics(_p(gt), _p(pred), n, h, w, _p(out), C.c_void_p(ws.data_ptr() + off),
+                              C.c_size_t(need), _stream()))
+    return out

@@ -117,6 +117,79 @@ int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, fl
                      int32_t d0, int32_t d1, int32_t accumulate, void* workspace, size_t ws_bytes,
                      cdbStream_t stream);
 
+/* ---- K4: statistics, norm + activation (+ residual, + reflect halo) and their backward --------
+ * Replace aten.native_batch_norm(_backward) (nn.InstanceNorm2d / nn.BatchNorm2d),
+ * aten.reflection_pad2d(_backward), relu_/leaky_relu_/threshold_backward and the residual add of
+ * models/networks.py:157-188,206-236,277-310,330-356. */
+typedef struct CdbNormDesc {
+  int32_t norm;           /* CDB_NORM_* */
+  int32_t act;            /* CDB_ACT_NONE / RELU / LEAKY (TANH, SIGMOID forward only) */
+  float slope, eps;
+  int32_t channels;       /* real channels; stored channels = round_up(channels, 8) */
+  int32_t pad;            /* reflect halo (pixels) written around / folded from the interior */
+  int32_t use_running;    /* eval-mode batch norm: normalise with running_mean / running_var */
+  int32_t update_running; /* training-mode batch norm: also update the running statistics */
+  float momentum;
+  int32_t reserved;
+  const float* stats;     /* [groups][channels][2] sums (sum, sum of squares); groups = n (instance) or 1 */
+  const float* gamma;     /* [channels] or NULL */
+  const float* beta;      /* [channels] or NULL */
+  float* running_mean;    /* [channels] or NULL */
+  float* running_var;     /* [channels] or NULL */
+} CdbNormDesc;
+
+/* stats[g][c][2] += (sum, sum of squares) of y over pixels; g = image if per_image else 0. */
+int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_image, float* stats, cdbStream_t stream);
+/* out(interior view, same n/h/w as y) = [residual +] act(norm(y)); the reflect halo of d->pad pixels
+ * around the interior is written too (the buffer behind `out` must extend that far). */
+int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const CdbAct* residual, const CdbAct* out,
+                     cdbStream_t stream);
+/* g = fold_reflect(dout, d->pad) + dskip;  dy = norm_bwd(act_bwd(g));  optionally gsum = g.
+ * bstats[groups][channels][2] (zeroed by the caller) receives (sum ga, sum ga*xhat): the gradients of
+ * beta and gamma for an affine norm, and the bias gradient for norm none. */
+int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const CdbAct* dout, const CdbAct* dskip,
+                     float* bstats, const CdbAct* dy, const CdbAct* gsum, cdbStream_t stream);
+
+/* ---- module boundary: NCHW fp32 <-> NHWC bf16 ------------------------------------------------ */
+/* src (fp32, strides in elements) -> interior view `out` (bf16 NHWC, out->c stored channels, extra
+ * channels 0) with a reflect halo of `pad`; with act_out != NULL the value is multiplied by the
+ * derivative of `act` evaluated at the activation output act_out (same layout as src). */
+int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t h, int32_t w, int64_t s_n, int64_t s_c,
+                     int64_t s_h, int64_t s_w, const float* act_out, int32_t act, float slope,
+                     const CdbAct* out, int32_t pad, cdbStream_t stream);
+/* dst[nc][h][w] (+)= reflect-fold of src[nc][h+2p][w+2p] (backward of nn.ReflectionPad2d on NCHW fp32). */
+int cdb_reflect_fold_nchw(const float* src, float* dst, int32_t nc, int32_t h, int32_t w, int32_t pad,
+                          int32_t accumulate, cdbStream_t stream);
+
+/* db[c] = sum over n,h,w of g * act'(act_out) on contiguous fp32 NCHW tensors (bias gradient of a final
+ * convolution + activation layer; act_out may be NULL for no activation). */
+int cdb_bias_grad_nchw(const float* g, const float* act_out, int32_t act, float slope, int32_t n, int32_t c,
+                       int64_t hw, float* db, cdbStream_t stream);
+
+/* ---- K6: fused losses (forward scalar + gradient in one pass) ----------------------------------
+ * GANLoss (models/networks.py:119-138: MSELoss / BCELoss against a constant label), L1Loss
+ * (models/cycle_gan_model.py:63-64,119-134; models/pix2pix_model.py:49,93).
+ * *loss_acc += weight * mean(l(x));  grad[i] = weight * l'(x[i]) / numel  (grad may be NULL). */
+int cdb_loss_mse_const(const float* x, int64_t numel, float target, float weight, float* loss_acc, float* grad,
+                       cdbStream_t stream);
+int cdb_loss_bce_const(const float* x, int64_t numel, float target, float weight, float* loss_acc, float* grad,
+                       cdbStream_t stream);
+int cdb_loss_l1(const float* a, const float* b, int64_t numel, float weight, float* loss_acc, float* grad_a,
+                cdbStream_t stream);
+int cdb_scale_by_scalar(const float* a, const float* scalar, float* out, int64_t numel, cdbStream_t stream);
+
+/* torch.optim.Adam step (no amsgrad / weight decay) on one fp32 tensor (models/cycle_gan_model.py:66-69). */
+int cdb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                  float beta1, float beta2, float eps, int32_t step, cdbStream_t stream);
+
+/* ---- K7: depth metrics ---------------------------------------------------------------------------
+ * new_multi/my_eval.py:7-31 (compute_errors) applied as in eval_metric :52-100 to n_img pairs of
+ * uint8 [h][w] images stored back to back. out8_per_img[i] = {abs_rel, sq_rel, rmse, rmse_log, a1,
+ * a2, a3, masked pixel count} in float64 (count 0 => NaNs; the reference raises there). */
+size_t cdb_depth_metrics_workspace(int32_t n_img);
+int cdb_depth_metrics(const uint8_t* gt, const uint8_t* pred, int32_t n_img, int32_t h, int32_t w,
+                      double* out8_per_img, void* workspace, size_t ws_bytes, cdbStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
