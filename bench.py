@@ -1,0 +1,344 @@
+"""Headline benchmark: the full CycleGAN training step of the reference
+(models/cycle_gan_model.py:138-160 — G_A/G_B ResNet-9 generators, D_A/D_B 70x70 PatchGANs, LSGAN + L1
+cycle + identity losses, ImagePool 50, Adam, 4 D updates per G update) at batch 8, 256x256, on the B200
+kernels of this repo.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One JSON line on stdout (rank 0). See DESIGN.md "measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "cyclegan_train_iters_per_s"
+UNIT = "iters/s (batch-8 training steps at 256x256, summed over ranks)"
+TFLOP_PER_SAMPLE = 2.1046   # 16.837 TFLOP per batch-8 step, counted on the reference modules
+G_FWD_GFLOP = 99.10         # per image
+DOMINANT = dict(n=8, c=256, hw=64, k=3)  # the 18 x 6 residual-block convolutions of a step
+
+
+def make_opt(device):
+    return argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
+                              n_layers_D=3, norm='instance', no_dropout=True, init_type='normal', init_gain=0.02,
+                              no_lsgan=False, pool_size=50, lr=2e-4, beta1=0.5, lambda_A=10.0, lambda_B=10.0,
+                              lambda_identity=0.5, isTrain=True, device=device, direction='AtoB')
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    hbm=p["hbm_gbs"], source="MEASURED_PEAKS.json")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def synthetic_batch(batch, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand((batch, 3, size, size), generator=g) * 2 - 1,
+            torch.rand((batch, 3, size, size), generator=g) * 2 - 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle restatement of the reference step on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_step_builder(size, batch):
+    from oracle import networks_oracle as O
+    from cycle_depth_estimation_b200 import networks as N
+    import contextlib
+    import io
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        nets = [N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+        nets += [N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+    oracle = O.CycleGANStepOracle(*[n.state_dict() for n in nets])
+    a, b = synthetic_batch(batch, size, 1234)
+    return lambda: oracle.step(a, b)
+
+
+def run_cpu_sample(steps, warmup, budget_s):
+    """Times `steps` CPU steps of a bounded sample (batch 1; 256x256, or 128x128 when a 256 step would
+    blow the budget). Returns (equivalent batch-8 256x256 iters/s, description, seconds per sample step)."""
+    import random
+    random.seed(1234)
+    torch.set_num_threads(os.cpu_count() or 1)
+    size = 256
+    step = cpu_reference_step_builder(size, 1)
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    used_warm = 1
+    if first * (steps + max(warmup - 1, 0)) > budget_s:
+        size = 128
+        step = cpu_reference_step_builder(size, 1)
+        used_warm = 0
+    for _ in range(max(warmup - used_warm, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    scale = 8.0 * (256.0 / size) ** 2   # conv nets: work is linear in batch and in pixels
+    return 1.0 / (dt * scale), "batch 1 at %dx%d per step, scaled by %.0fx to batch 8 at 256x256" % (size, size, scale), dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, sample, dt = run_cpu_sample(args.steps, args.warmup, budget_s=200.0)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "CycleGAN training step (reference restated on torch CPU), " + sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def time_dominant_kernel(peaks, iters=40):
+    """CUDA-event timing of the dominant kernel (igemm_kernel on the 3x3 256->256 residual-block
+    convolution at 64x64, batch 8: M=32768, N=256, K=2304) on torch's current stream."""
+    from cycle_depth_estimation_b200 import ops
+    d = DOMINANT
+    n, c, hw, k = d["n"], d["c"], d["hw"], d["k"]
+    x = torch.randn((n, hw + 2, hw + 2, c), device="cuda").to(torch.bfloat16)
+    w = (torch.randn((c, c, k, k), device="cuda") * 0.02).contiguous()
+    wp, rows_pad, kpad = ops.pack_conv_weight(w, True)
+    y = torch.empty((n, hw, hw, c), dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros((n, c, 2), dtype=torch.float32, device="cuda")
+    g = ops.geom(k, k)
+    ov = ops.out_view_nhwc(y, c)
+    for _ in range(5):
+        ops.conv2d_fwd(g, x, wp, rows_pad, kpad, ov, None, ops.ACT_NONE, 0.0, stats)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.conv2d_fwd(g, x, wp, rows_pad, kpad, ov, None, ops.ACT_NONE, 0.0, stats)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * n * hw * hw * c * c * k * k
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_burst"], "traffic": None, "kernel": "igemm_kernel",
+            "shape": "3x3 conv 256->256, 64x64, batch 8 (M=32768 N=256 K=2304), fused IN statistics",
+            "us_per_launch": ms * 1e3, "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
+
+
+def b200_arm(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from cycle_depth_estimation_b200 import _lib
+    from cycle_depth_estimation_b200.cycle_gan_model import CycleGANModel
+    import contextlib
+    import io
+    import random
+
+    lib = _lib.lib()
+    peaks = load_peaks()
+    batch, size = args.batch, args.size
+    torch.manual_seed(0)            # identical initial weights on every rank
+    random.seed(1234)               # identical ImagePool stream on every rank
+    model = CycleGANModel()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model.initialize(make_opt("cuda"))
+    host_a, host_b = synthetic_batch(batch, size, 1234 + rank)
+    host_a, host_b = host_a.pin_memory(), host_b.pin_memory()
+    dev = {"img_source": host_a.cuda(), "img_target": host_b.cuda()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        model.set_input(dev)
+        model.optimize_parameters("train")
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.cdb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model.set_input(dev)
+        model.optimize_parameters("train")
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.cdb_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * 1e3 / ms_step * (batch / 8.0)
+
+    # ---- end to end: pinned host inputs every step, losses read back every step
+    host = {"img_source": host_a, "img_target": host_b}
+    model.set_input(host)
+    model.optimize_parameters("train")
+    model.get_current_losses()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        model.set_input(host)
+        model.optimize_parameters("train")
+        losses = model.get_current_losses()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {"value": world * 1e3 / ms_e2e * (batch / 8.0), "unit": UNIT,
+           "h2d_bytes_per_step": int(host_a.numel() * 4 * 2), "d2h_bytes_per_step": 4 * len(losses),
+           "ms_per_step": ms_e2e}
+    abort = lib.cdb_device_abort_flag()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- generator inference (BASELINE configs[0]) and the dominant kernel, rank 0 only
+    with torch.no_grad():
+        x1 = dev["img_source"][:1]
+        for _ in range(3):
+            model.netG_A(x1)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            model.netG_A(x1)
+        e1.record()
+        torch.cuda.synchronize()
+        g_ms = e0.elapsed_time(e1) / 20
+    roof = time_dominant_kernel(peaks)
+    step_tflops = TFLOP_PER_SAMPLE * batch / (ms_step * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample, _ = run_cpu_sample(steps=2, warmup=1, budget_s=40.0)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": "CycleGAN training step: G_A/G_B resnet_9blocks + D_A/D_B 70x70 PatchGAN, LSGAN + L1 "
+                        "cycle/identity, ImagePool 50, Adam, 4 D updates per G update; batch %d per GPU at %dx%d "
+                        "(BASELINE configs[1])" % (batch, size, size),
+            "per_gpu_batch": batch, "image": size, "parallelism": "dp%d" % world,
+            "l2": "working set per step (saved activations of 6 generator + 18 discriminator passes, > 5 GB) "
+                  "exceeds the 126 MB L2; no explicit flush",
+            "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * batch,
+            "step_tflops_per_gpu": step_tflops,
+            "step_frac_of_sustained_bf16_peak": step_tflops / peaks["bf16_sustained"],
+            "g_forward_img_per_s_batch1": 1e3 / g_ms,
+            "g_forward_tflops_batch1": G_FWD_GFLOP / g_ms,
+            "device_abort_flag": abort,
+        },
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,7 @@ def lib():
     L.cdb_version.restype = C.c_int
     L.cdb_last_error.restype = C.c_char_p
     L.cdb_device_abort_flag.restype = C.c_int
+    L.cdb_launch_count.restype = C.c_longlong
     L.cdb_conv2d_wgrad_workspace.restype = C.c_size_t
     L.cdb_depth_metrics_workspace.restype = C.c_size_t
     _lib = L

@@ -1,4 +1,5 @@
 // Library plumbing: version, error strings, the device abort flag and tensor-map encoding.
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -16,6 +17,9 @@ int fail(int status, const char* fmt, ...) {
   va_end(ap);
   return status;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 __device__ int g_device_abort = 0;
 
@@ -94,6 +98,8 @@ int sm_count() {
 extern "C" {
 
 int cdb_version(void) { return 100; }
+
+long long cdb_launch_count(void) { return cdb::g_launches.load(std::memory_order_relaxed); }
 
 const char* cdb_last_error(void) { return cdb::error_buffer(); }
 

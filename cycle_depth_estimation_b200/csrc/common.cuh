@@ -27,6 +27,13 @@ int fail(int status, const char* fmt, ...);
     }                                                                                       \
   } while (0)
 
+// After every kernel launch: count it (cdb_launch_count) and surface launch errors.
+#define CDB_LAUNCH_OK()                        \
+  do {                                         \
+    ::cdb::note_launch();                      \
+    CDB_CUDA_OK(cudaGetLastError());           \
+  } while (0)
+
 #define CDB_REQUIRE(cond, status, ...)                  \
   do {                                                  \
     if (!(cond)) return ::cdb::fail(status, __VA_ARGS__); \
@@ -41,6 +48,7 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, co
               const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
+void note_launch();
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -347,7 +347,7 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
   if (grid < 1) return CDB_OK;
   prm.abort_flag = device_abort_flag_ptr();
   igemm_kernel<<<grid, 256, smem, stream>>>(maps, prm);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 

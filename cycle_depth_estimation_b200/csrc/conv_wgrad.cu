@@ -351,7 +351,7 @@ extern "C" int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_weight_kernel<<<blocks, 256, 0, stream>>>(w4, static_cast<__nv_bfloat16*>(out), d0, d1, r, s,
                                                  rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad, n_taps);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -473,7 +473,7 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   const int items = pl.n_taps * pl.m_tiles * pl.n_tiles * pl.splits;
   int grid = items < sm_count() ? items : sm_count();
   wgrad_kernel<<<grid, 256, smem, stream>>>(maps, prm);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
 
   const int64_t total = (int64_t)d0 * d1 * g->r * g->s;
   int blocks = (int)((total + 255) / 256);
@@ -482,6 +482,6 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   wgrad_finalize_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), dw4, d0, d1, g->r,
                                                     g->s, pl.n_taps, pl.splits, pl.mpad, pl.npad, pl.m_is_s,
                                                     g->rowpack, accumulate);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }

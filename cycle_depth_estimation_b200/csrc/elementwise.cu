@@ -236,7 +236,7 @@ extern "C" int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t 
   p.act = act;
   p.slope = slope;
   nchw_to_nhwc_kernel<<<grid_for((int64_t)n * h * w, 1), 256, 0, stream>>>(p);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -245,7 +245,7 @@ extern "C" int cdb_reflect_fold_nchw(const float* src, float* dst, int32_t nc, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(src && dst && pad >= 0 && pad < h && pad < w, CDB_ERR_BAD_DESC, "reflect_fold_nchw: bad argument");
   reflect_fold_nchw_kernel<<<grid_for((int64_t)nc * h * w, 1), 256, 0, stream>>>(src, dst, nc, h, w, pad, accumulate);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -254,7 +254,7 @@ extern "C" int cdb_bias_grad_nchw(const float* g, const float* act_out, int32_t 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(g && db && n > 0 && c > 0 && hw > 0, CDB_ERR_BAD_DESC, "bias_grad_nchw: bad argument");
   bias_grad_nchw_kernel<<<c, 256, 0, stream>>>(g, act_out, act, slope, n, c, hw, db);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -263,7 +263,7 @@ extern "C" int cdb_loss_mse_const(const float* x, int64_t numel, float target, f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(x && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_mse_const: bad argument");
   loss_kernel<kLossMse><<<grid_for(numel), 256, 0, stream>>>(x, nullptr, target, numel, weight, loss_acc, grad);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -272,7 +272,7 @@ extern "C" int cdb_loss_bce_const(const float* x, int64_t numel, float target, f
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(x && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_bce_const: bad argument");
   loss_kernel<kLossBce><<<grid_for(numel), 256, 0, stream>>>(x, nullptr, target, numel, weight, loss_acc, grad);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -281,7 +281,7 @@ extern "C" int cdb_loss_l1(const float* a, const float* b, int64_t numel, float 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(a && b && loss_acc && numel > 0, CDB_ERR_BAD_DESC, "loss_l1: bad argument");
   loss_kernel<kLossL1><<<grid_for(numel), 256, 0, stream>>>(a, b, 0.f, numel, weight, loss_acc, grad_a);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -290,7 +290,7 @@ extern "C" int cdb_scale_by_scalar(const float* a, const float* scalar, float* o
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(a && scalar && out && numel > 0, CDB_ERR_BAD_DESC, "scale_by_scalar: bad argument");
   scale_by_scalar_kernel<<<grid_for(numel), 256, 0, stream>>>(a, scalar, out, numel);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -302,6 +302,6 @@ extern "C" int cdb_adam_step(float* param, const float* grad, float* exp_avg, fl
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(numel), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
                                                    (float)bc1, (float)sqrt(bc2));
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }

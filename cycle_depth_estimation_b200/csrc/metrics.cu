@@ -340,15 +340,15 @@ extern "C" int cdb_depth_metrics(const uint8_t* gt, const uint8_t* pred, int32_t
   double* partial = reinterpret_cast<double*>(ws + a + b);
   const int64_t pixels = (int64_t)h * w;
   metrics_init_kernel<<<ceil_div(n_img, 256), 256, 0, stream>>>(info, n_img);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   dim3 grid(kMetricChunks, n_img);
   metrics_minmax_kernel<<<grid, 256, 0, stream>>>(gt, pred, pixels, info);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   metrics_lut_kernel<<<n_img, 256, 0, stream>>>(info, lut);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   metrics_accum_kernel<<<grid, 256, 0, stream>>>(gt, pred, pixels, lut, partial);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   metrics_finalize_kernel<<<ceil_div(n_img, 128), 128, 0, stream>>>(partial, kMetricChunks, n_img, out8_per_img);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -381,7 +381,7 @@ extern "C" int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_im
   const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
   dim3 grid(chunks, y->n, m.cv_tiles);
   channel_stats_kernel<<<grid, 256, 0, stream>>>(view_of(y), y->h, y->w, c_real, m.vt, per_image, stats);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }
 
@@ -442,12 +442,12 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
   dim3 grid(chunks, y->n, m.cv_tiles);
   norm_act_fwd_kernel<<<grid, 256, 0, stream>>>(p);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   if (d->norm == CDB_NORM_BATCH && !d->use_running && d->update_running && d->running_mean && d->running_var) {
     const float count = (float)((int64_t)y->n * y->h * y->w);
     bn_running_kernel<<<ceil_div(d->channels, 128), 128, 0, stream>>>(d->stats, d->channels, count, d->momentum,
                                                                       d->running_mean, d->running_var);
-    CDB_CUDA_OK(cudaGetLastError());
+    CDB_LAUNCH_OK();
   }
   return CDB_OK;
 }
@@ -504,9 +504,9 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   if (need_reduce || (bstats && d->norm == CDB_NORM_NONE)) {
     // norm none + bstats: the reduction yields the bias gradient (sum of ga) in component 0
     norm_act_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
-    CDB_CUDA_OK(cudaGetLastError());
+    CDB_LAUNCH_OK();
   }
   norm_act_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
-  CDB_CUDA_OK(cudaGetLastError());
+  CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -223,5 +223,6 @@ class CycleGANModel:
     def get_current_losses(self):
         out = OrderedDict()
         for name in self.loss_names:
-            out[name] = float(getattr(self, 'loss_' + name))
+            v = getattr(self, 'loss_' + name)
+            out[name] = float(v.detach()) if torch.is_tensor(v) else float(v)
         return out

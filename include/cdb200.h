@@ -89,6 +89,8 @@ typedef struct CdbEpilogue {
 /* ---- library ------------------------------------------------------------------------------ */
 int cdb_version(void);
 const char* cdb_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
+long long cdb_launch_count(void);
 /* Reads-and-clears the device-side abort flag raised when a kernel's bounded mbarrier wait timed out. */
 int cdb_device_abort_flag(void);
 
