@@ -106,30 +106,30 @@ __global__ void reflect_fold_nchw_kernel(const float* __restrict__ src, float* _
   }
 }
 
-// db[c] = sum_{n,h,w} g[n,c,h,w] * act'(out[n,c,h,w])  — bias gradient of a final conv (+ activation)
-// layer taken from the fp32 NCHW tensors, one block per channel.
+// db[c] += sum_{n,h,w} g[n,c,h,w] * act'(out[n,c,h,w])  — bias gradient of a final conv (+ activation)
+// layer taken from the fp32 NCHW tensors; grid (chunks, n*c), one atomicAdd per block (db zeroed first).
 __global__ void __launch_bounds__(256)
-bias_grad_nchw_kernel(const float* __restrict__ g, const float* __restrict__ act_out, int act, float slope, int N,
-                      int C, int64_t HW, float* __restrict__ db) {
+bias_grad_nchw_kernel(const float* __restrict__ g, const float* __restrict__ act_out, int act, float slope, int C,
+                      int64_t HW, float* __restrict__ db) {
   __shared__ float red[32];
-  const int c = blockIdx.x;
+  const int nc = blockIdx.y;
+  const int c = nc % C;
+  const int64_t base = static_cast<int64_t>(nc) * HW;
   float acc = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const int64_t base = (static_cast<int64_t>(n) * C + c) * HW;
-    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
-      float v = g[base + i];
-      if (act_out != nullptr) {
-        const float o = act_out[base + i];
-        if (act == CDB_ACT_TANH) v *= (1.f - o * o);
-        else if (act == CDB_ACT_SIGMOID) v *= o * (1.f - o);
-        else if (act == CDB_ACT_LEAKY) v *= (o > 0.f ? 1.f : slope);
-        else if (act == CDB_ACT_RELU) v *= (o > 0.f ? 1.f : 0.f);
-      }
-      acc += v;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < HW;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = g[base + i];
+    if (act_out != nullptr) {
+      const float o = act_out[base + i];
+      if (act == CDB_ACT_TANH) v *= (1.f - o * o);
+      else if (act == CDB_ACT_SIGMOID) v *= o * (1.f - o);
+      else if (act == CDB_ACT_LEAKY) v *= (o > 0.f ? 1.f : slope);
+      else if (act == CDB_ACT_RELU) v *= (o > 0.f ? 1.f : 0.f);
     }
+    acc += v;
   }
   const float r = block_reduce_sum(acc, red);
-  if (threadIdx.x == 0) db[c] = r;
+  if (threadIdx.x == 0) atomicAdd(db + c, r);
 }
 
 // ---- losses: loss_acc += weight * mean(f(x)); grad = weight * f'(x) / numel -----------------------
@@ -253,7 +253,10 @@ extern "C" int cdb_bias_grad_nchw(const float* g, const float* act_out, int32_t 
                                   int32_t c, int64_t hw, float* db, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(g && db && n > 0 && c > 0 && hw > 0, CDB_ERR_BAD_DESC, "bias_grad_nchw: bad argument");
-  bias_grad_nchw_kernel<<<c, 256, 0, stream>>>(g, act_out, act, slope, n, c, hw, db);
+  CDB_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * c, stream));
+  int chunks = (int)((hw + 256 * 8 - 1) / (256 * 8));
+  if (chunks > 64) chunks = 64;
+  bias_grad_nchw_kernel<<<dim3(chunks, n * c), 256, 0, stream>>>(g, act_out, act, slope, c, hw, db);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -1,0 +1,94 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/cdb200.h declares, the
+drop-in modules keep the reference's constructor / state_dict contract, and the product refuses to run
+without CUDA (no silent fallback)."""
+import argparse
+import re
+
+import pytest
+import torch
+
+from helpers import quiet
+
+
+def test_library_exports_every_declared_symbol():
+    from cycle_depth_estimation_b200 import _lib
+    L = _lib.lib()
+    syms = _lib.exported_symbols_from_header()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), s
+    assert L.cdb_version() >= 100
+    assert L.cdb_launch_count() == 0
+
+
+def test_error_convention_without_gpu():
+    """Bad descriptors are rejected on the host (negative status + message) before any CUDA call."""
+    import ctypes as C
+    from cycle_depth_estimation_b200 import _lib
+    L = _lib.lib()
+    rc = L.cdb_conv2d_fwd(None, None, None, 0, 0, None, None, None)
+    assert rc == -1 and b"null" in L.cdb_last_error()
+    g = _lib.CdbConvGeom(3, 3, 3, 0, 0, 1, 0, 0)  # stride 3 is unsupported
+    x = _lib.CdbAct(16, 1, 8, 8, 8, 512, 64, 8, _lib.BF16, 0)
+    y = _lib.CdbOut(16, 1, 2, 2, 8, 8, _lib.BF16, 32, 16, 8, 1)
+    rc = L.cdb_conv2d_fwd(C.byref(g), C.byref(x), C.c_void_p(16), 16, 64, C.byref(y), None, None)
+    assert rc == -2
+    with pytest.raises(NotImplementedError):
+        _lib.check(rc)
+    x.sw = 4  # misaligned pixel stride
+    g.stride = 1
+    assert L.cdb_conv2d_fwd(C.byref(g), C.byref(x), C.c_void_p(16), 16, 64, C.byref(y), None, None) == -3
+
+
+def test_ops_refuse_cpu_tensors():
+    from cycle_depth_estimation_b200 import losses, networks as N
+    with quiet():
+        d = N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cpu'])
+    with pytest.raises(RuntimeError):
+        d(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        losses.l1(torch.zeros(4), torch.zeros(4))
+
+
+def test_constructor_contract_and_state_dict_keys():
+    from cycle_depth_estimation_b200 import networks as N
+    with quiet():
+        g = N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cpu'])
+        d = N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cpu'])
+        u = N.define_G(3, 3, 64, 'unet_256', 'batch', True, 'normal', 0.02, ['cpu'])
+    assert len(g.state_dict()) == 48 and sum(p.numel() for p in g.parameters()) == 11378179
+    assert list(d.state_dict())[:2] == ['model.0.weight', 'model.0.bias']
+    assert sum(p.numel() for p in d.parameters()) == 2764737
+    assert sum(p.numel() for p in u.parameters()) == 54413955
+    assert any(k.endswith('num_batches_tracked') for k in u.state_dict())
+    # DataParallel-prefixed checkpoints load after stripping the prefix, strictly
+    g.load_state_dict({k: v for k, v in (("module." + k, v) for k, v in g.state_dict().items())
+                       for k in [k[len("module."):]]}, strict=True)
+    with pytest.raises(NotImplementedError):
+        N.define_G(3, 3, 64, '3blocks', 'instance', False, 'normal', 0.02, ['cpu'])
+    with pytest.raises(IndexError):
+        with quiet():
+            N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, [])
+    sched = N.get_scheduler(torch.optim.SGD(d.parameters(), lr=1.0), argparse.Namespace(lr_policy='lambda'))
+    assert sched.get_last_lr() == [1.0]
+    assert isinstance(N.get_scheduler(None, argparse.Namespace(lr_policy='nope')), NotImplementedError)
+
+
+def test_engine_plan_of_the_resnet_generator():
+    from cycle_depth_estimation_b200 import engine, networks as N
+    with quiet():
+        g = N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cpu'])
+    plan = g._plan()
+    assert len(plan.stages) == 24
+    assert [s.reflect for s in plan.stages[:4]] == [3, 0, 0, 1] and plan.stages[-1].reflect == 3
+    assert [s.res is not None for s in plan.stages[3:21]] == [False, True] * 9
+    assert [s.transposed for s in plan.stages[21:23]] == [True, True]
+    assert plan.halo[0] == 3 and plan.halo[3] == 1 and plan.halo[21] == 0 and plan.halo[23] == 3
+    assert len(plan.params) == 48
+
+
+def test_gan_loss_buffers_in_state_dict():
+    from cycle_depth_estimation_b200 import networks as N
+    crit = N.GANLoss(use_lsgan=True)
+    assert set(crit.state_dict()) == {'real_label', 'fake_label'}
+    assert crit.get_target_tensor(torch.zeros(2, 1, 3, 3), True).shape == (2, 1, 3, 3)
