@@ -25,7 +25,8 @@ class CdbOut(C.Structure):
 
 class CdbConvGeom(C.Structure):
     _fields_ = [("r", C.c_int32), ("s", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32),
-                ("pad_w", C.c_int32), ("dil", C.c_int32), ("transposed", C.c_int32), ("rowpack", C.c_int32)]
+                ("pad_w", C.c_int32), ("dil", C.c_int32), ("transposed", C.c_int32), ("rowpack", C.c_int32),
+                ("flip", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CdbEpilogue(C.Structure):

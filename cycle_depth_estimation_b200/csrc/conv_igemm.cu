@@ -360,6 +360,14 @@ static int check_act(const CdbAct* x, const char* name) {
   return CDB_OK;
 }
 
+int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, int w_rows_pad, int w_kpad,
+                     const CdbOut* y, const CdbEpilogue* ep, int flip, int use_base_offset, cudaStream_t stream);
+
+static int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 }  // namespace cdb
 
 using namespace cdb;
@@ -399,6 +407,16 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   prm.k_chunks = w_kpad / 64;
   prm.dom_n = y->n;
 
+  CDB_REQUIRE(!(g->flip && (g->transposed || g->rowpack)), CDB_ERR_UNSUPPORTED, "conv2d_fwd: flip with transposed/rowpack");
+  // Stride-1 convolutions over a contiguous buffer with materialised padding take the flat kernel
+  // (A rows shared by the S taps of a filter row, two accumulators per weight tile).
+  if (!g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw == x->c &&
+      x->sh == (int64_t)x->w * x->c && x->sn == (int64_t)x->h * x->w * x->c &&
+      y->h == x->h - (g->r - 1) * g->dil && y->w == x->w - (g->s - 1) * g->dil && y->n == x->n &&
+      (g->s - 1) * g->dil <= 64 && (int64_t)y->h * x->w >= 256 && !env_flag("CDB_DISABLE_FLAT", 0)) {
+    return launch_flat_conv(g, x, wpacked, w_rows_pad, w_kpad, y, ep, g->flip, env_flag("CDB_FLAT_BASE_OFFSET", 0),
+                            stream);
+  }
   if (!g->transposed) {
     // ---------------- direct convolution: parity views of the input for stride 2
     SrcView views[4];
@@ -452,7 +470,7 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
           t.map = (int16_t)(a * st + b);
           t.dh = (int16_t)((ih - a) / st);
           t.dw = (int16_t)((iw - b) / st);
-          t.wk = (r * g->s + s) * w_kpad;
+          t.wk = (g->flip ? (g->r * g->s - 1 - (r * g->s + s)) : (r * g->s + s)) * w_kpad;
         }
     }
     prm.dom_h = y->h;

@@ -61,6 +61,23 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   }
 }
 
+// Same, for warps that wait for a long time (epilogue warps waiting for a whole main loop): back off
+// with nanosleep so the spinning warps do not take issue slots from the producer / MMA threads.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                                  unsigned sleep_ns) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (sleep_ns) __nanosleep(sleep_ns);
+    if (mbar_try_wait(bar, parity)) return true;
+    if (*abort_flag) return false;
+    if (clock64() - t0 > CDB_WAIT_TIMEOUT_CYCLES) {
+      *abort_flag = 1;
+      return false;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared, completion on an mbarrier)
 // ----------------------------------------------------------------------------------------------
@@ -160,6 +177,38 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 consecutive columns per thread.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      " {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      "  %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// TMA tiled store (shared -> global) as a bulk async group.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -179,6 +228,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2;
+// Same, for a start address that is not aligned to the 1024-byte swizzle pattern: the descriptor's
+// "matrix base offset" (bits [49,52)) carries (start >> 7) & 7.
+__device__ __forceinline__ uint64_t make_smem_desc_unaligned(uint32_t saddr, uint32_t lbo_bytes,
+                                                             uint32_t sbo_bytes, uint32_t layout,
+                                                             uint32_t use_base_offset) {
+  uint64_t d = make_smem_desc(saddr, lbo_bytes, sbo_bytes, layout);
+  if (use_base_offset) d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;
+  return d;
+}
 
 // Instruction descriptor for kind::f16 / kind::tf32, dense, f32 accumulate.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32;  major: 0 = K-major, 1 = MN-major.

@@ -55,8 +55,17 @@ def out_view_nchw(t):
                   t.stride(0), t.stride(2), t.stride(3), t.stride(1))
 
 
-def geom(r, s, stride=1, pad_h=0, pad_w=0, dil=1, transposed=False, rowpack=0):
-    return CdbConvGeom(r, s, stride, pad_h, pad_w, dil, 1 if transposed else 0, rowpack)
+def alloc_flat_output(n, ho, wo, wp, cstore, device, zero=False):
+    """Output buffer for a stride-1 convolution read from a contiguous [n, hp, wp, c] input: rows follow
+    the INPUT pitch wp and each image owns a multiple of 256 rows, which lets the flat kernel store whole
+    tiles with TMA (cdb_conv2d_fwd fast output path). Returns the NHWC view [n, ho, wo, cstore]."""
+    rows = (ho * wp + 255) // 256 * 256
+    base = (torch.zeros if zero else torch.empty)((n, rows, cstore), dtype=torch.bfloat16, device=device)
+    return base.as_strided((n, ho, wo, cstore), (rows * cstore, wp * cstore, cstore, 1))
+
+
+def geom(r, s, stride=1, pad_h=0, pad_w=0, dil=1, transposed=False, rowpack=0, flip=False):
+    return CdbConvGeom(r, s, stride, pad_h, pad_w, dil, 1 if transposed else 0, rowpack, 1 if flip else 0, 0)
 
 
 def packed_weight_shape(d0, d1, r, s, rows_are_dim0, rowpack=0):

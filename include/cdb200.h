@@ -76,6 +76,10 @@ typedef struct CdbConvGeom {
   int32_t dil;
   int32_t transposed;
   int32_t rowpack;
+  int32_t flip;    /* direct convolutions only: use the packed taps in reverse order, W[R-1-r][S-1-s]; the
+                    * data gradient of a stride-1 convolution is then a direct convolution of the
+                    * zero-haloed dy (halo (R-1)*dil) with flip = 1 and the dgrad packing of W */
+  int32_t reserved;
 } CdbConvGeom;
 
 typedef struct CdbEpilogue {

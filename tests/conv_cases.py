@@ -34,7 +34,7 @@ def nhwc(x_nchw, cstore=None):
 
 
 def conv_fwd_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=False, out_pad=0,
-                  out_mode="nhwc", bias=False, act=ops.ACT_NONE, stats=False, seed=0):
+                  out_mode="nhwc", bias=False, act=ops.ACT_NONE, stats=False, seed=0, flip=False, pitched=False):
     gen = torch.Generator(device="cuda").manual_seed(seed)
     x = _rand((n, cin, h, w), gen)
     if transposed:
@@ -42,7 +42,7 @@ def conv_fwd_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=Fals
         ref = F.conv_transpose2d(x.float(), w4.float(), None, stride, pad, out_pad, 1, dil)
     else:
         w4 = _rand((cout, cin, k, k), gen, 0.05)
-        ref = F.conv2d(x.float(), w4.float(), None, stride, pad, dil)
+        ref = F.conv2d(x.float(), w4.float().flip(2, 3) if flip else w4.float(), None, stride, pad, dil)
     b = None
     if bias:
         b = torch.randn(cout, generator=gen, device="cuda")
@@ -56,11 +56,15 @@ def conv_fwd_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=Fals
     p, q = ref.shape[2], ref.shape[3]
     xs = nhwc(x)
     wp, rows_pad, kpad = ops.pack_conv_weight(w4.float().contiguous(), rows_are_dim0=not transposed)
-    g = ops.geom(k, k, stride, pad, pad, dil, transposed)
+    g = ops.geom(k, k, stride, pad, pad, dil, transposed, 0, flip)
     st = torch.zeros((n, cout, 2), dtype=torch.float32, device="cuda") if stats else None
     if out_mode == "nhwc":
         cs = ops.round_up(cout, 8)
-        y = torch.full((n, p, q, cs), float("nan"), dtype=torch.bfloat16, device="cuda")
+        if pitched:
+            y = ops.alloc_flat_output(n, p, q, w, cs, "cuda")
+            y.fill_(float("nan"))
+        else:
+            y = torch.full((n, p, q, cs), float("nan"), dtype=torch.bfloat16, device="cuda")
         ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nhwc(y, cout), b, act, 0.2, st)
         got = y[..., :cout].permute(0, 3, 1, 2).float()
         tol = TOL_BF16
@@ -154,6 +158,21 @@ FWD_CASES = {
     "convT4x4_s2": dict(n=2, cin=128, cout=64, h=8, w=8, k=4, stride=2, pad=1, transposed=True),
     "convT4x4_s2_from1x1": dict(n=4, cin=512, cout=512, h=1, w=1, k=4, stride=2, pad=1, transposed=True),
     "dgrad_like_3x3_pad2": dict(n=1, cin=256, cout=256, h=64, w=64, k=3, pad=2),
+    # flat kernel (stride 1, materialised padding, contiguous input)
+    "flat_r256_stats": dict(n=3, cin=256, cout=256, h=66, w=66, k=3, stats=True),
+    "flat_r256_flip": dict(n=2, cin=256, cout=256, h=68, w=68, k=3, flip=True),
+    "flat_3x3_c64_n128_dil2": dict(n=2, cin=64, cout=128, h=44, w=52, k=3, dil=2),
+    "flat_7x7_c64_cout3_wide": dict(n=2, cin=64, cout=3, h=134, w=262, k=7, bias=True, act=ops.ACT_TANH, out_mode="nchw"),
+    "flat_4x4_c512_cout1": dict(n=2, cin=512, cout=1, h=33, w=33, k=4, bias=True, out_mode="nchw"),
+    "flat_1x1_c128_n320": dict(n=1, cin=128, cout=320, h=24, w=80, k=1),
+    "generic_flip_s1_pad1": dict(n=1, cin=64, cout=64, h=20, w=20, k=3, pad=1, flip=True),
+    # flat kernel, TMA-store output path (pitched output buffer)
+    "flatfast_r256_stats": dict(n=3, cin=256, cout=256, h=66, w=66, k=3, stats=True, pitched=True),
+    "flatfast_r256_flip": dict(n=2, cin=256, cout=256, h=68, w=68, k=3, flip=True, pitched=True),
+    "flatfast_c128_bias_leaky": dict(n=2, cin=128, cout=128, h=40, w=50, k=3, bias=True, act=ops.ACT_LEAKY, pitched=True),
+    "flatfast_cout72_stats": dict(n=2, cin=64, cout=72, h=30, w=34, k=3, stats=True, pitched=True),
+    "flatfast_cout320": dict(n=1, cin=128, cout=320, h=26, w=82, k=3, pitched=True),
+    "flatfast_4x4_c256_512": dict(n=2, cin=256, cout=512, h=34, w=34, k=4, stats=True, pitched=True),
 }
 
 ROWPACK_CASES = {
