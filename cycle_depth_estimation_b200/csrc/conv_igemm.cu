@@ -40,6 +40,7 @@ struct IgemmParams {
   float slope;
   int32_t stages;
   int32_t stats_on;
+  int32_t fast_out;
   const float* bias;
   void* out;
   int64_t o_sn, o_sh, o_sw, o_sc;
@@ -51,6 +52,7 @@ struct IgemmParams {
 struct IgemmMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap out;  // fast output path: bf16 NHWC 4-D map, box {64, bw, bh, bn} = 32 rows, 128B swizzle
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -185,6 +187,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int r_w = row % p.tile_w;
     const int r_h = (row / p.tile_w) % p.tile_h;
     const int r_n = row / (p.tile_w * p.tile_h);
+    // the 32 rows of this warp as a sub-box of the tile (all tile dimensions are powers of two)
+    const int m0 = ew * 32;
+    const int w_off = m0 % p.tile_w, h_off = (m0 / p.tile_w) % p.tile_h, n_off = m0 / (p.tile_w * p.tile_h);
+    const bool one_image = p.tile_w * p.tile_h >= 32;  // all 32 rows of a warp belong to one image
+    const uint32_t stage_addr = smem_base + p.stages * stage_bytes + ew * 4096;
+    float* slab = reinterpret_cast<float*>(smem_raw + (stage_addr - smem_u32(smem_raw)));
+    const bool has_bias = p.bias != nullptr;
+    const int act = p.act;
+    const float slope = p.slope;
+    const int cout = p.cout, cstore = p.cstore;
+    const bool stats_on = p.stats_on != 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int buf = local & 1;
@@ -200,80 +213,132 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const int q = tw * p.tile_w + r_w, pp = th * p.tile_h + r_h, img = tn * p.tile_n + r_n;
       const bool valid = (q < p.dom_w) && (pp < p.dom_h) && (img < p.dom_n);
       const int n0 = n_tile * p.bn;
-      const int64_t obase = img * p.o_sn + pp * p.o_sh + q * p.o_sw;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(buf) * 256u;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        if (n0 + c0 >= p.cstore) break;  // uniform across the CTA
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        float f[16];
+      if (p.fast_out) {
+        // ---- bf16 NHWC: 64-column slabs -> swizzled staging -> TMA store (clips the tile edges)
+        for (int c0 = 0; c0 < p.bn; c0 += 64) {
+          if (n0 + c0 >= cstore) break;
+          uint32_t v[64];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld32(taddr + c0 + 32, v + 32);
+          tmem_ld_wait();
+          if (has_bias) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int ch = n0 + c0 + j;
-          float x = __uint_as_float(v[j]);
-          if (p.bias != nullptr && ch < p.cout) x += __ldg(p.bias + ch);
-          x = apply_act(x, p.act, p.slope);
-          f[j] = ch < p.cout ? x : 0.f;
-        }
-        if (p.stats_on) {
-          // per-(image, channel) sum and sum of squares of the fp32 accumulators of this tile
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float s1 = valid ? f[j] : 0.f;
-            float s2 = s1 * s1;
-            if (p.tile_n == 1) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              }
+            for (int j = 0; j < 64; ++j) {
               const int ch = n0 + c0 + j;
-              if (lane == 0 && ch < p.cout && (tn * p.tile_n) < p.dom_n) {
-                atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.cout + ch) * 2, s1);
-                atomicAdd(p.stats + (static_cast<int64_t>(tn) * p.cout + ch) * 2 + 1, s2);
+              if (ch < cout) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + ch));
+            }
+          }
+          if (act != CDB_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(apply_act(__uint_as_float(v[j]), act, slope));
+          }
+          if (n0 + c0 + 64 > cout || c0 + 64 > p.bn) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (n0 + c0 + j >= cout || c0 + j >= p.bn) v[j] = 0u;
+          }
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          if (stats_on) {
+            if (one_image) {
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                if (c0 + qd * 16 >= p.bn) break;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) slab[lane * 17 + j] = valid ? __uint_as_float(v[qd * 16 + j]) : 0.f;
+                __syncwarp();
+                if (lane < 16) {
+                  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                  for (int i = 0; i < 32; ++i) {
+                    const float t = slab[i * 17 + lane];
+                    s1 += t;
+                    s2 = fmaf(t, t, s2);
+                  }
+                  const int ch = n0 + c0 + qd * 16 + lane;
+                  const int simg = tn * p.tile_n + n_off;
+                  if (ch < cout && simg < p.dom_n) {
+                    atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2, s1);
+                    atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2 + 1, s2);
+                  }
+                }
+                __syncwarp();
               }
-            } else {
-              const int ch = n0 + c0 + j;
-              if (valid && ch < p.cout) {
-                atomicAdd(p.stats + (static_cast<int64_t>(img) * p.cout + ch) * 2, s1);
-                atomicAdd(p.stats + (static_cast<int64_t>(img) * p.cout + ch) * 2 + 1, s2);
+            } else if (valid) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                const int ch = n0 + c0 + j;
+                if (ch < cout && c0 + j < p.bn) {
+                  const float t = __uint_as_float(v[j]);
+                  atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2, t);
+                  atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2 + 1, t * t);
+                }
               }
             }
           }
-        }
-        if (valid) {
-          if (p.out_dtype == CDB_BF16 && p.o_sc == 1) {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + obase + n0 + c0;
+          const uint32_t rbase = stage_addr + lane * 128;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (n0 + c0 + h * 8 < p.cstore) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[h * 8 + 0], f[h * 8 + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[h * 8 + 2], f[h * 8 + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[h * 8 + 4], f[h * 8 + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[h * 8 + 6], f[h * 8 + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(o + h * 8) = pk;
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = rbase + ((static_cast<uint32_t>(j) ^ (lane & 7u)) << 4);
+            st_shared_v4(a, pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1])),
+                         pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3])),
+                         pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5])),
+                         pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7])));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&maps.out, stage_addr, n0 + c0, tw * p.tile_w + w_off, th * p.tile_h + h_off,
+                         tn * p.tile_n + n_off);
+            bulk_commit();
+          }
+        }
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      } else {
+        // ---- generic path: strided / fp32 / NCHW outputs, 16 columns at a time
+        const int64_t obase = img * p.o_sn + pp * p.o_sh + q * p.o_sw;
+        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+          if (n0 + c0 >= cstore) break;  // uniform across the CTA
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ch = n0 + c0 + j;
+            float x = __uint_as_float(v[j]);
+            if (has_bias && ch < cout) x += __ldg(p.bias + ch);
+            x = apply_act(x, act, slope);
+            f[j] = ch < cout ? x : 0.f;
+          }
+          if (stats_on && valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = n0 + c0 + j;
+              if (ch < cout) {
+                atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2, f[j]);
+                atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2 + 1, f[j] * f[j]);
               }
             }
-          } else if (p.out_dtype == CDB_BF16) {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + obase;
+          }
+          if (valid) {
+            if (p.out_dtype == CDB_BF16) {
+              __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + obase;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ch = n0 + c0 + j;
-              if (ch < p.cstore) o[ch * p.o_sc] = __float2bfloat16(f[j]);
-            }
-          } else {
-            float* o = static_cast<float*>(p.out) + obase;
+              for (int j = 0; j < 16; ++j) {
+                const int ch = n0 + c0 + j;
+                if (ch < cstore) o[ch * p.o_sc] = __float2bfloat16(f[j]);
+              }
+            } else {
+              float* o = static_cast<float*>(p.out) + obase;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ch = n0 + c0 + j;
-              if (ch < p.cstore) o[ch * p.o_sc] = f[j];
+              for (int j = 0; j < 16; ++j) {
+                const int ch = n0 + c0 + j;
+                if (ch < cstore) o[ch * p.o_sc] = f[j];
+              }
             }
           }
         }
@@ -331,12 +396,23 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
     int rc = make_tmap(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, str, box);
     if (rc != CDB_OK) return rc;
   }
+  prm.fast_out = (prm.out_dtype == CDB_BF16 && prm.o_sc == 1) ? 1 : 0;
+  if (prm.fast_out) {
+    const int bw = prm.tile_w < 32 ? prm.tile_w : 32;
+    const int bh = prm.tile_h < 32 / bw ? prm.tile_h : 32 / bw;
+    const int bnn = 32 / (bw * bh);
+    uint64_t dims[4] = {(uint64_t)prm.cstore, (uint64_t)prm.dom_w, (uint64_t)prm.dom_h, (uint64_t)prm.dom_n};
+    uint64_t str[3] = {(uint64_t)prm.o_sw * 2, (uint64_t)prm.o_sh * 2, (uint64_t)prm.o_sn * 2};
+    uint32_t box[4] = {64u, (uint32_t)bw, (uint32_t)bh, (uint32_t)bnn};
+    int rc = make_tmap(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, prm.out, dims, str, box);
+    if (rc != CDB_OK) return rc;
+  }
   const int stage_bytes = kABytes + prm.bn * 128;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (200 * 1024 - 16384) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   prm.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 16384 + 1024;
   static size_t smem_attr = 0;
   if (smem > smem_attr) {
     CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -412,7 +488,7 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   // (A rows shared by the S taps of a filter row, two accumulators per weight tile).
   if (!g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw == x->c &&
       x->sh == (int64_t)x->w * x->c && x->sn == (int64_t)x->h * x->w * x->c &&
-      y->h == x->h - (g->r - 1) * g->dil && y->w == x->w - (g->s - 1) * g->dil && y->n == x->n &&
+      y->h <= x->h - (g->r - 1) * g->dil && y->w <= x->w - (g->s - 1) * g->dil && y->n == x->n &&
       (g->s - 1) * g->dil <= 64 && (int64_t)y->h * x->w >= 256 && !env_flag("CDB_DISABLE_FLAT", 0)) {
     return launch_flat_conv(g, x, wpacked, w_rows_pad, w_kpad, y, ep, g->flip, env_flag("CDB_FLAT_BASE_OFFSET", 0),
                             stream);

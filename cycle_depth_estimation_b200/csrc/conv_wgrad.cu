@@ -382,7 +382,8 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   CDB_REQUIRE(g && x && dy && dw4 && workspace, CDB_ERR_BAD_DESC, "conv2d_wgrad: null argument");
   CDB_REQUIRE(x->dtype == CDB_BF16 && dy->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: bf16 only");
   CDB_REQUIRE(g->stride == 1 || g->stride == 2, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: stride %d", g->stride);
-  CDB_REQUIRE(!(g->rowpack && g->transposed), CDB_ERR_UNSUPPORTED, "conv2d_wgrad: rowpack with transposed");
+  // rowpack applies to the SHIFTED tensor: x for Conv2d, dy for the transposed form (used for layers with
+  // very few output channels: dy then carries 8 channels per pixel and one K block covers a filter row).
   const CdbAct *s_act, *g_act;
   wgrad_roles(g, x, dy, &s_act, &g_act);
   WgPlan pl;

@@ -181,6 +181,12 @@ class Plan:
             self.readers[st.src].append(idx)
             if st.reflect:
                 self.halo[st.src] = max(self.halo[st.src], st.reflect)
+        # zero halo materialised for stride-1 zero-padded direct convolutions (lets them take the flat kernel)
+        self.zero_halo = [0] * self.n_values
+        for idx, st in enumerate(stages):
+            c = st.conv
+            if (st.src != 0 and not st.transposed and not st.reflect and c.stride[0] == 1 and c.padding[0] > 0):
+                self.zero_halo[st.src] = c.padding[0]
         for v in range(1, self.n_values):
             rs = self.readers[v]
             if len(rs) > 1:
@@ -216,6 +222,15 @@ def _norm_kind(st):
     if st.norm is None:
         return NORM_NONE
     return NORM_INSTANCE if isinstance(st.norm, nn.InstanceNorm2d) else NORM_BATCH
+
+
+def _flat_stage(plan, st, is_first, rowpack):
+    """Stride-1 direct convolution whose input buffer carries its padding -> flat kernel."""
+    if st.transposed or st.conv.stride[0] != 1 or (is_first and rowpack):
+        return False
+    if st.reflect:
+        return True
+    return st.conv.padding[0] == 0 or (st.src != 0 and plan.zero_halo[st.src] == st.conv.padding[0])
 
 
 class _Run:
@@ -289,7 +304,9 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         is_first = idx == 0
         is_last = idx == len(plan.stages) - 1
         rowpack = rp if is_first else 0
-        materialised = bool(st.reflect) or (is_first and rp)
+        zero_mat = st.src != 0 and plan.zero_halo[st.src] > 0
+        materialised = bool(st.reflect) or bool(is_first and rp) or zero_mat
+        flat = _flat_stage(plan, st, is_first, rowpack)
         g = _geom_fwd(st, materialised, rowpack)
         wp, rows_pad, kpad = _pack_cache.get(conv.weight, not st.transposed, rowpack)
         xin = run.vals[st.src] if materialised else run.inner[st.src]
@@ -301,8 +318,15 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
             run.dims[st.dst] = (ho, wo, co)
             continue
         halo = plan.halo[st.dst]
-        dbuf = torch.empty((n, ho + 2 * halo, wo + 2 * halo, cs), dtype=BF16, device=dev)
-        dinner = dbuf[:, halo:halo + ho, halo:halo + wo, :]
+        zh = plan.zero_halo[st.dst]
+        if zh:
+            if halo:
+                raise NotImplementedError("value with both a reflect and a zero halo")
+            dbuf = torch.zeros((n, ho + 2 * zh, wo + 2 * zh, cs), dtype=BF16, device=dev)
+            dinner = dbuf[:, zh:zh + ho, zh:zh + wo, :]
+        else:
+            dbuf = torch.empty((n, ho + 2 * halo, wo + 2 * halo, cs), dtype=BF16, device=dev)
+            dinner = dbuf[:, halo:halo + ho, halo:halo + wo, :]
         run.vals[st.dst] = dbuf
         run.inner[st.dst] = dinner
         run.dims[st.dst] = (ho, wo, co)
@@ -314,7 +338,10 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
             ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(dinner, co), conv.bias, st.act, st.slope)
             continue
         # conv -> raw y (+ fused per-channel sums) -> norm/act/residual/halo
-        y = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+        if flat:
+            y = ops.alloc_flat_output(n, ho, wo, xin.shape[2], cs, dev)  # pitched: TMA-store epilogue
+        else:
+            y = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
         use_running = nk == NORM_BATCH and not training and st.norm.track_running_stats
         stats = None
         # A bias in front of a normalisation cancels exactly (InstanceNorm affine=False /
@@ -370,13 +397,23 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
         cs = ops.round_up(co, 8)
         nk = _norm_kind(st)
         rowpack = run.rowpack if is_first else 0
-        materialised = bool(st.reflect) or (is_first and rowpack)
+        zero_mat = st.src != 0 and plan.zero_halo[st.src] > 0
+        materialised = bool(st.reflect) or bool(is_first and rowpack) or zero_mat
+        flat = _flat_stage(plan, st, is_first, rowpack)
         want_w = needs_param_grad.get(conv.weight, False)
         want_b = conv.bias is not None and needs_param_grad.get(conv.bias, False)
         affine = st.norm is not None and getattr(st.norm, "affine", False)
         want_dx = (not is_first) or need_input_grad
-        # ---- dY: gradient w.r.t. the raw convolution output
-        dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+        # ---- dY: gradient w.r.t. the raw convolution output. For flat stages it lives inside a zero halo
+        # of (k-1)*dil pixels, so that the data gradient is again a flat (flipped) convolution.
+        flat_dgrad = flat and want_dx and not is_first
+        if flat_dgrad:
+            hz = (conv.kernel_size[0] - 1) * conv.dilation[0]
+            slack = 64 // cs if cs <= 16 else 0   # room for the row-packed view used by the few-channel wgrad
+            dyp = torch.zeros((n, ho + 2 * hz, wo + 2 * hz + slack, cs), dtype=BF16, device=dev)
+            dy = dyp[:, hz:hz + ho, hz:hz + wo, :]
+        else:
+            dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
         if is_last:
             ops.nchw_to_nhwc(gout, dy, pad=0, act_out=run.out if st.act != ACT_NONE else None, act=st.act,
                              slope=st.slope)
@@ -386,8 +423,9 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                 grads[conv.bias] = db
         else:
             halo = plan.halo[st.dst]
+            off = halo + plan.zero_halo[st.dst]
             dout_full = dpad[st.dst]
-            dout_inner = dout_full[:, halo:halo + ho, halo:halo + wo, :] if dout_full is not None else None
+            dout_inner = dout_full[:, off:off + ho, off:off + wo, :] if dout_full is not None else None
             use_running = nk == NORM_BATCH and not run.training and st.norm.track_running_stats
             groups = n if nk == NORM_INSTANCE else 1
             need_b = (nk != NORM_NONE and not use_running) or (nk == NORM_NONE and want_b) or affine
@@ -427,8 +465,17 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
         # ---- wgrad
         xin = run.vals[st.src] if materialised else run.inner[st.src]
         if want_w:
-            dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-            ops.conv2d_wgrad(_geom_fwd(st, materialised, rowpack), xin, dy, dw, False)
+            k = conv.kernel_size[0]
+            if flat_dgrad and cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
+                # few output channels (the 7x7 c7s1-3 layer): correlate the padded input with the zero-haloed
+                # dy, whose 8 channels x 8 pixels form one K block per filter row; the result comes out as
+                # [cin, cout, R-1-r, S-1-s]
+                tmp = torch.empty((ci, co, k, k), dtype=torch.float32, device=dev)
+                ops.conv2d_wgrad(ops.geom(k, k, 1, 0, 0, 1, True, cs), xin, dyp, tmp, False)
+                dw = tmp.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+            else:
+                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                ops.conv2d_wgrad(_geom_fwd(st, materialised, rowpack), xin, dy, dw, False)
             grads[conv.weight] = dw
         # ---- dgrad
         if want_dx:
@@ -445,6 +492,15 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                 else:
                     gx = torch.empty((n, cin, hi, wi), dtype=torch.float32, device=dev)
                     ops.conv2d_fwd(gd, dy, wd, rows_pad, kpad, ops.out_view_nchw(gx))
+            elif flat_dgrad:
+                src_full = run.vals[st.src]
+                hp, wp_ = src_full.shape[1], src_full.shape[2]
+                dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], src_full.shape[3], dev)
+                gflip = ops.geom(conv.kernel_size[0], conv.kernel_size[1], 1, 0, 0, conv.dilation[0], False, 0, True)
+                ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+                dpad[st.src] = dfull
+                if DEBUG_RECORD is not None:
+                    DEBUG_RECORD[('dfull', st.src)] = dfull.clone()
             else:
                 src_full = run.vals[st.src]
                 if materialised:

@@ -116,7 +116,9 @@ int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int
 /* ---- K3: weight gradient -------------------------------------------------------------------
  * Replaces the filter-gradient half of aten.convolution_backward.
  *   dW4[d0][d1][r][s] (+)= sum_{n,p,q} dy[n,p,q,o] * x[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, i]
- * with (o,i) = (d0,d1) for Conv2d and x/dy swapped roles for ConvTranspose2d (g->transposed).
+ * with (o,i) = (d0,d1) for Conv2d and x/dy swapped roles for ConvTranspose2d (g->transposed):
+ *   transposed: dW4[d0][d1][r][s] (+)= sum_{n,p,q} x[n,p,q,d0] * dy[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, d1]
+ * g->rowpack refers to the shifted tensor (x, or dy when transposed), see CdbConvGeom.
  * workspace: cdb_conv2d_wgrad_workspace() bytes of fp32 split-K partials. */
 size_t cdb_conv2d_wgrad_workspace(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy);
 int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, float* dw4,

@@ -181,6 +181,33 @@ ROWPACK_CASES = {
     "rowpack16_4x4_s2_cin6": dict(n=1, cin=6, cout=64, h=34, w=34, k=4, stride=2, rowpack=16),
 }
 
+def conv_wgrad_fewcout_case(n, cin, cout, h, w, k, seed=0):
+    """Weight gradient of a stride-1 convolution with <= 8 output channels through the transposed +
+    row-packed form (x: padded input, dy: zero-haloed by k-1), as the engine does for the c7s1-3 layer."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = _rand((n, cin, h, w), gen)
+    w4 = torch.zeros((cout, cin, k, k), device="cuda", requires_grad=True)
+    y = F.conv2d(x.float(), w4)
+    dy = _rand(tuple(y.shape), gen, 0.1)
+    y.backward(dy.float())
+    ho, wo = y.shape[2], y.shape[3]
+    hz = k - 1
+    dyp = torch.zeros((n, ho + 2 * hz, wo + 2 * hz + 8, 8), dtype=torch.bfloat16, device="cuda")
+    dyp[:, hz:hz + ho, hz:hz + wo, :cout] = dy.permute(0, 2, 3, 1)
+    tmp = torch.empty((cin, cout, k, k), dtype=torch.float32, device="cuda")
+    ops.conv2d_wgrad(ops.geom(k, k, 1, 0, 0, 1, True, 8), nhwc(x), dyp, tmp, False)
+    torch.cuda.synchronize()
+    got = tmp.flip(2, 3).permute(1, 0, 2, 3)
+    err = rel_l2(got, w4.grad)
+    return {"err": err, "tol": 1e-3, "ok": err <= 1e-3}
+
+
+WGRAD_FEWCOUT_CASES = {
+    "wgrad_fewcout_7x7_64_3": dict(n=2, cin=64, cout=3, h=70, w=70, k=7),
+    "wgrad_fewcout_3x3_128_1": dict(n=1, cin=128, cout=1, h=20, w=36, k=3),
+}
+
+
 WGRAD_CASES = {
     "wgrad_3x3_256": dict(n=2, cin=256, cout=256, h=34, w=34, k=3),
     "wgrad_3x3_pad1_128_64": dict(n=2, cin=128, cout=64, h=32, w=32, k=3, pad=1, accumulate=True),

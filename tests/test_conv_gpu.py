@@ -27,3 +27,8 @@ def test_conv_rowpack(name):
 @pytest.mark.parametrize("name", sorted(cc.WGRAD_CASES))
 def test_conv_wgrad(name):
     _assert_ok(cc.conv_wgrad_case(**cc.WGRAD_CASES[name]))
+
+
+@pytest.mark.parametrize("name", sorted(cc.WGRAD_FEWCOUT_CASES))
+def test_conv_wgrad_few_output_channels(name):
+    _assert_ok(cc.conv_wgrad_fewcout_case(**cc.WGRAD_FEWCOUT_CASES[name]))

@@ -23,7 +23,8 @@ def run_group(group):
     import conv_cases as cc
     from cycle_depth_estimation_b200 import _lib
     table = {"fwd": (cc.FWD_CASES, cc.conv_fwd_case), "rowpack": (cc.ROWPACK_CASES, cc.conv_rowpack_case),
-             "wgrad": (cc.WGRAD_CASES, cc.conv_wgrad_case)}
+             "wgrad": (cc.WGRAD_CASES, cc.conv_wgrad_case),
+             "wgrad2": (cc.WGRAD_FEWCOUT_CASES, cc.conv_wgrad_fewcout_case)}
     cases, fn = table[group]
     for name, kw in cases.items():
         rec = {"group": group, "case": name}
@@ -44,7 +45,7 @@ def run_group(group):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=None)
-    ap.add_argument("--groups", default="fwd,rowpack,wgrad")
+    ap.add_argument("--groups", default="fwd,rowpack,wgrad,wgrad2")
     args = ap.parse_args()
     if args.group:
         run_group(args.group)
