@@ -190,32 +190,51 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormFwdParams p) {
   const __nv_bfloat16* rb = p.has_res ? p.res.ptr + n * p.res.sn + cvec * 8 : nullptr;
   __nv_bfloat16* ob = p.out.ptr + n * p.out.sn + cvec * 8;
   const int pad = p.pad, H = p.H, W = p.W;
-  for (int px = p0 + lane; px < p1; px += lanes) {
-    const int h = px / W, w = px - h * W;
-    float f[8];
-    unpack8(ld16(yb + h * p.y.sh + w * p.y.sw), f);
+  // four pixels per iteration, all loads issued before the first use (memory-level parallelism)
+  constexpr int U = 4;
+  for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
+    uint4 yr[U], rr[U];
+    int hs[U], ws[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * scale[j] + shift[j], p.act, p.slope);
-    if (p.has_res) {
-      float r[8];
-      unpack8(ld16(rb + h * p.res.sh + w * p.res.sw), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    for (int u = 0; u < U; ++u) {
+      const int px = px0 + u * lanes;
+      hs[u] = px / W;
+      ws[u] = px - hs[u] * W;
+      if (px < p1) {
+        yr[u] = ld16(yb + hs[u] * p.y.sh + ws[u] * p.y.sw);
+        if (p.has_res) rr[u] = ld16(rb + hs[u] * p.res.sh + ws[u] * p.res.sw);
+      }
     }
-    const uint4 o = pack8(f);
-    st16(ob + h * p.out.sh + w * p.out.sw, o);
-    if (pad > 0) {
-      // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
-      int hh[2], ww[2];
-      int nh = 0, nw = 0;
-      if (h >= 1 && h <= pad) hh[nh++] = -h;
-      if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
-      if (w >= 1 && w <= pad) ww[nw++] = -w;
-      if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
-      for (int a = 0; a < nh; ++a) st16(ob + hh[a] * p.out.sh + w * p.out.sw, o);
-      for (int b = 0; b < nw; ++b) st16(ob + h * p.out.sh + ww[b] * p.out.sw, o);
-      for (int a = 0; a < nh; ++a)
-        for (int b = 0; b < nw; ++b) st16(ob + hh[a] * p.out.sh + ww[b] * p.out.sw, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int px = px0 + u * lanes;
+      if (px >= p1) break;
+      const int h = hs[u], w = ws[u];
+      float f[8];
+      unpack8(yr[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * scale[j] + shift[j], p.act, p.slope);
+      if (p.has_res) {
+        float r[8];
+        unpack8(rr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      const uint4 o = pack8(f);
+      st16(ob + h * p.out.sh + w * p.out.sw, o);
+      if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad)) {
+        // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
+        int hh[2], ww[2];
+        int nh = 0, nw = 0;
+        if (h >= 1 && h <= pad) hh[nh++] = -h;
+        if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
+        if (w >= 1 && w <= pad) ww[nw++] = -w;
+        if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
+        for (int a = 0; a < nh; ++a) st16(ob + hh[a] * p.out.sh + w * p.out.sw, o);
+        for (int b = 0; b < nw; ++b) st16(ob + h * p.out.sh + ww[b] * p.out.sw, o);
+        for (int a = 0; a < nh; ++a)
+          for (int b = 0; b < nw; ++b) st16(ob + hh[a] * p.out.sh + ww[b] * p.out.sw, o);
+      }
     }
   }
 }
@@ -253,36 +272,26 @@ struct NormBwdParams {
   float* bstats;  // [g][c][2]
 };
 
-__device__ __forceinline__ void load_folded(const NormBwdParams& p, const __nv_bfloat16* db,
-                                            const __nv_bfloat16* sb, int h, int w, float* g) {
+// Adds to g the reflect images of (h, w) other than (h, w) itself (border pixels only).
+__device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const __nv_bfloat16* db, int h, int w,
+                                                  float* g) {
+  const int pad = p.pad, H = p.H, W = p.W;
+  int hh[3], ww[3];
+  int nh = 0, nw = 0;
+  hh[nh++] = h;
+  ww[nw++] = w;
+  if (h >= 1 && h <= pad) hh[nh++] = -h;
+  if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
+  if (w >= 1 && w <= pad) ww[nw++] = -w;
+  if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) {
+      if (a == 0 && b == 0) continue;
+      float t[8];
+      unpack8(ld16(db + hh[a] * p.dout.sh + ww[b] * p.dout.sw), t);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  if (p.has_dout) {
-    int hh[3], ww[3];
-    int nh = 0, nw = 0;
-    hh[nh++] = h;
-    ww[nw++] = w;
-    const int pad = p.pad, H = p.H, W = p.W;
-    if (pad > 0) {
-      if (h >= 1 && h <= pad) hh[nh++] = -h;
-      if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
-      if (w >= 1 && w <= pad) ww[nw++] = -w;
-      if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
+      for (int j = 0; j < 8; ++j) g[j] += t[j];
     }
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b) {
-        float t[8];
-        unpack8(ld16(db + hh[a] * p.dout.sh + ww[b] * p.dout.sw), t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] += t[j];
-      }
-  }
-  if (p.has_dskip) {
-    float t[8];
-    unpack8(ld16(sb + h * p.dskip.sh + w * p.dskip.sw), t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += t[j];
-  }
 }
 
 template <bool kApply>
@@ -316,30 +325,63 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
     const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
     const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
     const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
-    for (int px = p0 + lane; px < p1; px += lanes) {
-      const int h = px / p.W, w = px - h * p.W;
-      float g[8], f[8];
-      load_folded(p, db, sb, h, w, g);
-      unpack8(ld16(yb + h * p.y.sh + w * p.y.sw), f);
-      if (kApply && p.write_gsum) st16(p.gsum.ptr + n * p.gsum.sn + h * p.gsum.sh + w * p.gsum.sw + cvec * 8, pack8(g));
-      float o[8];
+    constexpr int U = 2;  // two pixels per iteration, centre loads issued first
+    const int pad = p.pad, H = p.H, W = p.W;
+    for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
+      uint4 yr[U], dr[U], sr[U];
+      int hs[U], ws[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float z = f[j] * scale[j] + shift[j];
-        float ga = g[j];
-        if (p.act == CDB_ACT_RELU) ga = z > 0.f ? ga : 0.f;
-        else if (p.act == CDB_ACT_LEAKY) ga = z > 0.f ? ga : ga * p.slope;
-        const float xhat = (f[j] - mean[j]) * rstd[j];
-        if (kApply) {
-          o[j] = (p.norm == CDB_NORM_NONE) ? ga
-                 : p.use_running          ? ga * scale[j]
-                                          : scale[j] * (ga - m1[j] - xhat * m2[j]);
-        } else {
-          s1[j] += ga;
-          s2[j] += ga * xhat;
+      for (int u = 0; u < U; ++u) {
+        const int px = px0 + u * lanes;
+        hs[u] = px / W;
+        ws[u] = px - hs[u] * W;
+        if (px < p1) {
+          yr[u] = ld16(yb + hs[u] * p.y.sh + ws[u] * p.y.sw);
+          if (p.has_dout) dr[u] = ld16(db + hs[u] * p.dout.sh + ws[u] * p.dout.sw);
+          if (p.has_dskip) sr[u] = ld16(sb + hs[u] * p.dskip.sh + ws[u] * p.dskip.sw);
         }
       }
-      if (kApply) st16(p.dy.ptr + n * p.dy.sn + h * p.dy.sh + w * p.dy.sw + cvec * 8, pack8(o));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int px = px0 + u * lanes;
+        if (px >= p1) break;
+        const int h = hs[u], w = ws[u];
+        float g[8], f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        if (p.has_dout) {
+          unpack8(dr[u], g);
+          if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad))
+            add_folded_extras(p, db, h, w, g);
+        }
+        if (p.has_dskip) {
+          float t[8];
+          unpack8(sr[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += t[j];
+        }
+        unpack8(yr[u], f);
+        if (kApply && p.write_gsum)
+          st16(p.gsum.ptr + n * p.gsum.sn + h * p.gsum.sh + w * p.gsum.sw + cvec * 8, pack8(g));
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float z = f[j] * scale[j] + shift[j];
+          float ga = g[j];
+          if (p.act == CDB_ACT_RELU) ga = z > 0.f ? ga : 0.f;
+          else if (p.act == CDB_ACT_LEAKY) ga = z > 0.f ? ga : ga * p.slope;
+          const float xhat = (f[j] - mean[j]) * rstd[j];
+          if (kApply) {
+            o[j] = (p.norm == CDB_NORM_NONE) ? ga
+                   : p.use_running          ? ga * scale[j]
+                                            : scale[j] * (ga - m1[j] - xhat * m2[j]);
+          } else {
+            s1[j] += ga;
+            s2[j] += ga * xhat;
+          }
+        }
+        if (kApply) st16(p.dy.ptr + n * p.dy.sn + h * p.dy.sh + w * p.dy.sw + cvec * 8, pack8(o));
+      }
     }
   }
   if (!kApply) {
