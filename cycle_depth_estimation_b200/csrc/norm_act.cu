@@ -46,6 +46,23 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
+// Walks pixels p0+lane, p0+lane+lanes, ... of a W-wide image keeping (h, w) without divisions.
+struct PixelWalk {
+  int h, w, W;
+  __device__ __forceinline__ void init(int px, int W_) {
+    W = W_;
+    h = px / W_;
+    w = px - h * W_;
+  }
+  __device__ __forceinline__ void advance(int step) {
+    w += step;
+    while (w >= W) {
+      w -= W;
+      ++h;
+    }
+  }
+};
+
 // Thread -> (channel vector, pixel lane) mapping shared by all kernels of this file.
 struct Mapping {
   int vt;      // channel vectors handled per block (power of two <= 256)
@@ -62,8 +79,9 @@ static Mapping mapping_for(int c) {
   m.cv_tiles = ceil_div(cv, vt);
   return m;
 }
-static int chunks_for(int pixels, int lanes, int n, int cv_tiles) {
-  int want = (4 * sm_count()) / (n * cv_tiles > 0 ? n * cv_tiles : 1);
+static int chunks_for(int pixels, int lanes, int n, int cv_tiles, int per_sm_default = 2) {
+  const int per_sm = getenv("CDB_NORM_BLOCKS_PER_SM") ? atoi(getenv("CDB_NORM_BLOCKS_PER_SM")) : per_sm_default;
+  int want = (per_sm * sm_count()) / (n * cv_tiles > 0 ? n * cv_tiles : 1);
   if (want < 1) want = 1;
   int max_chunks = ceil_div(pixels, lanes * 4);
   if (max_chunks < 1) max_chunks = 1;
@@ -89,10 +107,12 @@ channel_stats_kernel(View y, int H, int W, int C, int vt, int per_image, float* 
   const bool active = cvec * 8 < C;
   if (active) {
     const __nv_bfloat16* base = y.ptr + n * y.sn + cvec * 8;
-    for (int p = p0 + lane; p < p1; p += lanes) {
-      const int h = p / W, w = p - h * W;
+    PixelWalk pw;
+    pw.init(p0 + lane, W);
+    const int ysh = static_cast<int>(y.sh), ysw = static_cast<int>(y.sw);
+    for (int p = p0 + lane; p < p1; p += lanes, pw.advance(lanes)) {
       float f[8];
-      unpack8(ld16(base + h * y.sh + w * y.sw), f);
+      unpack8(ld16(base + pw.h * ysh + pw.w * ysw), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s1[j] += f[j];
@@ -174,7 +194,7 @@ __device__ __forceinline__ void norm_coeffs(int norm, int use_running, const flo
   }
 }
 
-__global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormFwdParams p) {
+__global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(NormFwdParams p) {
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
   const int cvec = blockIdx.z * p.vt + v;
   if (cvec * 8 >= p.C) return;
@@ -190,19 +210,25 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormFwdParams p) {
   const __nv_bfloat16* rb = p.has_res ? p.res.ptr + n * p.res.sn + cvec * 8 : nullptr;
   __nv_bfloat16* ob = p.out.ptr + n * p.out.sn + cvec * 8;
   const int pad = p.pad, H = p.H, W = p.W;
-  // four pixels per iteration, all loads issued before the first use (memory-level parallelism)
-  constexpr int U = 4;
+  // two pixels per iteration, loads issued before the first use
+  constexpr int U = 2;
+  PixelWalk pw;
+  pw.init(p0 + lane, W);
+  const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
+  const int rsh = static_cast<int>(p.res.sh), rsw = static_cast<int>(p.res.sw);
+  const int osh = static_cast<int>(p.out.sh), osw = static_cast<int>(p.out.sw);
   for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
     uint4 yr[U], rr[U];
     int hs[U], ws[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int px = px0 + u * lanes;
-      hs[u] = px / W;
-      ws[u] = px - hs[u] * W;
+      hs[u] = pw.h;
+      ws[u] = pw.w;
+      pw.advance(lanes);
       if (px < p1) {
-        yr[u] = ld16(yb + hs[u] * p.y.sh + ws[u] * p.y.sw);
-        if (p.has_res) rr[u] = ld16(rb + hs[u] * p.res.sh + ws[u] * p.res.sw);
+        yr[u] = ld16(yb + hs[u] * ysh + ws[u] * ysw);
+        if (p.has_res) rr[u] = ld16(rb + hs[u] * rsh + ws[u] * rsw);
       }
     }
 #pragma unroll
@@ -221,7 +247,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormFwdParams p) {
         for (int j = 0; j < 8; ++j) f[j] += r[j];
       }
       const uint4 o = pack8(f);
-      st16(ob + h * p.out.sh + w * p.out.sw, o);
+      st16(ob + h * osh + w * osw, o);
       if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad)) {
         // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
         int hh[2], ww[2];
@@ -230,10 +256,10 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(NormFwdParams p) {
         if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
         if (w >= 1 && w <= pad) ww[nw++] = -w;
         if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
-        for (int a = 0; a < nh; ++a) st16(ob + hh[a] * p.out.sh + w * p.out.sw, o);
-        for (int b = 0; b < nw; ++b) st16(ob + h * p.out.sh + ww[b] * p.out.sw, o);
+        for (int a = 0; a < nh; ++a) st16(ob + hh[a] * osh + w * osw, o);
+        for (int b = 0; b < nw; ++b) st16(ob + h * osh + ww[b] * osw, o);
         for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b) st16(ob + hh[a] * p.out.sh + ww[b] * p.out.sw, o);
+          for (int b = 0; b < nw; ++b) st16(ob + hh[a] * osh + ww[b] * osw, o);
       }
     }
   }
@@ -327,18 +353,28 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
     const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
     constexpr int U = 2;  // two pixels per iteration, centre loads issued first
     const int pad = p.pad, H = p.H, W = p.W;
+    PixelWalk pw;
+    pw.init(p0 + lane, W);
+    const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
+    const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
+    const int ssh = static_cast<int>(p.dskip.sh), ssw = static_cast<int>(p.dskip.sw);
+    const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
+    const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
+    __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
+    __nv_bfloat16* ob = kApply ? p.dy.ptr + n * p.dy.sn + cvec * 8 : nullptr;
     for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
       uint4 yr[U], dr[U], sr[U];
       int hs[U], ws[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int px = px0 + u * lanes;
-        hs[u] = px / W;
-        ws[u] = px - hs[u] * W;
+        hs[u] = pw.h;
+        ws[u] = pw.w;
+        pw.advance(lanes);
         if (px < p1) {
-          yr[u] = ld16(yb + hs[u] * p.y.sh + ws[u] * p.y.sw);
-          if (p.has_dout) dr[u] = ld16(db + hs[u] * p.dout.sh + ws[u] * p.dout.sw);
-          if (p.has_dskip) sr[u] = ld16(sb + hs[u] * p.dskip.sh + ws[u] * p.dskip.sw);
+          yr[u] = ld16(yb + hs[u] * ysh + ws[u] * ysw);
+          if (p.has_dout) dr[u] = ld16(db + hs[u] * dsh + ws[u] * dsw);
+          if (p.has_dskip) sr[u] = ld16(sb + hs[u] * ssh + ws[u] * ssw);
         }
       }
 #pragma unroll
@@ -361,8 +397,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
           for (int j = 0; j < 8; ++j) g[j] += t[j];
         }
         unpack8(yr[u], f);
-        if (kApply && p.write_gsum)
-          st16(p.gsum.ptr + n * p.gsum.sn + h * p.gsum.sh + w * p.gsum.sw + cvec * 8, pack8(g));
+        if (kApply && p.write_gsum) st16(gb + h * gsh + w * gsw, pack8(g));
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -380,7 +415,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
             s2[j] += ga * xhat;
           }
         }
-        if (kApply) st16(p.dy.ptr + n * p.dy.sn + h * p.dy.sh + w * p.dy.sw + cvec * 8, pack8(o));
+        if (kApply) st16(ob + h * osh + w * osw, pack8(o));
       }
     }
   }
@@ -481,7 +516,7 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.beta = d->beta;
   p.running_mean = d->running_mean;
   p.running_var = d->running_var;
-  const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
+  const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles, 3);
   dim3 grid(chunks, y->n, m.cv_tiles);
   norm_act_fwd_kernel<<<grid, 256, 0, stream>>>(p);
   CDB_LAUNCH_OK();

@@ -29,6 +29,10 @@ for e in prof.events():
 print("total kernel us", round(tot, 1))
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
     print("%-72s n=%5d %10.1f us %5.1f%% avg %7.1f" % (k, v[0], v[1], 100 * v[1] / tot, v[1] / v[0]))
-# biggest individual igemm launches
-big = sorted([(e.device_time, e.name[:40]) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], reverse=True)[:40]
-print([ (round(t), n) for t, n in big])
+for kname in ("igemm_flat", "igemm_kernel", "wgrad_kernel", "norm_act_bwd_kernel<true>", "norm_act_fwd"):
+    b = collections.defaultdict(lambda: [0, 0.0])
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA and kname in e.name:
+            key = int(round(e.device_time / 5.0) * 5)
+            b[key][0] += 1; b[key][1] += e.device_time
+    print(kname, sorted([(k, v[0], round(v[1])) for k, v in b.items()], key=lambda t: -t[2])[:14])
