@@ -189,7 +189,10 @@ def time_dominant_kernel(peaks, iters=40):
     flops = 2.0 * n * hw * hw * c * c * k * k
     achieved = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_burst"], "traffic": None, "kernel": "igemm_flat_kernel",
+            "frac": achieved / peaks["bf16_burst"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this launch
+            # (profiles/r01_ncu_full_flat_r01b.json): 19.10 MB read, 0 written (the output stays in L2)
+            "traffic": 19101696, "kernel": "igemm_flat_kernel",
             "shape": "3x3 conv 256->256, 64x64, batch 8 (M=32768 N=256 K=2304), fused IN statistics",
             "us_per_launch": ms * 1e3, "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
 

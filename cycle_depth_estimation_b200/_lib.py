@@ -31,13 +31,13 @@ class CdbConvGeom(C.Structure):
 
 class CdbEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("slope", C.c_float), ("stats", C.c_void_p),
-                ("reserved", C.c_int64)]
+                ("flags", C.c_int64)]
 
 
 class CdbNormDesc(C.Structure):
     _fields_ = [("norm", C.c_int32), ("act", C.c_int32), ("slope", C.c_float), ("eps", C.c_float),
                 ("channels", C.c_int32), ("pad", C.c_int32), ("use_running", C.c_int32),
-                ("update_running", C.c_int32), ("momentum", C.c_float), ("reserved", C.c_int32),
+                ("update_running", C.c_int32), ("momentum", C.c_float), ("flags", C.c_int32),
                 ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
 

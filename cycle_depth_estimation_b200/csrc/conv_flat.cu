@@ -32,7 +32,7 @@ struct FlatParams {
   int32_t dom_h, dom_w;              // valid outputs: h < dom_h, w < dom_w with (h, w) = divmod(f, wp)
   int32_t halo_rows;                 // extra rows after the BM block (multiple of 8)
   int32_t a_stages, b_stages;
-  int32_t cout, cstore, out_dtype, act, stats_on, use_base_offset, sleep_ns, rotate, fast_out, out_rows_per_img;
+  int32_t cout, cstore, out_dtype, act, stats_on, stats_batch, use_base_offset, sleep_ns, rotate, fast_out, out_rows_per_img;
   float slope;
   const float* bias;
   void* out;
@@ -260,7 +260,7 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
       const int n0 = n_tile * p.bn;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(buf * 2 * acc_cols + sub * acc_cols);
-      float* stats_img = stats_on ? p.stats + static_cast<int64_t>(img) * cout * 2 : nullptr;
+      float* stats_img = stats_on ? p.stats + static_cast<int64_t>(p.stats_batch ? 0 : img) * cout * 2 : nullptr;
       if (p.fast_out) {
         // ---- fast path: 64-column slabs -> bf16 -> swizzled staging -> TMA store (coalesced, async)
         const int out_row0 = img * p.out_rows_per_img + f0 + sub * 128 + quarter * 32;
@@ -448,6 +448,7 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   prm.bias = ep ? ep->bias : nullptr;
   prm.stats = ep ? ep->stats : nullptr;
   prm.stats_on = prm.stats != nullptr;
+  prm.stats_batch = (ep && (ep->flags & CDB_EP_STATS_BATCH)) ? 1 : 0;
   prm.use_base_offset = use_base_offset;
   prm.out = y->ptr;
   prm.o_sn = y->sn;

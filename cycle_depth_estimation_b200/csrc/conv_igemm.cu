@@ -40,6 +40,7 @@ struct IgemmParams {
   float slope;
   int32_t stages;
   int32_t stats_on;
+  int32_t stats_batch;  // 1: one statistics group for the whole batch (BatchNorm)
   int32_t fast_out;
   const float* bias;
   void* out;
@@ -242,7 +243,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
           if (stats_on) {
-            if (one_image) {
+            if (one_image || p.stats_batch) {
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
                 if (c0 + qd * 16 >= p.bn) break;
@@ -258,7 +259,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     s2 = fmaf(t, t, s2);
                   }
                   const int ch = n0 + c0 + qd * 16 + lane;
-                  const int simg = tn * p.tile_n + n_off;
+                  const int simg = p.stats_batch ? 0 : tn * p.tile_n + n_off;
                   if (ch < cout && simg < p.dom_n) {
                     atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2, s1);
                     atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2 + 1, s2);
@@ -315,12 +316,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             f[j] = ch < cout ? x : 0.f;
           }
           if (stats_on && valid) {
+            const int simg = p.stats_batch ? 0 : img;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ch = n0 + c0 + j;
               if (ch < cout) {
-                atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2, f[j]);
-                atomicAdd(p.stats + (static_cast<int64_t>(img) * cout + ch) * 2 + 1, f[j] * f[j]);
+                atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2, f[j]);
+                atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2 + 1, f[j] * f[j]);
               }
             }
           }
@@ -480,6 +482,7 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   prm.bias = ep ? ep->bias : nullptr;
   prm.stats = ep ? ep->stats : nullptr;
   prm.stats_on = prm.stats != nullptr;
+  prm.stats_batch = (ep && (ep->flags & CDB_EP_STATS_BATCH)) ? 1 : 0;
   prm.k_chunks = w_kpad / 64;
   prm.dom_n = y->n;
 

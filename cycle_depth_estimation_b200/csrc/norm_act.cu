@@ -288,6 +288,8 @@ struct NormBwdParams {
   View y, dout, dskip, dy, gsum;
   int H, W, C, vt;
   int norm, act, pad, has_dout, has_dskip, write_gsum, use_running;
+  int pre_act;    // ACT_FIRST: y is act(conv); the result is multiplied by act'(y)
+  int accum_f32;  // dy is an fp32 view that receives +=
   float slope, eps, inv_count;
   int per_image;
   const float* stats;
@@ -410,12 +412,26 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
             o[j] = (p.norm == CDB_NORM_NONE) ? ga
                    : p.use_running          ? ga * scale[j]
                                             : scale[j] * (ga - m1[j] - xhat * m2[j]);
+            if (p.pre_act == CDB_ACT_RELU) o[j] = f[j] > 0.f ? o[j] : 0.f;
+            else if (p.pre_act == CDB_ACT_LEAKY) o[j] = f[j] > 0.f ? o[j] : o[j] * p.slope;
           } else {
             s1[j] += ga;
             s2[j] += ga * xhat;
           }
         }
-        if (kApply) st16(ob + h * osh + w * osw, pack8(o));
+        if (kApply) {
+          if (p.accum_f32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dy.ptr) + n * p.dy.sn + cvec * 8 +
+                                                   static_cast<int64_t>(h) * p.dy.sh + static_cast<int64_t>(w) * p.dy.sw);
+            float4 a = o4[0], b = o4[1];
+            a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3];
+            b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
+            o4[0] = a;
+            o4[1] = b;
+          } else {
+            st16(ob + h * osh + w * osw, pack8(o));
+          }
+        }
       }
     }
   }
@@ -504,7 +520,7 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   const Mapping m = mapping_for(round_up(p.C, 8));
   p.vt = m.vt;
   p.norm = d->norm;
-  p.act = d->act;
+  p.act = (d->flags & CDB_NORM_FLAG_ACT_FIRST) ? CDB_ACT_NONE : d->act;
   p.slope = d->slope;
   p.eps = d->eps;
   p.pad = d->pad;
@@ -535,8 +551,15 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   CDB_REQUIRE(d, CDB_ERR_BAD_DESC, "norm_act_bwd: null desc");
   int rc = check_view(y, "norm_act_bwd y");
   if (rc) return rc;
-  rc = check_view(dy, "norm_act_bwd dy");
-  if (rc) return rc;
+  const bool accum_f32 = (d->flags & CDB_NORM_FLAG_ACCUM_F32) != 0;
+  if (accum_f32) {
+    CDB_REQUIRE(dy && dy->ptr && dy->dtype == CDB_F32 && dy->sn % 8 == 0 && dy->sh % 8 == 0 && dy->sw % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(dy->ptr) & 31) == 0,
+                CDB_ERR_ALIGNMENT, "norm_act_bwd: ACCUM_F32 needs an fp32 dy view with 32-byte aligned pixels");
+  } else {
+    rc = check_view(dy, "norm_act_bwd dy");
+    if (rc) return rc;
+  }
   const bool has_dout = dout && dout->ptr, has_dskip = dskip && dskip->ptr, has_gsum = gsum && gsum->ptr;
   CDB_REQUIRE(has_dout || has_dskip, CDB_ERR_BAD_DESC, "norm_act_bwd: no incoming gradient");
   if (has_dout && (rc = check_view(dout, "norm_act_bwd dout"))) return rc;
@@ -563,7 +586,10 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   const Mapping m = mapping_for(round_up(p.C, 8));
   p.vt = m.vt;
   p.norm = d->norm;
-  p.act = d->act;
+  const bool act_first = (d->flags & CDB_NORM_FLAG_ACT_FIRST) != 0;
+  p.act = act_first ? CDB_ACT_NONE : d->act;
+  p.pre_act = act_first ? d->act : CDB_ACT_NONE;
+  p.accum_f32 = accum_f32 ? 1 : 0;
   p.slope = d->slope;
   p.eps = d->eps;
   p.pad = d->pad;

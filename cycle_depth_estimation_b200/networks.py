@@ -13,7 +13,8 @@ import torch.nn as nn
 from torch.nn import init
 from torch.optim import lr_scheduler
 
-from . import engine, losses
+from . import engine, graph, losses
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 
 
 # ------------------------------------------------------------------------------------------------
@@ -259,8 +260,15 @@ class PixelDiscriminator(_FusedNet):
 
 
 class UnetGenerator(nn.Module):
-    """models/networks.py:243-260. Module tree / state_dict identical; execution on the fused engine is
-    not wired yet for the skip-connection topology (raises, never falls back)."""
+    """models/networks.py:243-260. Module tree / state_dict identical to the reference; ``forward`` runs the
+    whole U-Net on the graph engine (``graph.py``):
+
+    * every skip concatenation ``cat([x, model(x)], 1)`` (:316) is one preallocated NHWC buffer whose two
+      channel halves are written by their producers — ``torch.cat`` never runs;
+    * the skip half carries LeakyReLU(x) because the child's in-place ``downrelu`` mutates x before the
+      concatenation materialises (:279,:316, SURVEY B-5), and the parent's in-place ``uprelu`` then acts on the
+      whole concatenation: the buffer therefore stores relu(leaky(x)) = relu(x) next to relu(up-path);
+    * down path: conv -> norm -> LeakyReLU fused per level; up path: convT -> norm -> ReLU (-> dropout)."""
 
     def __init__(self, input_nc, output_nc, num_downs, ngf=64, norm_layer=nn.BatchNorm2d, use_dropout=False):
         super(UnetGenerator, self).__init__()
@@ -274,8 +282,61 @@ class UnetGenerator(nn.Module):
         self.model = UnetSkipConnectionBlock(output_nc, ngf, input_nc=input_nc, submodule=block, outermost=True,
                                              norm_layer=norm_layer)
 
+    def _levels(self):
+        """[(downconv, downnorm, upconv, upnorm, dropout)] from the outermost block inwards."""
+        levels, b = [], self.model
+        while b is not None:
+            mods = list(b.model.children())
+            sub = [m for m in mods if isinstance(m, UnetSkipConnectionBlock)]
+            down = [m for m in mods if isinstance(m, nn.Conv2d)][0]
+            up = [m for m in mods if isinstance(m, nn.ConvTranspose2d)][0]
+            norms = [m for m in mods if isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d))]
+            drop = [m for m in mods if isinstance(m, nn.Dropout)]
+            downnorm = upnorm = None
+            if b.outermost:
+                pass
+            elif b.innermost:
+                upnorm = norms[0]
+            else:
+                downnorm, upnorm = norms[0], norms[1]
+            levels.append((down, downnorm, up, upnorm, drop[0] if drop else None))
+            b = sub[0] if sub else None
+        return levels
+
+    def _body(self, tape, x):
+        lv = self._levels()
+        L = len(lv)
+        n = x.shape[0]
+        img = tape.input_nchw(x, first_conv=lv[0][0], want_grad=tape.input_wants[0])
+        # ---- down path: d[j] = LeakyReLU(norm_j(conv_j(d[j-1]))); skips[j] = concat buffer read by upconv_{j-1}
+        cur = img
+        skips = [None] * L
+        for j in range(L - 1):
+            down, downnorm = lv[j][0], lv[j][1]
+            cur = tape.stage(cur, down, downnorm, ACT_LEAKY, 0.2)
+            _, h, w, _ = cur.t.shape
+            c = cur.c
+            cat = tape.concat_buffer(n, h, w, 2 * c)
+            tape.norm_act(cur, None, ACT_RELU, out=cat.slice(0, c))     # relu(leaky(x)) half of the skip
+            skips[j + 1] = cat
+        # ---- innermost: relu(downconv(.)) -> upconv -> upnorm
+        down, _, up, upnorm, _ = lv[L - 1]
+        inner = tape.stage(cur, down, None, ACT_RELU)
+        c = skips[L - 1].c // 2
+        tape.stage(inner, up, upnorm, ACT_RELU, out=skips[L - 1].slice(c, 2 * c))
+        # ---- up path
+        for j in range(L - 2, 0, -1):
+            _, _, up, upnorm, drop = lv[j]
+            c = skips[j].c // 2
+            dst = skips[j].slice(c, 2 * c)
+            tape.stage(skips[j + 1], up, upnorm, ACT_RELU, out=dst)
+            if drop is not None:
+                tape.dropout(dst, float(drop.p))
+        out, slot = tape.stage(skips[1], lv[0][2], None, ACT_TANH, out_nchw=True)
+        return [out], [slot], [img]
+
     def forward(self, input):
-        raise NotImplementedError("cdb200: UnetGenerator execution is not implemented yet (no fallback path)")
+        return graph.run(self, self._body, [input])[0]
 
 
 class UnetSkipConnectionBlock(nn.Module):
@@ -306,4 +367,4 @@ class UnetSkipConnectionBlock(nn.Module):
         self.model = nn.Sequential(*model)
 
     def forward(self, x):
-        raise NotImplementedError("cdb200: UnetSkipConnectionBlock runs only inside a fused UnetGenerator")
+        raise RuntimeError("UnetSkipConnectionBlock runs as part of a fused cdb200 network (UnetGenerator.forward)")

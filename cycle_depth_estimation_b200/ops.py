@@ -137,9 +137,9 @@ def _p(t):
 
 
 def norm_desc(norm, act, slope, eps, channels, pad, stats=None, gamma=None, beta=None, running_mean=None,
-              running_var=None, use_running=False, update_running=False, momentum=0.1):
+              running_var=None, use_running=False, update_running=False, momentum=0.1, flags=0):
     return CdbNormDesc(norm, act, slope, eps, channels, pad, 1 if use_running else 0, 1 if update_running else 0,
-                       momentum, 0, stats.data_ptr() if stats is not None else None,
+                       momentum, flags, stats.data_ptr() if stats is not None else None,
                        gamma.data_ptr() if gamma is not None else None,
                        beta.data_ptr() if beta is not None else None,
                        running_mean.data_ptr() if running_mean is not None else None,
@@ -254,3 +254,114 @@ def depth_metrics(gt, pred):
     check(L.cdb_depth_metrics(_p(gt), _p(pred), n, h, w, _p(out), C.c_void_p(ws.data_ptr() + off),
                               C.c_size_t(need), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K5 / K6b: small NHWC kernels and the seg/depth losses (csrc/pointwise.cu, seg_depth_losses.cu)
+# ---------------------------------------------------------------------------------------------
+EP_STATS_BATCH = 1
+NORM_FLAG_ACT_FIRST, NORM_FLAG_ACCUM_F32 = 1, 2
+
+
+def conv2d_fwd_ex(g, x, wpacked, rows_pad, kpad, out, bias=None, act=ACT_NONE, slope=0.0, stats=None,
+                  stats_batch=False):
+    """conv2d_fwd with the statistics accumulated into ONE group [c][2] (BatchNorm) when stats_batch."""
+    _require_cuda(x, wpacked)
+    xv = act_view(x)
+    ep = CdbEpilogue(bias.data_ptr() if bias is not None else None, act, slope,
+                     stats.data_ptr() if stats is not None else None, EP_STATS_BATCH if stats_batch else 0)
+    check(_lib.lib().cdb_conv2d_fwd(C.byref(g), C.byref(xv), C.c_void_p(wpacked.data_ptr()), rows_pad, kpad,
+                                    C.byref(out), C.byref(ep), _stream()))
+
+
+def _v(t):
+    return C.byref(act_view(t))
+
+
+def add(a, b, out):
+    _require_cuda(a, b, out)
+    check(_lib.lib().cdb_add(_v(a), _v(b), _v(out), _stream()))
+
+
+def cast(src, dst, accumulate=False):
+    _require_cuda(src, dst)
+    check(_lib.lib().cdb_cast(_v(src), _v(dst), 1 if accumulate else 0, _stream()))
+
+
+def avgpool2_fwd(x, out):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_avgpool2_fwd(_v(x), _v(out), _stream()))
+
+
+def avgpool2_bwd(dout, dx):
+    _require_cuda(dout, dx)
+    check(_lib.lib().cdb_avgpool2_bwd(_v(dout), _v(dx), _stream()))
+
+
+def gate_fwd(base, s, att_sum, c_real, inv_hw, out):
+    _require_cuda(s, att_sum, out)
+    check(_lib.lib().cdb_gate_fwd(_v(base) if base is not None else None, _v(s), _p(att_sum), c_real,
+                                  C.c_float(inv_hw), _v(out), _stream()))
+
+
+def gate_bwd(g, s, att_sum, c_real, inv_hw, ds, dsum):
+    _require_cuda(g, s, att_sum, ds, dsum)
+    check(_lib.lib().cdb_gate_bwd(_v(g), _v(s), _p(att_sum), c_real, C.c_float(inv_hw), _v(ds), _p(dsum), _stream()))
+
+
+def gate_bcast(dsum, att_sum, c_real, inv_hw, dt):
+    _require_cuda(dsum, att_sum, dt)
+    check(_lib.lib().cdb_gate_bcast(_p(dsum), _p(att_sum), c_real, C.c_float(inv_hw), _v(dt), _stream()))
+
+
+def bilinear2x_fwd(x, out):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_bilinear2x_fwd(_v(x), _v(out), _stream()))
+
+
+def bilinear2x_bwd(dout, dx):
+    _require_cuda(dout, dx)
+    check(_lib.lib().cdb_bilinear2x_bwd(_v(dout), _v(dx), _stream()))
+
+
+def prelu_fwd(x, slope, out):
+    _require_cuda(x, slope, out)
+    check(_lib.lib().cdb_prelu_fwd(_v(x), _p(slope), _v(out), _stream()))
+
+
+def prelu_bwd(x, g, slope, dx, dslope):
+    _require_cuda(x, g, slope, dx)
+    check(_lib.lib().cdb_prelu_bwd(_v(x), _v(g), _p(slope), _v(dx), _p(dslope), _stream()))
+
+
+def dropout(x, out, seed, p_drop):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_dropout(_v(x), _v(out), C.c_uint64(seed), C.c_float(p_drop), _stream()))
+
+
+def nhwc_to_nchw(x, c_real, dst):
+    """bf16 NHWC view -> fp32 NCHW tensor [N,c_real,H,W] (any strides)."""
+    _require_cuda(x, dst)
+    assert dst.dtype == torch.float32 and dst.dim() == 4
+    check(_lib.lib().cdb_nhwc_to_nchw(_v(x), c_real, _p(dst), C.c_int64(dst.stride(0)), C.c_int64(dst.stride(1)),
+                                      C.c_int64(dst.stride(2)), C.c_int64(dst.stride(3)), _stream()))
+
+
+def loss_ce2d(logits, labels, ignore_index, acc2, grad=None):
+    """logits fp32 [N,C,H,W] contiguous, labels int64 [N,H,W]; acc2 (zeroed) receives (loss sum, count)."""
+    _require_cuda(logits, labels, acc2)
+    assert logits.is_contiguous() and logits.dtype == torch.float32
+    assert labels.is_contiguous() and labels.dtype == torch.int64
+    n, c, h, w = logits.shape
+    check(_lib.lib().cdb_loss_ce2d(_p(logits), _p(labels), n, c, C.c_int64(h * w), C.c_int64(ignore_index),
+                                   _p(acc2), _p(grad), _stream()))
+
+
+def loss_bcedep(x, target, l1_weight, loss_acc, grad=None):
+    """x fp32 [B,1,H,W], target fp32 [B,K,H,W] (both contiguous)."""
+    _require_cuda(x, target, loss_acc)
+    assert x.is_contiguous() and target.is_contiguous() and x.dtype == torch.float32 and target.dtype == torch.float32
+    b, k, h, w = target.shape
+    assert x.shape == (b, 1, h, w)
+    check(_lib.lib().cdb_loss_bcedep(_p(x), _p(target), b, k, C.c_int64(h * w), C.c_float(l1_weight), _p(loss_acc),
+                                     _p(grad), _stream()))

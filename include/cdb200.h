@@ -87,8 +87,10 @@ typedef struct CdbEpilogue {
   int32_t act;
   float slope;
   float* stats;      /* optional [n][c][2] fp32 (sum, sum of squares) accumulated with atomics, or NULL */
-  int64_t reserved;
+  int64_t flags;     /* CDB_EP_* */
 } CdbEpilogue;
+/* stats is ONE group [c][2] for the whole batch (BatchNorm) instead of one per image */
+enum { CDB_EP_STATS_BATCH = 1 };
 
 /* ---- library ------------------------------------------------------------------------------ */
 int cdb_version(void);
@@ -138,13 +140,19 @@ typedef struct CdbNormDesc {
   int32_t use_running;    /* eval-mode batch norm: normalise with running_mean / running_var */
   int32_t update_running; /* training-mode batch norm: also update the running statistics */
   float momentum;
-  int32_t reserved;
+  int32_t flags;          /* CDB_NORM_FLAG_* */
   const float* stats;     /* [groups][channels][2] sums (sum, sum of squares); groups = n (instance) or 1 */
   const float* gamma;     /* [channels] or NULL */
   const float* beta;      /* [channels] or NULL */
   float* running_mean;    /* [channels] or NULL */
   float* running_var;     /* [channels] or NULL */
 } CdbNormDesc;
+/* ACT_FIRST: the layer is conv -> act -> norm (new_multi/networks5_ds.py:636-638,661-676): y is the
+ *   ACTIVATED convolution output (the conv epilogue applied `act`), forward = norm only, backward
+ *   multiplies the gradient w.r.t. y by act'(y) so that dy is the gradient of the raw convolution.
+ * ACCUM_F32: backward only: dy is an fp32 view and receives dy += value (dense-block concatenation
+ *   gradients, new_multi/networks5_ds.py:122-146, summed over all consumers of a channel prefix). */
+enum { CDB_NORM_FLAG_ACT_FIRST = 1, CDB_NORM_FLAG_ACCUM_F32 = 2 };
 
 /* stats[g][c][2] += (sum, sum of squares) of y over pixels; g = image if per_image else 0. */
 int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_image, float* stats, cdbStream_t stream);
@@ -185,6 +193,50 @@ int cdb_loss_bce_const(const float* x, int64_t numel, float target, float weight
 int cdb_loss_l1(const float* a, const float* b, int64_t numel, float weight, float* loss_acc, float* grad_a,
                 cdbStream_t stream);
 int cdb_scale_by_scalar(const float* a, const float* scalar, float* out, int64_t numel, cdbStream_t stream);
+
+/* ---- K5: small NHWC kernels of the seg/depth networks and the U-Net skip topology ---------------
+ * (new_multi/networks5_ds.py; models/networks.py:266-316).  All views are bf16 NHWC unless stated. */
+/* out = a + b (gradient accumulation at fan-out points; residual / attention adds :337,649,700). */
+int cdb_add(const CdbAct* a, const CdbAct* b, const CdbAct* out, cdbStream_t stream);
+/* fp32 <-> bf16 view conversion (dense-block gradient accumulators); accumulate: dst(f32) += src(bf16). */
+int cdb_cast(const CdbAct* src, const CdbAct* dst, int32_t accumulate, cdbStream_t stream);
+/* nn.AvgPool2d(2, 2) (networks5_ds.py:355) and its backward (dx has the shape of the pooling input). */
+int cdb_avgpool2_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream);
+int cdb_avgpool2_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_t stream);
+/* Channel attention (networks5_ds.py:641-649,696-700):  out = [base +] sigmoid(att_sum[n][c][0]*inv_hw) * s
+ * where att_sum are the per-image channel sums (cdb_channel_stats layout [n][c][2]) of the tensor that
+ * nn.AdaptiveAvgPool2d(1) averages.  Backward: ds = g * sigmoid(.), dsum[n][c] += sum_px g*s, and
+ * cdb_gate_bcast writes dt[n,h,w,c] = dsum[n][c] * sigmoid'(.) * inv_hw (gradient of the pooled tensor). */
+int cdb_gate_fwd(const CdbAct* base, const CdbAct* s, const float* att_sum, int32_t c_real, float inv_hw,
+                 const CdbAct* out, cdbStream_t stream);
+int cdb_gate_bwd(const CdbAct* g, const CdbAct* s, const float* att_sum, int32_t c_real, float inv_hw,
+                 const CdbAct* ds, float* dsum, cdbStream_t stream);
+int cdb_gate_bcast(const float* dsum, const float* att_sum, int32_t c_real, float inv_hw, const CdbAct* dt,
+                   cdbStream_t stream);
+/* nn.UpsamplingBilinear2d(scale_factor=2) == align_corners=True (networks5_ds.py:637,713). */
+int cdb_bilinear2x_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream);
+int cdb_bilinear2x_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_t stream);
+/* nn.PReLU() with one learnable slope read from device memory (networks5_ds.py:498,551); *dslope += .. */
+int cdb_prelu_fwd(const CdbAct* x, const float* slope, const CdbAct* out, cdbStream_t stream);
+int cdb_prelu_bwd(const CdbAct* x, const CdbAct* g, const float* slope, const CdbAct* dx, float* dslope,
+                  cdbStream_t stream);
+/* nn.Dropout(p) (models/networks.py:305-306): out = x * keep / (1-p), keep = hash(seed, index) >= p.
+ * Calling it again on the gradient with the same seed is the backward pass. */
+int cdb_dropout(const CdbAct* x, const CdbAct* out, uint64_t seed, float p_drop, cdbStream_t stream);
+/* NHWC bf16 view -> NCHW fp32 tensor (module outputs), dst strides in elements. */
+int cdb_nhwc_to_nchw(const CdbAct* x, int32_t c_real, float* dst, int64_t d_n, int64_t d_c, int64_t d_h,
+                     int64_t d_w, cdbStream_t stream);
+
+/* ---- K6b: losses of the seg/depth step ---------------------------------------------------------------
+ * torch.nn.CrossEntropyLoss(ignore_index) on [n][c][hw] logits (new_multi/model5.py:281): acc2[0] += sum of
+ * the per-pixel losses, acc2[1] += number of non-ignored pixels; grad = softmax - onehot (unscaled). */
+int cdb_loss_ce2d(const float* logits, const int64_t* labels, int32_t n, int32_t c, int64_t hw,
+                  int64_t ignore_index, float* acc2, float* grad, cdbStream_t stream);
+/* BCEDepLoss (new_multi/networks5_ds.py:947-956) with o_m = (target == 1), z_m = (target == -1)
+ * (get_masks :973-982): x [b][1][hw] broadcast against target [b][k][hw]; *loss_acc += loss,
+ * grad_x = d loss / d x. */
+int cdb_loss_bcedep(const float* x, const float* target, int32_t b, int32_t k, int64_t hw, float l1_weight,
+                    float* loss_acc, float* grad_x, cdbStream_t stream);
 
 /* torch.optim.Adam step (no amsgrad / weight decay) on one fp32 tensor (models/cycle_gan_model.py:66-69). */
 int cdb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,

@@ -293,3 +293,48 @@ class CycleGANStepOracle:
                     self.opt_D.step()
         self.fake_A, self.fake_B, self.rec_A, self.rec_B = fake_A, fake_B, rec_A, rec_B
         return {k: float(v) for k, v in L.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# pix2pix training step (models/pix2pix_model.py)
+# ------------------------------------------------------------------------------------------------
+class Pix2PixStepOracle:
+    """Restated glue of Pix2PixModel (models/pix2pix_model.py:24-111): U-Net generator, PatchGAN on
+    cat(A, B) with BatchNorm + sigmoid, BCE GAN loss + lambda_L1 * L1, Adam; D first (:101-105), then G
+    (:107-111). pool_size is 0 in the reference defaults (:16), so the pool returns its input."""
+
+    def __init__(self, sd_G, sd_D, num_downs=8, lr=2e-4, beta1=0.5, lambda_L1=100.0, use_lsgan=False):
+        is_param = lambda k, v: v.is_floating_point() and 'running_' not in k
+        mk = lambda sd: {k: v.detach().clone().requires_grad_(is_param(k, v)) for k, v in sd.items()}
+        self.G, self.D = mk(sd_G), mk(sd_D)
+        self.num_downs, self.lambda_L1, self.use_lsgan = num_downs, lambda_L1, use_lsgan
+        params = lambda d: [p for p in d.values() if p.requires_grad]
+        self.D_params = params(self.D)
+        self.opt_G = torch.optim.Adam(params(self.G), lr=lr, betas=(beta1, 0.999))
+        self.opt_D = torch.optim.Adam(params(self.D), lr=lr, betas=(beta1, 0.999))
+        self.losses = {}
+
+    def _d(self, x):
+        return nlayer_discriminator(self.D, x, 'batch', use_sigmoid=not self.use_lsgan)
+
+    def step(self, real_A, real_B, apply_updates=True, dropout_masks=None):
+        L = self.losses
+        fake_B = unet_generator(self.G, real_A, self.num_downs, 'batch', True, dropout_masks)
+        for p in self.D_params:
+            p.requires_grad_(True)
+        self.opt_D.zero_grad()
+        L['D_fake'] = gan_loss(self._d(torch.cat((real_A, fake_B), 1).detach()), False, self.use_lsgan)
+        L['D_real'] = gan_loss(self._d(torch.cat((real_A, real_B), 1)), True, self.use_lsgan)
+        ((L['D_fake'] + L['D_real']) * 0.5).backward()
+        if apply_updates:
+            self.opt_D.step()
+        for p in self.D_params:
+            p.requires_grad_(False)
+        self.opt_G.zero_grad()
+        L['G_GAN'] = gan_loss(self._d(torch.cat((real_A, fake_B), 1)), True, self.use_lsgan)
+        L['G_L1'] = l1(fake_B, real_B) * self.lambda_L1
+        (L['G_GAN'] + L['G_L1']).backward()
+        if apply_updates:
+            self.opt_G.step()
+        self.fake_B = fake_B
+        return {k: float(v.detach()) for k, v in L.items()}

@@ -37,4 +37,5 @@ def seeded_image(n, c, h, w, seed=1234, device="cuda"):
 
 def leaf_state(module):
     """state_dict of leaf tensors requiring grad, keyed like the reference, sharing no storage."""
-    return {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in module.state_dict().items()}
+    return {k: v.detach().clone().requires_grad_(v.is_floating_point() and 'running_' not in k)
+            for k, v in module.state_dict().items()}
