@@ -145,9 +145,9 @@ class Tape:
         full = buf if slack_w == 0 else buf[:, :, :w + 2 * halo, :]
         return Val(t, c, full, halo, halo_kind if halo else None)
 
-    def concat_buffer(self, n, h, w, c, f32grad=False, stats=False):
+    def concat_buffer(self, n, h, w, c, f32grad=False, stats=False, halo=0, halo_kind=None):
         """Preallocated concatenation buffer whose channel slices are written by the producers."""
-        v = self.new_val(n, h, w, c)
+        v = self.new_val(n, h, w, c, halo, halo_kind)
         if f32grad and self.record:
             v.grad32 = torch.zeros((n, h, w, ops.round_up(c, 8)), dtype=torch.float32, device=self.dev)
         if stats:
@@ -155,7 +155,7 @@ class Tape:
         return v
 
     # ---------------------------------------------------------------- module boundary
-    def input_nchw(self, x, pad=0, pad_kind=None, first_conv=None, want_grad=False):
+    def input_nchw(self, x, pad=0, pad_kind=None, first_conv=None, want_grad=False, out=None):
         """fp32 NCHW tensor -> Val (with the first convolution's padding materialised). Returns the Val;
         the gradient w.r.t. x (fp32 NCHW) is produced by input_grad() during the backward replay."""
         if not x.is_cuda:
@@ -180,12 +180,20 @@ class Tape:
             ops.nchw_to_nhwc(x, t, pad=p0 if kind == 'reflect' else 0)
             v = Val(t, c, buf, p0, kind if p0 else None)
             v.rowpack = rp
+        elif out is not None:
+            v = out
+            ops.nchw_to_nhwc(x, v.t, pad=0)
+            self._fill_stats(v)
         else:
             v = self.new_val(n, h, w, c, pad, pad_kind)
             ops.nchw_to_nhwc(x, v.t, pad=pad if pad_kind == 'reflect' else 0)
         v.is_input = True
         v.want_grad = want_grad
         return v
+
+    def _fill_stats(self, v):
+        if v.stats is not None:
+            ops.channel_stats(v.t, v.c, False, v.stats)
 
     def input_grad(self, v, shape):
         """fp32 NCHW gradient of a network input (after the backward replay)."""
@@ -516,10 +524,11 @@ class Tape:
         return outv
 
     # ---------------------------------------------------------------- pooling / resampling / gates
-    def avgpool2(self, x):
+    def avgpool2(self, x, out=None):
         n, h, w, _ = x.t.shape
-        outv = self.new_val(n, h // 2, w // 2, x.c)
+        outv = out if out is not None else self.new_val(n, h // 2, w // 2, x.c)
         ops.avgpool2_fwd(x.t, outv.t)
+        self._fill_stats(outv)
         if self.record:
             def backward():
                 g = self.total_grad(outv)
@@ -546,7 +555,7 @@ class Tape:
             self.back.append(backward)
         return outv
 
-    def gate(self, base, s, att, halo=0, halo_kind=None):
+    def gate(self, base, s, att, halo=0, halo_kind=None, out=None):
         """out = [base +] sigmoid(mean_hw(att)) * s  (nn.AdaptiveAvgPool2d(1) + nn.Sigmoid + torch.mul [+ add],
         networks5_ds.py:641-649 and :696-700)."""
         n, h, w, _ = s.t.shape
@@ -556,7 +565,7 @@ class Tape:
         sums = torch.zeros((n, c, 2), dtype=torch.float32, device=self.dev)
         ops.channel_stats(att.t, c, True, sums)
         inv = 1.0 / float(ha * wa)
-        outv = self.new_val(n, h, w, c, halo, halo_kind)
+        outv = out if out is not None else self.new_val(n, h, w, c, halo, halo_kind)
         ops.gate_fwd(base.t if base is not None else None, s.t, sums, c, inv, outv.t)
         if self.record:
             def backward():

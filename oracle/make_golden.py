@@ -113,6 +113,50 @@ def make_metrics(E):
     return dict(pairs=pairs, rows=rows)
 
 
+def make_networks5(N5):
+    """Outputs of the reference's own G_1 / General_net / R_dep / _Discriminator classes (CPU, training-mode
+    BatchNorm) on name-keyed synthetic weights (networks5_oracle.synth_state_dict) at small spatial sizes."""
+    import builtins
+    from oracle import networks5_oracle as O5
+    fx = {}
+    real_print = builtins.print
+    builtins.print = lambda *a, **k: None       # R_dep.forward prints (networks5_ds.py:791)
+    try:
+        def load(net, seed):
+            sd = O5.synth_state_dict(net.state_dict(), seed)
+            if 'model.10.weight' in sd and 'model.1.weight' in sd:   # the shared nn.PReLU of _Discriminator
+                sd['model.1.weight'] = sd['model.10.weight']
+            net.load_state_dict(sd, strict=True)
+            return net.train()
+        g1 = load(N5.G_1(), 1)
+        x = image(2, 3, 32, 64, 31)
+        ss = g1(x)
+        fx['g1'] = dict(x=x, out=ss.detach())
+        g2 = load(N5.General_net(), 2)
+        head_s, feats_s = g2(ss.detach(), 'S')
+        xr = image(2, 3, 32, 64, 32)
+        head_r, feats_r = g2(xr, 'R')
+        fx['g2_S'] = dict(head=head_s.detach(), feat_means=[float(f.mean()) for f in feats_s],
+                          feat_abs=[float(f.abs().mean()) for f in feats_s], feat3=feats_s[3].detach())
+        fx['g2_R'] = dict(x=xr, head=head_r.detach(), feat_abs=[float(f.abs().mean()) for f in feats_r])
+        rd = load(N5.R_dep(), 3)
+        feats, seg, (dep4, dep1) = rd(feats_s, head_s.detach())
+        fx['rd'] = dict(out0=feats[0].detach(), out1=feats[1].detach(), out2=feats[2].detach()[:, :, ::2, ::2],
+                        seg=seg.detach()[:, :, ::2, ::2], dep4=[d.detach() for d in dep4], dep1=dep1.detach())
+        fd = load(N5._Discriminator(input_nc=128), 4)
+        xd = image(2, 128, 32, 64, 33)
+        fx['fd'] = dict(x=xd, out=fd(xd).detach())
+        t = image(2, 4, 8, 8, 34)
+        t[t > 0.5] = 1.0
+        t[t < -0.5] = -1.0
+        o_m, z_m = N5.get_masks(t)
+        xin = torch.tanh(image(2, 1, 8, 8, 35))
+        fx['bcedep'] = dict(x=xin, t=t, o_m=o_m, z_m=z_m, loss=float(N5.BCEDepLoss()(xin, t, o_m, z_m)))
+    finally:
+        builtins.print = real_print
+    return fx
+
+
 def main():
     if not available():
         raise SystemExit("reference not found at %s" % REF)
@@ -123,6 +167,10 @@ def main():
     torch.save(make_networks(N), os.path.join(OUT, "networks.pt"))
     torch.save(make_pool(P), os.path.join(OUT, "image_pool.pt"))
     torch.save(make_metrics(E), os.path.join(OUT, "metrics.pt"))
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    N5 = load_ref("ref_networks5_ds", "new_multi/networks5_ds.py")
+    torch.save(make_networks5(N5), os.path.join(OUT, "networks5.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
