@@ -327,6 +327,164 @@ def b200_arm(args):
         dist.destroy_process_group()
 
 
+
+# ---------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE configs[0], [2], [3], [4]): same JSON schema, selected with --workload
+# ---------------------------------------------------------------------------------------------------
+def _time_steps(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _model5_batch(b, h, w, seed):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(s, generator=g) * 2 - 1
+    seg_syn = torch.randint(0, 28, (b, 1, h, w), generator=g)
+    seg_real = torch.randint(0, 28, (b, 1, h, w), generator=g)
+    seg_real[torch.rand((b, 1, h, w), generator=g) < 0.02] = 255
+    dls = r(b, 4, h, w)
+    dls[dls > 0.9] = 1.0
+    dls[dls < -0.9] = -1.0
+    return {'img_real': r(b, 3, h, w), 'img_syn': r(b, 3, h, w), 'seg_l_real': seg_real, 'seg_l_syn': seg_syn,
+            'dep_l_syn': r(b, 1, h, w), 'depth_l_s': dls}
+
+
+def secondary_arm(args):
+    """pix2pix step (configs[2]), seg/depth step (configs[3]), generator inference (configs[0]), depth metrics
+    (configs[4]) on one GPU. FLOP / byte figures: SURVEY 8(d)."""
+    import contextlib
+    import io
+    import random
+    import numpy as np
+    from cycle_depth_estimation_b200 import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    lib = _lib.lib()
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    random.seed(1234)
+    wl = args.workload
+    sampler = ClockSampler(0)
+    launches0 = lib.cdb_launch_count()
+    extra = {}
+    if wl == "pix2pix":
+        from cycle_depth_estimation_b200.pix2pix_model import Pix2PixModel
+        b = args.batch if args.batch != 8 else 16
+        opt = argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='unet_256', netD='basic', n_layers_D=3,
+                                 norm='batch', no_dropout=False, init_type='normal', init_gain=0.02, no_lsgan=True,
+                                 pool_size=0, lr=2e-4, beta1=0.5, lambda_L1=100.0, isTrain=True, device='cuda',
+                                 direction='AtoB')
+        model = Pix2PixModel()
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.initialize(opt)
+        a, bb = synthetic_batch(b, 256, 1234)
+        host = {'A': a.pin_memory(), 'B': bb.pin_memory(), 'A_paths': None}
+        dev = {'A': a.cuda(), 'B': bb.cuda(), 'A_paths': None}
+
+        def step():
+            model.set_input(dev)
+            model.optimize_parameters()
+
+        def step_e2e():
+            model.set_input(host)
+            model.optimize_parameters()
+            return model.get_current_losses()
+        ms = _time_steps(step, args.steps, args.warmup)
+        ms_e2e = _time_steps(step_e2e, args.steps, 1)
+        tflop = 1.391 * b / 16.0
+        metric, unit = "pix2pix_train_iters_per_s", "iters/s (batch-%d training steps at 256x256)" % b
+        workload = ("pix2pix training step: UnetGenerator unet_256 (BatchNorm, dropout) + NLayerDiscriminator n_layers=3 on "
+                    "cat(A,B), BCE GAN + 100 L1, Adam; batch %d at 256x256 (BASELINE configs[2])" % b)
+        h2d, d2h = int(a.numel() * 4 * 2), 16
+    elif wl == "model5":
+        from cycle_depth_estimation_b200.model5 import Seg_Depth
+        b = args.batch
+        model = Seg_Depth()
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.initialize(argparse.Namespace(lr=2e-4, beta1=0.5, pool_size=50))
+        data = _model5_batch(b, 192, 640, 90)
+        host = {k: v.pin_memory() for k, v in data.items()}
+        dev = {k: v.cuda() for k, v in data.items()}
+
+        def step():
+            model.set_input(dev, 'train')
+            model.optimize_parameters('train')
+
+        def step_e2e():
+            model.set_input(host, 'train')
+            model.optimize_parameters('train')
+            return model.get_current_losses()
+        ms = _time_steps(step, args.steps, args.warmup)
+        ms_e2e = _time_steps(step_e2e, args.steps, 1)
+        tflop = 3.251 * b
+        metric, unit = "seg_depth_train_iters_per_s", "iters/s (batch-%d training steps at 192x640)" % b
+        workload = ("new_multi model5 step: G_1 + General_net + R_dep + 3 feature discriminators, CE + L1 + BCEDep + "
+                    "LSGAN, 8 optimizer updates; batch %d at 192x640 (BASELINE configs[3])" % b)
+        h2d, d2h = int(sum(v.numel() * v.element_size() for v in data.values())), 32
+    elif wl == "g_infer":
+        from cycle_depth_estimation_b200 import networks as N
+        b = args.batch if args.batch != 8 else 1
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cuda']).eval()
+        a, _ = synthetic_batch(b, 256, 1234)
+        host, dev = a.pin_memory(), a.cuda()
+        with torch.no_grad():
+            ms = _time_steps(lambda: net(dev), args.steps, args.warmup)
+            ms_e2e = _time_steps(lambda: net(host.cuda(non_blocking=True)).cpu(), args.steps, 1)
+        tflop = 0.0991 * b
+        metric, unit = "resnet9_generator_img_per_s", "img/s (256x256 forward, batch %d)" % b
+        workload = "ResnetGenerator resnet_9blocks ngf=64 InstanceNorm forward, batch %d, 256x256 (BASELINE configs[0])" % b
+        h2d, d2h = int(a.numel() * 4), int(a.numel() * 4)
+        extra["images_per_step"] = b
+    elif wl == "metrics":
+        from cycle_depth_estimation_b200 import my_eval
+        n_img, h, w = 697, 375, 1242
+        rng = np.random.default_rng(2019)
+        gt = rng.integers(0, 80, (n_img, h, w), dtype=np.uint8)
+        gt[rng.random((n_img, h, w)) < 0.3] = 0
+        pred = rng.integers(0, 256, (n_img, h, w), dtype=np.uint8)
+        hg, hp = torch.from_numpy(gt).pin_memory(), torch.from_numpy(pred).pin_memory()
+        dg, dp = hg.cuda(), hp.cuda()
+        from cycle_depth_estimation_b200 import ops
+        ms = _time_steps(lambda: ops.depth_metrics(dg, dp), args.steps, args.warmup)
+        ms_e2e = _time_steps(lambda: my_eval.eval_metric_arrays(hg, hp), args.steps, 1)
+        tflop = 0.0
+        metric, unit = "depth_metrics_img_per_s", "images/s (375x1242 uint8 pairs, 7 metrics each)"
+        workload = "my_eval.py depth metrics over 697 synthetic 375x1242 KITTI Eigen-split pairs (BASELINE configs[4])"
+        h2d, d2h = int(2 * n_img * h * w), 697 * 8 * 8
+        extra["images_per_step"] = n_img
+        extra["algorithmic_gb_per_s"] = 2.0 * n_img * h * w / (ms * 1e-3) / 1e9
+        extra["frac_of_hbm_peak"] = extra["algorithmic_gb_per_s"] / peaks["hbm"]
+    else:
+        raise SystemExit("unknown workload " + wl)
+    launches = lib.cdb_launch_count() - launches0
+    clocks = sampler.stop()
+    per_step = extra.get("images_per_step", 1)
+    line = {
+        "metric": metric, "value": per_step * 1e3 / ms, "unit": unit, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f64" if wl == "metrics" else "bf16", "data": "synthetic",
+        "config": dict({"workload": workload, "l2": "inputs + saved activations exceed the 126 MB L2; no explicit flush",
+                        "algorithmic_tflop_per_step": tflop,
+                        "step_tflops": tflop / (ms * 1e-3) if tflop else None,
+                        "step_frac_of_sustained_bf16_peak": tflop / (ms * 1e-3) / peaks["bf16_sustained"] if tflop else None,
+                        "device_abort_flag": lib.cdb_device_abort_flag()}, **extra),
+        "e2e": {"value": per_step * 1e3 / ms_e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,9 +494,13 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cyclegan", choices=["cyclegan", "pix2pix", "model5", "g_infer", "metrics"],
+                    help="cyclegan (default, the headline metric) or one of the secondary BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload != "cyclegan":
+        secondary_arm(args)
     else:
         b200_arm(args)
 
