@@ -5,13 +5,8 @@
 //   v = (pred - min)/(max - min)*49 + 1;  thr = max(gt/v, v/gt);  a_k = mean(thr < 1.25^k);
 //   rmse = sqrt(mean((gt-v)^2));  rmse_log = sqrt(mean((log(gt)-log(v))^2));
 //   abs_rel = mean(|gt-v|/gt);  sq_rel = mean((gt-v)^2/gt).
-// gt has 48 admissible values and pred 256, so everything is a function of the pair (gt, pred):
-//   pass A  masked min / max / count of pred_u8 (integer, exact)
-//   pass L  per image look-up tables: v[256], log v[256] and, per gt value, the exact pred-index
-//           interval on which each threshold test is true (evaluated in IEEE double with the
-//           reference's operation order and no FMA contraction, so the COUNTS are bit-exact)
-//   pass B  stream the two byte planes once more (16 pixels per 128-bit load) and accumulate
-//   pass F  deterministic reduction of the per-block partials
+// gt has 48 admissible values and pred 256, so everything is a function of the pair (gt, pred): see
+// metrics_hist_kernel below (one pass, joint histogram in shared memory).
 // np.log of a uint8 array is computed in float16 by numpy; kLogU8 holds
 // numpy's own values.
 #include "common.cuh"
@@ -54,103 +49,19 @@ __constant__ float kLogU8[256] = {
     5.5234375f, 5.52734375f, 5.53125f, 5.53515625f, 5.5390625f, 5.54296875f
 };
 
-struct ImgInfo {
-  int pmin, pmax, count, pad_;
-};
-
-struct ImgLut {
-  float v[256];
-  float lv[256];
-  float gf[64];    // indexed by gt-2 (48 used)
-  float invg[64];
-  float lg[64];
-  uint8_t lo[3][64];
-  uint8_t hi[3][64];
-};
-
-__global__ void metrics_init_kernel(ImgInfo* info, int n_img) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_img) {
-    info[i].pmin = 255;
-    info[i].pmax = 0;
-    info[i].count = 0;
-    info[i].pad_ = 0;
-  }
-}
+// Single pass over HBM: ONE 1024-thread block per image builds the joint histogram H[gt-2][pred]
+// (48 x 256 counters in shared memory, shared-memory atomics) of the masked pixels.  Everything the
+// reference computes per pixel is a function of the pair (gt, pred), so the block then evaluates
+//   pmin / pmax / count            from the occupied histogram columns,
+//   v[p], log v[p]                 in IEEE double with the reference's operation order (no FMA contraction),
+//   sums  = sum_{g,p} H[g][p] * f(g, p)   in double,
+//   a_k   = sum_{g,p} H[g][p] * [max(g / v[p], v[p] / g) < 1.25^k]   (integer counts: bit-exact)
+// and writes the 8 outputs.  Algorithmic traffic = 2 bytes per pixel, read exactly once.
+constexpr int kHistRows = 48;
+constexpr int kHistCells = kHistRows * 256;
+constexpr int kMetricThreads = 1024;
 
 __device__ __forceinline__ bool masked(uint32_t g) { return (g - 2u) < 48u; }
-
-// chunk geometry shared by passes A and B: [begin, end) byte range of one block within an image
-__device__ __forceinline__ void chunk_range(int64_t pixels, int chunk, int chunks, int64_t* b, int64_t* e) {
-  int64_t per = (pixels + chunks - 1) / chunks;
-  per = (per + 15) & ~static_cast<int64_t>(15);
-  *b = static_cast<int64_t>(chunk) * per;
-  *e = *b + per < pixels ? *b + per : pixels;
-  if (*b > pixels) *b = pixels;
-}
-
-__global__ void __launch_bounds__(256)
-metrics_minmax_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int64_t pixels,
-                      ImgInfo* __restrict__ info) {
-  const int img = blockIdx.y;
-  const uint8_t* g = gt + img * pixels;
-  const uint8_t* p = pred + img * pixels;
-  int64_t b, e;
-  chunk_range(pixels, blockIdx.x, gridDim.x, &b, &e);
-  int mn = 255, mx = 0, cnt = 0;
-  // scalar head up to 16-byte alignment of the absolute address, vector body, scalar tail
-  int64_t i = b + threadIdx.x;
-  const int64_t head_end = min(e, b + ((16 - ((reinterpret_cast<uintptr_t>(g) + b) & 15)) & 15));
-  for (; i < head_end; i += 256) {
-    if (masked(g[i])) {
-      mn = min(mn, (int)p[i]);
-      mx = max(mx, (int)p[i]);
-      ++cnt;
-    }
-  }
-  const bool same_align = ((reinterpret_cast<uintptr_t>(g) ^ reinterpret_cast<uintptr_t>(p)) & 15) == 0;
-  int64_t body_end = head_end;
-  if (same_align) {
-    const int64_t nvec = (e - head_end) / 16;
-    body_end = head_end + nvec * 16;
-    for (int64_t vi = threadIdx.x; vi < nvec; vi += 256) {
-      const uint4 gv = *reinterpret_cast<const uint4*>(g + head_end + vi * 16);
-      const uint4 pv = *reinterpret_cast<const uint4*>(p + head_end + vi * 16);
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-      const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t gg = (gw[k] >> (8 * j)) & 255u;
-          const int pp = (pw[k] >> (8 * j)) & 255u;
-          if (masked(gg)) {
-            mn = min(mn, pp);
-            mx = max(mx, pp);
-            ++cnt;
-          }
-        }
-    }
-  }
-  for (i = body_end + threadIdx.x; i < e; i += 256) {
-    if (masked(g[i])) {
-      mn = min(mn, (int)p[i]);
-      mx = max(mx, (int)p[i]);
-      ++cnt;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  if ((threadIdx.x & 31) == 0 && cnt > 0) {
-    atomicMin(&info[img].pmin, mn);
-    atomicMax(&info[img].pmax, mx);
-    atomicAdd(&info[img].count, cnt);
-  }
-}
 
 // pred_u8 -> clip(pred/255*80, 1, 50) exactly as numpy evaluates it (two separate roundings).
 __device__ __forceinline__ double pred_value(int p) {
@@ -160,195 +71,171 @@ __device__ __forceinline__ double pred_value(int p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) metrics_lut_kernel(const ImgInfo* __restrict__ info, ImgLut* __restrict__ lut) {
-  __shared__ double vd[256];
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t g, uint32_t p) {
+  if (masked(g)) atomicAdd(&hist[(g - 2u) * 256u + p], 1u);
+}
+
+__global__ void __launch_bounds__(kMetricThreads)
+metrics_hist_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int64_t pixels,
+                    double* __restrict__ out) {
+  extern __shared__ uint32_t hist[];            // [48][256]
+  __shared__ double vd[256], lvd[256];
+  __shared__ double red[32][8];
+  __shared__ int s_min[32], s_max[32];
+  __shared__ int s_pmin, s_pmax;
+  const int tid = threadIdx.x;
   const int img = blockIdx.x;
-  const int p = threadIdx.x;
-  const ImgInfo inf = info[img];
-  const double lo = pred_value(inf.pmin), hi = pred_value(inf.pmax);
-  // (x - min) / (max - min) * 49 + 1, each operation rounded separately (no FMA)
-  const double v = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(pred_value(p), lo), __dsub_rn(hi, lo)), 49.0), 1.0);
-  vd[p] = v;
-  lut[img].v[p] = static_cast<float>(v);
-  lut[img].lv[p] = static_cast<float>(log(v));
-  __syncthreads();
-  if (p < 48) {
-    const int g = p + 2;
-    const double gd = static_cast<double>(g);
-    lut[img].gf[p] = static_cast<float>(g);
-    lut[img].invg[p] = static_cast<float>(1.0 / gd);
-    lut[img].lg[p] = kLogU8[g];
-    const double thr[3] = {1.25, 1.5625, 1.953125};  // 1.25**k, exact in binary
-#pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      int first = 1, last = 0;
-      bool any = false;
-      for (int q = inf.pmin; q <= inf.pmax; ++q) {
-        const double a = __ddiv_rn(gd, vd[q]), b = __ddiv_rn(vd[q], gd);
-        const double m = fmax(a, b);  // np.maximum propagates NaN; NaN < thr is false either way
-        const bool ok = (a != a || b != b) ? false : (m < thr[t]);
-        if (ok) {
-          if (!any) first = q;
-          last = q;
-          any = true;
-        }
-      }
-      lut[img].lo[t][p] = static_cast<uint8_t>(first);
-      lut[img].hi[t][p] = static_cast<uint8_t>(last);
-    }
-  }
-}
-
-struct Acc {
-  double sq, lg, ar, sr;
-  int n, a1, a2, a3;
-};
-
-__device__ __forceinline__ void accum_pixel(const ImgLut& L, uint32_t g, uint32_t p, float& sq, float& lg, float& ar,
-                                            float& sr, int& n, int& a1, int& a2, int& a3) {
-  if (!masked(g)) return;
-  const int gi = g - 2;
-  const float v = L.v[p];
-  const float d = L.gf[gi] - v;
-  const float dl = L.lg[gi] - L.lv[p];
-  const float ig = L.invg[gi];
-  const float d2 = d * d;
-  sq += d2;
-  lg = fmaf(dl, dl, lg);
-  ar = fmaf(fabsf(d), ig, ar);
-  sr = fmaf(d2, ig, sr);
-  ++n;
-  a1 += (p >= L.lo[0][gi] && p <= L.hi[0][gi]) ? 1 : 0;
-  a2 += (p >= L.lo[1][gi] && p <= L.hi[1][gi]) ? 1 : 0;
-  a3 += (p >= L.lo[2][gi] && p <= L.hi[2][gi]) ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256)
-metrics_accum_kernel(const uint8_t* __restrict__ gt, const uint8_t* __restrict__ pred, int64_t pixels,
-                     const ImgLut* __restrict__ lut, double* __restrict__ partial /*[img][chunks][8]*/) {
-  __shared__ ImgLut L;
-  __shared__ double red[8][8];
-  const int img = blockIdx.y;
-  {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(lut + img);
-    uint32_t* d = reinterpret_cast<uint32_t*>(&L);
-    for (int i = threadIdx.x; i < (int)(sizeof(ImgLut) / 4); i += 256) d[i] = s[i];
-  }
+  for (int i = tid; i < kHistCells; i += kMetricThreads) hist[i] = 0u;
   __syncthreads();
   const uint8_t* g = gt + img * pixels;
   const uint8_t* p = pred + img * pixels;
-  int64_t b, e;
-  chunk_range(pixels, blockIdx.x, gridDim.x, &b, &e);
-  Acc acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0};
-  float sq = 0.f, lg = 0.f, ar = 0.f, sr = 0.f;
-  const int64_t head_end = min(e, b + ((16 - ((reinterpret_cast<uintptr_t>(g) + b) & 15)) & 15));
-  for (int64_t i = b + threadIdx.x; i < head_end; i += 256)
-    accum_pixel(L, g[i], p[i], sq, lg, ar, sr, acc.n, acc.a1, acc.a2, acc.a3);
+  // scalar head up to 16-byte alignment of gt, vector body when pred shares the alignment, scalar tail
+  const int64_t head_end = min(pixels, static_cast<int64_t>((16 - (reinterpret_cast<uintptr_t>(g) & 15)) & 15));
+  for (int64_t i = tid; i < head_end; i += kMetricThreads) hist_add(hist, g[i], p[i]);
   const bool same_align = ((reinterpret_cast<uintptr_t>(g) ^ reinterpret_cast<uintptr_t>(p)) & 15) == 0;
   int64_t body_end = head_end;
   if (same_align) {
-    const int64_t nvec = (e - head_end) / 16;
+    const int64_t nvec = (pixels - head_end) / 16;
     body_end = head_end + nvec * 16;
-    for (int64_t vi = threadIdx.x; vi < nvec; vi += 256) {
-      const uint4 gv = *reinterpret_cast<const uint4*>(g + head_end + vi * 16);
-      const uint4 pv = *reinterpret_cast<const uint4*>(p + head_end + vi * 16);
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-      const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+    const uint4* gv4 = reinterpret_cast<const uint4*>(g + head_end);
+    const uint4* pv4 = reinterpret_cast<const uint4*>(p + head_end);
+    int64_t vi = tid;
+    // two vectors per iteration: four 16-byte loads in flight per thread
+    for (; vi + kMetricThreads < nvec; vi += 2 * kMetricThreads) {
+      const uint4 ga = gv4[vi], pa = pv4[vi];
+      const uint4 gb = gv4[vi + kMetricThreads], pb = pv4[vi + kMetricThreads];
+      const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const uint32_t pw[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hist_add(hist, (gw[k] >> (8 * j)) & 255u, (pw[k] >> (8 * j)) & 255u);
+    }
+    for (; vi < nvec; vi += kMetricThreads) {
+      const uint4 ga = gv4[vi], pa = pv4[vi];
+      const uint32_t gw[4] = {ga.x, ga.y, ga.z, ga.w};
+      const uint32_t pw[4] = {pa.x, pa.y, pa.z, pa.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          accum_pixel(L, (gw[k] >> (8 * j)) & 255u, (pw[k] >> (8 * j)) & 255u, sq, lg, ar, sr, acc.n, acc.a1,
-                      acc.a2, acc.a3);
-      // flush the short fp32 runs into the double accumulators
-      acc.sq += sq;
-      acc.lg += lg;
-      acc.ar += ar;
-      acc.sr += sr;
-      sq = lg = ar = sr = 0.f;
+        for (int j = 0; j < 4; ++j) hist_add(hist, (gw[k] >> (8 * j)) & 255u, (pw[k] >> (8 * j)) & 255u);
     }
   }
-  for (int64_t i = body_end + threadIdx.x; i < e; i += 256)
-    accum_pixel(L, g[i], p[i], sq, lg, ar, sr, acc.n, acc.a1, acc.a2, acc.a3);
-  acc.sq += sq;
-  acc.lg += lg;
-  acc.ar += ar;
-  acc.sr += sr;
-  double vals[8] = {acc.sq, acc.lg, acc.ar, acc.sr, (double)acc.n, (double)acc.a1, (double)acc.a2, (double)acc.a3};
+  for (int64_t i = body_end + tid; i < pixels; i += kMetricThreads) hist_add(hist, g[i], p[i]);
+  __syncthreads();
+
+  // ---- occupied prediction range
+  int mn = 256, mx = -1;
+  if (tid < 256) {
+    uint32_t any = 0u;
+    for (int r = 0; r < kHistRows; ++r) any |= hist[r * 256 + tid];
+    if (any) mn = mx = tid;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) {
+    s_min[warp] = mn;
+    s_max[warp] = mx;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 256, b = -1;
+    for (int w = 0; w < kMetricThreads / 32; ++w) {
+      a = min(a, s_min[w]);
+      b = max(b, s_max[w]);
+    }
+    s_pmin = a;
+    s_pmax = b;
+  }
+  __syncthreads();
+  const int pmin = s_pmin, pmax = s_pmax;
+  if (tid < 256) {
+    // (x - min) / (max - min) * 49 + 1, each operation rounded separately (no FMA)
+    const double lo = pred_value(pmin < 256 ? pmin : 0), hi = pred_value(pmax >= 0 ? pmax : 0);
+    const double v = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(pred_value(tid), lo), __dsub_rn(hi, lo)), 49.0), 1.0);
+    vd[tid] = v;
+    lvd[tid] = log(v);
+  }
+  __syncthreads();
+
+  // ---- sums over the histogram cells
+  double sq = 0.0, lg = 0.0, ar = 0.0, sr = 0.0, cnt = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int i = tid; i < kHistCells; i += kMetricThreads) {
+    const uint32_t c = hist[i];
+    if (c == 0u) continue;
+    const int gi = (i >> 8) + 2, pi = i & 255;
+    const double cd = static_cast<double>(c), gd = static_cast<double>(gi), v = vd[pi];
+    const double d = __dsub_rn(gd, v);
+    const double d2 = __dmul_rn(d, d);
+    const double dl = __dsub_rn(static_cast<double>(kLogU8[gi]), lvd[pi]);
+    sq += cd * d2;
+    lg += cd * __dmul_rn(dl, dl);
+    ar += cd * __ddiv_rn(fabs(d), gd);
+    sr += cd * __ddiv_rn(d2, gd);
+    cnt += cd;
+    const double qa = __ddiv_rn(gd, v), qb = __ddiv_rn(v, gd);
+    const double m = fmax(qa, qb);          // np.maximum propagates NaN; NaN < thr is false either way
+    const bool nan = (qa != qa) || (qb != qb);
+    if (!nan) {
+      if (m < 1.25) a1 += cd;
+      if (m < 1.5625) a2 += cd;
+      if (m < 1.953125) a3 += cd;
+    }
+  }
+  double vals[8] = {sq, lg, ar, sr, cnt, a1, a2, a3};
 #pragma unroll
   for (int k = 0; k < 8; ++k)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0)
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[warp][k] = vals[k];
   __syncthreads();
-  if (threadIdx.x < 8) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    partial[(static_cast<int64_t>(img) * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = s;
+  if (tid == 0) {
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < kMetricThreads / 32; ++w)
+      for (int k = 0; k < 8; ++k) s[k] += red[w][k];
+    const double n = s[4];
+    double* o = out + static_cast<int64_t>(img) * 8;   // {abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, count}
+    o[0] = s[2] / n;
+    o[1] = s[3] / n;
+    o[2] = sqrt(s[0] / n);
+    o[3] = sqrt(s[1] / n);
+    o[4] = s[5] / n;
+    o[5] = s[6] / n;
+    o[6] = s[7] / n;
+    o[7] = n;
   }
 }
-
-// out[img] = {abs_rel, sq_rel, rmse, rmse_log, a1, a2, a3, count}
-__global__ void metrics_finalize_kernel(const double* __restrict__ partial, int chunks, int n_img,
-                                        double* __restrict__ out) {
-  const int img = blockIdx.x * blockDim.x + threadIdx.x;
-  if (img >= n_img) return;
-  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int c = 0; c < chunks; ++c)
-    for (int k = 0; k < 8; ++k) s[k] += partial[(static_cast<int64_t>(img) * chunks + c) * 8 + k];
-  const double n = s[4];
-  double* o = out + static_cast<int64_t>(img) * 8;
-  o[0] = s[2] / n;
-  o[1] = s[3] / n;
-  o[2] = sqrt(s[0] / n);
-  o[3] = sqrt(s[1] / n);
-  o[4] = s[5] / n;
-  o[5] = s[6] / n;
-  o[6] = s[7] / n;
-  o[7] = n;
-}
-
-constexpr int kMetricChunks = 8;
 
 }  // namespace cdb
 
 using namespace cdb;
 
 extern "C" size_t cdb_depth_metrics_workspace(int32_t n_img) {
-  size_t a = (size_t)n_img * sizeof(ImgInfo);
-  a = (a + 255) & ~(size_t)255;
-  size_t b = (size_t)n_img * sizeof(ImgLut);
-  b = (b + 255) & ~(size_t)255;
-  return a + b + (size_t)n_img * kMetricChunks * 8 * sizeof(double);
+  (void)n_img;
+  return 256;  // the single-pass kernel keeps all intermediate state on chip
 }
 
 extern "C" int cdb_depth_metrics(const uint8_t* gt, const uint8_t* pred, int32_t n_img, int32_t h, int32_t w,
                                  double* out8_per_img, void* workspace, size_t ws_bytes, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CDB_REQUIRE(gt && pred && out8_per_img && workspace && n_img > 0 && h > 0 && w > 0, CDB_ERR_BAD_DESC,
+  (void)workspace;
+  (void)ws_bytes;
+  CDB_REQUIRE(gt && pred && out8_per_img && n_img > 0 && h > 0 && w > 0, CDB_ERR_BAD_DESC,
               "depth_metrics: bad argument");
-  CDB_REQUIRE(ws_bytes >= cdb_depth_metrics_workspace(n_img), CDB_ERR_WORKSPACE, "depth_metrics: workspace too small");
-  CDB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, CDB_ERR_ALIGNMENT, "depth_metrics: workspace alignment");
-  char* ws = static_cast<char*>(workspace);
-  ImgInfo* info = reinterpret_cast<ImgInfo*>(ws);
-  size_t a = ((size_t)n_img * sizeof(ImgInfo) + 255) & ~(size_t)255;
-  ImgLut* lut = reinterpret_cast<ImgLut*>(ws + a);
-  size_t b = ((size_t)n_img * sizeof(ImgLut) + 255) & ~(size_t)255;
-  double* partial = reinterpret_cast<double*>(ws + a + b);
   const int64_t pixels = (int64_t)h * w;
-  metrics_init_kernel<<<ceil_div(n_img, 256), 256, 0, stream>>>(info, n_img);
-  CDB_LAUNCH_OK();
-  dim3 grid(kMetricChunks, n_img);
-  metrics_minmax_kernel<<<grid, 256, 0, stream>>>(gt, pred, pixels, info);
-  CDB_LAUNCH_OK();
-  metrics_lut_kernel<<<n_img, 256, 0, stream>>>(info, lut);
-  CDB_LAUNCH_OK();
-  metrics_accum_kernel<<<grid, 256, 0, stream>>>(gt, pred, pixels, lut, partial);
-  CDB_LAUNCH_OK();
-  metrics_finalize_kernel<<<ceil_div(n_img, 128), 128, 0, stream>>>(partial, kMetricChunks, n_img, out8_per_img);
+  const size_t smem = (size_t)kHistCells * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDB_CUDA_OK(cudaFuncSetAttribute(metrics_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  metrics_hist_kernel<<<n_img, kMetricThreads, smem, stream>>>(gt, pred, pixels, out8_per_img);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

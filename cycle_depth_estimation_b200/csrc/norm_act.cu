@@ -143,6 +143,7 @@ channel_stats_kernel(View y, int H, int W, int C, int vt, int per_image, float* 
 struct NormFwdParams {
   View y, res, out;
   int H, W, C, vt;
+  int rows_per_block;
   int norm, act, pad, has_res;
   float slope, eps, inv_count;
   int per_image;           // stats indexed per image
@@ -194,75 +195,109 @@ __device__ __forceinline__ void norm_coeffs(int norm, int use_running, const flo
   }
 }
 
+// Row-strip mapping: a block owns `rows_per_block` image rows of one image and one tile of channel
+// vectors; thread (v, lane) walks the pixels w = lane, lane + lanes, ... of each row, U pixels per
+// iteration with all loads issued before the first use.  ACT / HAS_RES are compile-time so the inner
+// loop carries no activation switch.
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float v, float slope) {
+  if (ACT == CDB_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == CDB_ACT_LEAKY) return v > 0.f ? v : v * slope;
+  if (ACT == CDB_ACT_TANH) return tanhf(v);
+  if (ACT == CDB_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+__device__ __forceinline__ void write_halo(__nv_bfloat16* ob, int osh, int osw, int h, int w, int H, int W,
+                                           int pad, const uint4& o) {
+  // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
+  int hh[2], ww[2];
+  int nh = 0, nw = 0;
+  if (h >= 1 && h <= pad) hh[nh++] = -h;
+  if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
+  if (w >= 1 && w <= pad) ww[nw++] = -w;
+  if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
+  for (int a = 0; a < nh; ++a) st16(ob + hh[a] * osh + w * osw, o);
+  for (int b = 0; b < nw; ++b) st16(ob + h * osh + ww[b] * osw, o);
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) st16(ob + hh[a] * osh + ww[b] * osw, o);
+}
+
+template <int ACT, bool HAS_RES>
 __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(NormFwdParams p) {
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
   const int cvec = blockIdx.z * p.vt + v;
   if (cvec * 8 >= p.C) return;
   const int n = blockIdx.y;
-  const int pixels = p.H * p.W;
-  const int per_chunk = (pixels + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per_chunk;
-  const int p1 = min(pixels, p0 + per_chunk);
+  const int r0 = blockIdx.x * p.rows_per_block;
+  const int r1 = min(p.H, r0 + p.rows_per_block);
   float scale[8], shift[8];
   norm_coeffs(p.norm, p.use_running, p.stats, p.gamma, p.beta, p.running_mean, p.running_var,
               p.per_image ? n : 0, p.C, cvec * 8, p.inv_count, p.eps, scale, shift, nullptr, nullptr);
   const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
-  const __nv_bfloat16* rb = p.has_res ? p.res.ptr + n * p.res.sn + cvec * 8 : nullptr;
+  const __nv_bfloat16* rb = HAS_RES ? p.res.ptr + n * p.res.sn + cvec * 8 : nullptr;
   __nv_bfloat16* ob = p.out.ptr + n * p.out.sn + cvec * 8;
   const int pad = p.pad, H = p.H, W = p.W;
-  // two pixels per iteration, loads issued before the first use
-  constexpr int U = 2;
-  PixelWalk pw;
-  pw.init(p0 + lane, W);
+  const float slope = p.slope;
+  constexpr int U = 4;
   const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
   const int rsh = static_cast<int>(p.res.sh), rsw = static_cast<int>(p.res.sw);
   const int osh = static_cast<int>(p.out.sh), osw = static_cast<int>(p.out.sw);
-  for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
-    uint4 yr[U], rr[U];
-    int hs[U], ws[U];
+  for (int h = r0; h < r1; ++h) {
+    const __nv_bfloat16* yr_ = yb + h * ysh;
+    const __nv_bfloat16* rr_ = HAS_RES ? rb + h * rsh : nullptr;
+    const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
+    for (int w0 = lane; w0 < W; w0 += lanes * U) {
+      uint4 yr[U], rr[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int px = px0 + u * lanes;
-      hs[u] = pw.h;
-      ws[u] = pw.w;
-      pw.advance(lanes);
-      if (px < p1) {
-        yr[u] = ld16(yb + hs[u] * ysh + ws[u] * ysw);
-        if (p.has_res) rr[u] = ld16(rb + hs[u] * rsh + ws[u] * rsw);
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * lanes;
+        if (w < W) {
+          yr[u] = ld16(yr_ + w * ysw);
+          if (HAS_RES) rr[u] = ld16(rr_ + w * rsw);
+        }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int px = px0 + u * lanes;
-      if (px >= p1) break;
-      const int h = hs[u], w = ws[u];
-      float f[8];
-      unpack8(yr[u], f);
+      for (int u = 0; u < U; ++u) {
+        const int w = w0 + u * lanes;
+        if (w >= W) break;
+        float f[8];
+        unpack8(yr[u], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * scale[j] + shift[j], p.act, p.slope);
-      if (p.has_res) {
-        float r[8];
-        unpack8(rr[u], r);
+        for (int j = 0; j < 8; ++j) f[j] = act_fwd_t<ACT>(f[j] * scale[j] + shift[j], slope);
+        if (HAS_RES) {
+          float r[8];
+          unpack8(rr[u], r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += r[j];
-      }
-      const uint4 o = pack8(f);
-      st16(ob + h * osh + w * osw, o);
-      if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad)) {
-        // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
-        int hh[2], ww[2];
-        int nh = 0, nw = 0;
-        if (h >= 1 && h <= pad) hh[nh++] = -h;
-        if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
-        if (w >= 1 && w <= pad) ww[nw++] = -w;
-        if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
-        for (int a = 0; a < nh; ++a) st16(ob + hh[a] * osh + w * osw, o);
-        for (int b = 0; b < nw; ++b) st16(ob + h * osh + ww[b] * osw, o);
-        for (int a = 0; a < nh; ++a)
-          for (int b = 0; b < nw; ++b) st16(ob + hh[a] * osh + ww[b] * osw, o);
+          for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        const uint4 o = pack8(f);
+        st16(ob + h * osh + w * osw, o);
+        if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) write_halo(ob, osh, osw, h, w, H, W, pad, o);
       }
     }
   }
+}
+
+template <bool HAS_RES>
+static void launch_norm_fwd(const NormFwdParams& p, dim3 grid, cudaStream_t stream) {
+  switch (p.act) {
+    case CDB_ACT_NONE: norm_act_fwd_kernel<CDB_ACT_NONE, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_RELU: norm_act_fwd_kernel<CDB_ACT_RELU, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_LEAKY: norm_act_fwd_kernel<CDB_ACT_LEAKY, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_TANH: norm_act_fwd_kernel<CDB_ACT_TANH, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    default: norm_act_fwd_kernel<CDB_ACT_SIGMOID, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+  }
+}
+
+// rows per block such that the grid holds about `per_sm` blocks per SM
+static int rows_per_block_for(int H, int n, int cv_tiles, int per_sm) {
+  const char* e = getenv("CDB_NORM_BLOCKS_PER_SM");
+  if (e) per_sm = atoi(e);
+  int chunks = (per_sm * sm_count()) / (n * cv_tiles > 0 ? n * cv_tiles : 1);
+  if (chunks < 1) chunks = 1;
+  if (chunks > H) chunks = H;
+  return ceil_div(H, chunks);
 }
 
 // Batch-norm running statistics (training mode): r = (1-m) r + m * batch (unbiased variance).
@@ -287,6 +322,7 @@ __global__ void bn_running_kernel(const float* __restrict__ stats, int C, float 
 struct NormBwdParams {
   View y, dout, dskip, dy, gsum;
   int H, W, C, vt;
+  int rows_per_block;
   int norm, act, pad, has_dout, has_dskip, write_gsum, use_running;
   int pre_act;    // ACT_FIRST: y is act(conv); the result is multiplied by act'(y)
   int accum_f32;  // dy is an fp32 view that receives +=
@@ -322,25 +358,43 @@ __device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const 
     }
 }
 
-template <bool kApply>
-__global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
+// Per-channel constants: xhat = y*a1 + b1 (a1 = rstd, b1 = -mean*rstd); z = xhat*gamma + beta (AFFINE) or xhat;
+// apply: dy = c1*(ga - m1 - xhat*m2) with c1 = rstd*gamma.  Row-strip mapping as in the forward kernel.
+template <bool kApply, int ACT, bool AFFINE>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
   __shared__ float red[kApply ? 1 : 256 * 16];
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
   const int cvec = blockIdx.z * p.vt + v;
   const bool active = cvec * 8 < p.C;
   const int n = blockIdx.y;
-  const int pixels = p.H * p.W;
-  const int per_chunk = (pixels + gridDim.x - 1) / gridDim.x;
-  const int p0 = blockIdx.x * per_chunk;
-  const int p1 = min(pixels, p0 + per_chunk);
+  const int r0 = blockIdx.x * p.rows_per_block;
+  const int r1 = min(p.H, r0 + p.rows_per_block);
   const int grp = p.per_image ? n : 0;
-  float scale[8], shift[8], mean[8], rstd[8], m1[8], m2[8], s1[8], s2[8];
+  float a1[8], b1[8], gam[AFFINE ? 8 : 1], bet[AFFINE ? 8 : 1], c1[8], m1[8], m2[8], s1[kApply ? 1 : 8], s2[kApply ? 1 : 8];
+  if (!kApply) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = m1[j] = m2[j] = 0.f;
+    for (int j = 0; j < 8; ++j) s1[kApply ? 0 : j] = s2[kApply ? 0 : j] = 0.f;
+  }
   if (active) {
-    norm_coeffs(p.norm, p.use_running, p.stats, p.gamma, p.beta, p.running_mean, p.running_var, grp, p.C,
-                cvec * 8, p.inv_count, p.eps, scale, shift, mean, rstd);
-    if (kApply && p.norm != CDB_NORM_NONE && !p.use_running) {
+    {
+      float scale[8], shift[8], mean[8], rstd[8];
+      norm_coeffs(p.norm, p.use_running, p.stats, p.gamma, p.beta, p.running_mean, p.running_var, grp, p.C,
+                  cvec * 8, p.inv_count, p.eps, scale, shift, mean, rstd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] = rstd[j];
+        b1[j] = -mean[j] * rstd[j];
+        c1[j] = scale[j];
+        m1[j] = m2[j] = 0.f;
+        if (AFFINE) {
+          const int ch = cvec * 8 + j;
+          gam[AFFINE ? j : 0] = (p.gamma != nullptr && ch < p.C) ? p.gamma[ch] : 1.f;
+          bet[AFFINE ? j : 0] = (p.beta != nullptr && ch < p.C) ? p.beta[ch] : 0.f;
+        }
+      }
+    }
+    const bool batch_stats = p.norm != CDB_NORM_NONE && !p.use_running;
+    if (kApply && batch_stats) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int ch = cvec * 8 + j;
@@ -353,10 +407,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
     const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
     const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
     const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
-    constexpr int U = 2;  // two pixels per iteration, centre loads issued first
+    constexpr int U = 2;
     const int pad = p.pad, H = p.H, W = p.W;
-    PixelWalk pw;
-    pw.init(p0 + lane, W);
     const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
     const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
     const int ssh = static_cast<int>(p.dskip.sh), ssw = static_cast<int>(p.dskip.sw);
@@ -364,72 +416,74 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
     const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
     __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
     __nv_bfloat16* ob = kApply ? p.dy.ptr + n * p.dy.sn + cvec * 8 : nullptr;
-    for (int px0 = p0 + lane; px0 < p1; px0 += lanes * U) {
-      uint4 yr[U], dr[U], sr[U];
-      int hs[U], ws[U];
+    const bool has_dout = p.has_dout, has_dskip = p.has_dskip;
+    const int pre_act = p.pre_act;
+    const float slope = p.slope;
+    const bool plain_norm = p.norm == CDB_NORM_NONE, running = p.use_running != 0;
+    for (int h = r0; h < r1; ++h) {
+      const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
+      for (int w0 = lane; w0 < W; w0 += lanes * U) {
+        uint4 yr[U], dr[U], sr[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int px = px0 + u * lanes;
-        hs[u] = pw.h;
-        ws[u] = pw.w;
-        pw.advance(lanes);
-        if (px < p1) {
-          yr[u] = ld16(yb + hs[u] * ysh + ws[u] * ysw);
-          if (p.has_dout) dr[u] = ld16(db + hs[u] * dsh + ws[u] * dsw);
-          if (p.has_dskip) sr[u] = ld16(sb + hs[u] * ssh + ws[u] * ssw);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int px = px0 + u * lanes;
-        if (px >= p1) break;
-        const int h = hs[u], w = ws[u];
-        float g[8], f[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = 0.f;
-        if (p.has_dout) {
-          unpack8(dr[u], g);
-          if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad))
-            add_folded_extras(p, db, h, w, g);
-        }
-        if (p.has_dskip) {
-          float t[8];
-          unpack8(sr[u], t);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] += t[j];
-        }
-        unpack8(yr[u], f);
-        if (kApply && p.write_gsum) st16(gb + h * gsh + w * gsw, pack8(g));
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float z = f[j] * scale[j] + shift[j];
-          float ga = g[j];
-          if (p.act == CDB_ACT_RELU) ga = z > 0.f ? ga : 0.f;
-          else if (p.act == CDB_ACT_LEAKY) ga = z > 0.f ? ga : ga * p.slope;
-          const float xhat = (f[j] - mean[j]) * rstd[j];
-          if (kApply) {
-            o[j] = (p.norm == CDB_NORM_NONE) ? ga
-                   : p.use_running          ? ga * scale[j]
-                                            : scale[j] * (ga - m1[j] - xhat * m2[j]);
-            if (p.pre_act == CDB_ACT_RELU) o[j] = f[j] > 0.f ? o[j] : 0.f;
-            else if (p.pre_act == CDB_ACT_LEAKY) o[j] = f[j] > 0.f ? o[j] : o[j] * p.slope;
-          } else {
-            s1[j] += ga;
-            s2[j] += ga * xhat;
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * lanes;
+          if (w < W) {
+            yr[u] = ld16(yb + h * ysh + w * ysw);
+            if (has_dout) dr[u] = ld16(db + h * dsh + w * dsw);
+            if (has_dskip) sr[u] = ld16(sb + h * ssh + w * ssw);
           }
         }
-        if (kApply) {
-          if (p.accum_f32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dy.ptr) + n * p.dy.sn + cvec * 8 +
-                                                   static_cast<int64_t>(h) * p.dy.sh + static_cast<int64_t>(w) * p.dy.sw);
-            float4 a = o4[0], b = o4[1];
-            a.x += o[0]; a.y += o[1]; a.z += o[2]; a.w += o[3];
-            b.x += o[4]; b.y += o[5]; b.z += o[6]; b.w += o[7];
-            o4[0] = a;
-            o4[1] = b;
-          } else {
-            st16(ob + h * osh + w * osw, pack8(o));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * lanes;
+          if (w >= W) break;
+          float g[8], f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = 0.f;
+          if (has_dout) {
+            unpack8(dr[u], g);
+            if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) add_folded_extras(p, db, h, w, g);
+          }
+          if (has_dskip) {
+            float t[8];
+            unpack8(sr[u], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] += t[j];
+          }
+          unpack8(yr[u], f);
+          if (kApply && gb != nullptr) st16(gb + h * gsh + w * gsw, pack8(g));
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xhat = f[j] * a1[j] + b1[j];
+            float ga = g[j];
+            if (ACT != CDB_ACT_NONE) {
+              const float z = AFFINE ? xhat * gam[AFFINE ? j : 0] + bet[AFFINE ? j : 0] : xhat;
+              if (ACT == CDB_ACT_RELU) ga = z > 0.f ? ga : 0.f;
+              else ga = z > 0.f ? ga : ga * slope;
+            }
+            if (kApply) {
+              float r = plain_norm ? ga : running ? ga * c1[j] : c1[j] * (ga - m1[j] - xhat * m2[j]);
+              if (pre_act == CDB_ACT_RELU) r = f[j] > 0.f ? r : 0.f;
+              else if (pre_act == CDB_ACT_LEAKY) r = f[j] > 0.f ? r : r * slope;
+              o[j] = r;
+            } else {
+              s1[kApply ? 0 : j] += ga;
+              s2[kApply ? 0 : j] += ga * xhat;
+            }
+          }
+          if (kApply) {
+            if (p.accum_f32) {
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dy.ptr) + n * p.dy.sn + cvec * 8 +
+                                                     static_cast<int64_t>(h) * p.dy.sh + static_cast<int64_t>(w) * p.dy.sw);
+              float4 qa = o4[0], qb = o4[1];
+              qa.x += o[0]; qa.y += o[1]; qa.z += o[2]; qa.w += o[3];
+              qb.x += o[4]; qb.y += o[5]; qb.z += o[6]; qb.w += o[7];
+              o4[0] = qa;
+              o4[1] = qb;
+            } else {
+              st16(ob + h * osh + w * osw, pack8(o));
+            }
           }
         }
       }
@@ -438,8 +492,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
   if (!kApply) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      red[(j * 2) * 256 + threadIdx.x] = s1[j];
-      red[(j * 2 + 1) * 256 + threadIdx.x] = s2[j];
+      red[(kApply ? 0 : (j * 2) * 256) + (kApply ? 0 : threadIdx.x)] = s1[kApply ? 0 : j];
+      red[(kApply ? 0 : (j * 2 + 1) * 256) + (kApply ? 0 : threadIdx.x)] = s2[kApply ? 0 : j];
     }
     __syncthreads();
     for (int t = threadIdx.x; t < p.vt * 16; t += 256) {
@@ -450,6 +504,20 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(NormBwdParams p) {
       if (ch < p.C) atomicAdd(p.bstats + (static_cast<int64_t>(grp) * p.C + ch) * 2 + (comp & 1), acc);
     }
   }
+}
+
+template <bool kApply, bool AFFINE>
+static void launch_norm_bwd_act(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  switch (p.act) {
+    case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE><<<grid, 256, 0, stream>>>(p); break;
+    default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE><<<grid, 256, 0, stream>>>(p); break;
+  }
+}
+template <bool kApply>
+static void launch_norm_bwd(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.gamma != nullptr || p.beta != nullptr) launch_norm_bwd_act<kApply, true>(p, grid, stream);
+  else launch_norm_bwd_act<kApply, false>(p, grid, stream);
 }
 
 }  // namespace cdb
@@ -532,9 +600,10 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.beta = d->beta;
   p.running_mean = d->running_mean;
   p.running_var = d->running_var;
-  const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles, 3);
-  dim3 grid(chunks, y->n, m.cv_tiles);
-  norm_act_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+  p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 3);
+  dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
+  if (has_res) launch_norm_fwd<true>(p, grid, stream);
+  else launch_norm_fwd<false>(p, grid, stream);
   CDB_LAUNCH_OK();
   if (d->norm == CDB_NORM_BATCH && !d->use_running && d->update_running && d->running_mean && d->running_var) {
     const float count = (float)((int64_t)y->n * y->h * y->w);
@@ -602,14 +671,14 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.running_mean = d->running_mean;
   p.running_var = d->running_var;
   p.bstats = bstats;
-  const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
-  dim3 grid(chunks, y->n, m.cv_tiles);
+  p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 2);
+  dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
   if (need_reduce || (bstats && d->norm == CDB_NORM_NONE)) {
     // norm none + bstats: the reduction yields the bias gradient (sum of ga) in component 0
-    norm_act_bwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+    launch_norm_bwd<false>(p, grid, stream);
     CDB_LAUNCH_OK();
   }
-  norm_act_bwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+  launch_norm_bwd<true>(p, grid, stream);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
