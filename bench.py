@@ -28,8 +28,8 @@ G_FWD_GFLOP = 99.10         # per image
 DOMINANT = dict(n=8, c=256, hw=64, k=3)  # the 18 x 6 residual-block convolutions of a step
 
 
-def make_opt(device):
-    return argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
+def make_opt(device, cuda_graph=False):
+    return argparse.Namespace(cuda_graph=cuda_graph, input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
                               n_layers_D=3, norm='instance', no_dropout=True, init_type='normal', init_gain=0.02,
                               no_lsgan=False, pool_size=50, lr=2e-4, beta1=0.5, lambda_A=10.0, lambda_B=10.0,
                               lambda_identity=0.5, isTrain=True, device=device, direction='AtoB')
@@ -218,12 +218,37 @@ def b200_arm(args):
     batch, size = args.batch, args.size
     torch.manual_seed(0)            # identical initial weights on every rank
     random.seed(1234)               # identical ImagePool stream on every rank
-    model = CycleGANModel()
-    with contextlib.redirect_stdout(io.StringIO()):
-        model.initialize(make_opt("cuda"))
     host_a, host_b = synthetic_batch(batch, size, 1234 + rank)
     host_a, host_b = host_a.pin_memory(), host_b.pin_memory()
     dev = {"img_source": host_a.cuda(), "img_target": host_b.cuda()}
+
+    def build(use_graph):
+        torch.manual_seed(0)
+        random.seed(1234)
+        m = CycleGANModel()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.initialize(make_opt("cuda", use_graph))
+        return m
+
+    # single process: the whole step is replayed as ONE CUDA graph (cycle_gan_model.py); data-parallel runs and
+    # --no-cuda-graph use eager launches. A failed capture falls back to eager and says so in the JSON line.
+    use_graph = world == 1 and not args.no_cuda_graph
+    graph_note = "cuda graph replay of the whole step" if use_graph else "eager launches"
+    model = build(use_graph)
+    if use_graph:
+        try:
+            for _ in range(CycleGANModel.GRAPH_WARMUP_STEPS + 2):
+                model.set_input(dev)
+                model.optimize_parameters("train")
+            torch.cuda.synchronize()
+            if model._graph is None:
+                raise RuntimeError("step was not captured")
+        except Exception as exc:  # noqa: BLE001
+            print("cuda graph capture failed (%s: %s); falling back to eager launches" % (type(exc).__name__, exc),
+                  file=sys.stderr)
+            torch.cuda.synchronize()
+            use_graph, graph_note = False, "eager launches (graph capture failed: %s)" % type(exc).__name__
+            model = build(False)
 
     def barrier():
         if world > 1:
@@ -253,6 +278,10 @@ def b200_arm(args):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.cdb_launch_count() - launches0
+    if use_graph:
+        # replays do not pass through the library's host entry points: count the kernels of one captured step
+        # (the launches the library recorded while the step was being captured) times the replays
+        launches = int(getattr(model, "_graph_launches", 0)) * args.steps
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = world * 1e3 / ms_step * (batch / 8.0)
@@ -307,7 +336,7 @@ def b200_arm(args):
             "workload": "CycleGAN training step: G_A/G_B resnet_9blocks + D_A/D_B 70x70 PatchGAN, LSGAN + L1 "
                         "cycle/identity, ImagePool 50, Adam, 4 D updates per G update; batch %d per GPU at %dx%d "
                         "(BASELINE configs[1])" % (batch, size, size),
-            "per_gpu_batch": batch, "image": size, "parallelism": "dp%d" % world,
+            "per_gpu_batch": batch, "image": size, "parallelism": "dp%d" % world, "launch_mode": graph_note,
             "l2": "working set per step (saved activations of 6 generator + 18 discriminator passes, > 5 GB) "
                   "exceeds the 126 MB L2; no explicit flush",
             "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * batch,
@@ -494,6 +523,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-graph", action="store_true", help="eager launches instead of replaying the captured step")
     ap.add_argument("--workload", default="cyclegan", choices=["cyclegan", "pix2pix", "model5", "g_infer", "metrics"],
                     help="cyclegan (default, the headline metric) or one of the secondary BASELINE configs")
     args = ap.parse_args()

@@ -194,6 +194,45 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Adam with the step count read from device memory, so that a CUDA graph of the training step stays valid
+// across replays (the host-side bias corrections of adam_kernel would be frozen at capture time).
+__global__ void adam_dev_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                     float* __restrict__ v, int64_t numel, float lr, float b1, float b2, float eps,
+                                     const int32_t* __restrict__ step_ptr) {
+  const float step = static_cast<float>(*step_ptr);
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < numel;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i];
+    const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+// ImagePool.query (util/image_pool.py:12-32) with the host's decisions supplied as a device table:
+// plan[i] = {return_from, store_to} (-1 = the incoming image / no store). Images are processed in order by
+// every thread for its own pixel, which preserves the sequential semantics of the reference (an image
+// stored by entry i can be returned by a later entry of the same batch).
+__global__ void pool_apply_kernel(const float* __restrict__ fake, float* __restrict__ pool,
+                                  const int32_t* __restrict__ plan, int b, int64_t chw, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < chw;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    for (int k = 0; k < b; ++k) {
+      const int ret = plan[2 * k], sto = plan[2 * k + 1];
+      const float x = fake[k * chw + i];
+      const float r = ret >= 0 ? pool[ret * chw + i] : x;
+      if (sto >= 0) pool[sto * chw + i] = x;
+      out[k * chw + i] = r;
+    }
+  }
+}
+
 static int grid_for(int64_t n, int per_thread = 4) {
   int64_t b = (n + 256 * per_thread - 1) / (256 * per_thread);
   const int cap = sm_count() * 8;
@@ -305,6 +344,27 @@ extern "C" int cdb_adam_step(float* param, const float* grad, float* exp_avg, fl
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(numel), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
                                                    (float)bc1, (float)sqrt(bc2));
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                                 float lr, float beta1, float beta2, float eps, const int32_t* step_dev,
+                                 cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && numel > 0, CDB_ERR_BAD_DESC,
+              "adam_step_dev: bad argument");
+  adam_dev_step_kernel<<<grid_for(numel), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2,
+                                                            eps, step_dev);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_image_pool_apply(const float* fake, float* pool, const int32_t* plan_dev, int32_t batch, int64_t chw,
+                                    float* out, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(fake && pool && plan_dev && out && batch > 0 && chw > 0, CDB_ERR_BAD_DESC, "image_pool_apply: bad argument");
+  pool_apply_kernel<<<grid_for(chw, 1), 256, 0, stream>>>(fake, pool, plan_dev, batch, chw, out);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

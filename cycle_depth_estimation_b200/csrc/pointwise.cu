@@ -628,3 +628,46 @@ extern "C" int cdb_nhwc_to_nchw(const CdbAct* x, int32_t c_real, float* dst, int
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
+
+// ---- few-output-channel convolutions (c7s1-3 of the ResNet generator, models/networks.py:184-186, and the
+// data gradient of its first layer c7s1-64): the S filter columns are folded into the GEMM N dimension, i.e.
+// a first pass computes T[n,p,q',(s,o)] = sum_{r,i} x[n,p+r,q',i] W[o,i,r,s] as an R x 1 convolution with
+// S*Cout output channels (7x fewer, 2x wider MMAs than 49 taps of N = 16), and this kernel finishes
+//   out[n,o,p,q] = act(bias[o] + sum_s T[n,p,q+s,(s,o)])      (fp32 NCHW, strided)
+namespace cdb {
+__global__ void __launch_bounds__(256)
+shift_add_kernel(const float* __restrict__ t, int N, int P, int Q, int wp, int S, int cout, int ct,
+                 const float* __restrict__ bias, int act, float slope, float* __restrict__ out, int64_t o_sn,
+                 int64_t o_sc, int64_t o_sh, int64_t o_sw) {
+  const int64_t total = (int64_t)N * P * Q;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % Q);
+    const int64_t np = idx / Q;
+    const int p = (int)(np % P);
+    const int n = (int)(np / P);
+    const float* row = t + (np * wp + q) * ct;
+    for (int o = 0; o < cout; ++o) {
+      float acc = bias != nullptr ? bias[o] : 0.f;
+      for (int s = 0; s < S; ++s) acc += row[(int64_t)s * ct + s * cout + o];
+      if (act == CDB_ACT_TANH) acc = tanhf(acc);
+      else if (act == CDB_ACT_SIGMOID) acc = 1.f / (1.f + __expf(-acc));
+      else if (act == CDB_ACT_RELU) acc = fmaxf(acc, 0.f);
+      else if (act == CDB_ACT_LEAKY) acc = acc > 0.f ? acc : acc * slope;
+      out[n * o_sn + o * o_sc + p * o_sh + q * o_sw] = acc;
+    }
+  }
+}
+}  // namespace cdb
+
+extern "C" int cdb_shift_add_nchw(const float* t, int32_t n, int32_t p, int32_t q, int32_t wp, int32_t s_taps,
+                                  int32_t cout, int32_t ct, const float* bias, int32_t act, float slope, float* out,
+                                  int64_t o_sn, int64_t o_sc, int64_t o_sh, int64_t o_sw, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(t && out && n > 0 && p > 0 && q > 0 && s_taps > 0 && cout > 0 && ct >= s_taps * cout && wp >= q + s_taps - 1,
+              CDB_ERR_BAD_DESC, "shift_add_nchw: bad argument");
+  const int64_t total = (int64_t)n * p * q;
+  shift_add_kernel<<<pw_grid(total), 256, 0, stream>>>(t, n, p, q, wp, s_taps, cout, ct, bias, act, slope, out, o_sn,
+                                                       o_sc, o_sh, o_sw);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}

@@ -25,10 +25,14 @@ class FusedAdam:
     parameter tensor). Keeps ``param_groups`` / ``zero_grad`` / ``step`` so schedulers and the step glue
     work unchanged."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, device_step=False):
         self.param_groups = [{'params': list(params), 'lr': lr, 'betas': betas, 'eps': eps, 'initial_lr': lr}]
         self.state = {}
         self.defaults = {'lr': lr, 'betas': betas, 'eps': eps}
+        # device_step: the step count lives in device memory (one counter per optimizer) so that a CUDA graph of
+        # the training step replays with the right bias corrections
+        self.device_step = device_step
+        self._step_dev = None
 
     def zero_grad(self, set_to_none=True):
         for g in self.param_groups:
@@ -40,6 +44,11 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
+        if self.device_step:
+            if self._step_dev is None:
+                dev = self.param_groups[0]['params'][0].device
+                self._step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+            self._step_dev.add_(1)
         for g in self.param_groups:
             b1, b2 = g['betas']
             for p in g['params']:
@@ -51,7 +60,13 @@ class FusedAdam:
                     self.state[p] = st
                 st['step'] += 1
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                ops.adam_step(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'], st['step'])
+                if self.device_step:
+                    # every parameter of this optimizer takes its first step together, so one counter serves all
+                    ops.adam_step_dev(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'],
+                                      self._step_dev)
+                else:
+                    ops.adam_step(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'],
+                                  st['step'])
                 # the kernel writes through raw pointers, which autograd's version counter cannot
                 # see; the packed-weight cache also keys on this explicit counter
                 p._cdb_version = getattr(p, '_cdb_version', 0) + 1
@@ -127,16 +142,34 @@ class CycleGANModel:
 
     def build_optimizers(self):
         opt = self.opt
-        adam = FusedAdam if getattr(opt, 'fused_adam', True) else torch.optim.Adam
+        self._graph_mode = bool(getattr(opt, 'cuda_graph', False))
+        if getattr(opt, 'fused_adam', True):
+            adam = lambda ps, **kw: FusedAdam(ps, device_step=self._graph_mode, **kw)
+        else:
+            adam = torch.optim.Adam
         self.optimizer_G = adam(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()),
                                 lr=opt.lr, betas=(opt.beta1, 0.999))
         self.optimizer_D = adam(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()),
                                 lr=opt.lr, betas=(opt.beta1, 0.999))
+        self._graph, self._graph_calls, self._plan_host, self._plan_dev = None, 0, None, None
+        self._plan_slot, self._plan_event, self._side_stream = 0, None, None
         self.optimizers = [self.optimizer_G, self.optimizer_D]
         self._buckets_G = GradBuckets(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()))
         self._buckets_D = GradBuckets(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()))
 
     def set_input(self, input):
+        if getattr(self, '_graph_mode', False):
+            # static input buffers: a captured step keeps reading the same device addresses
+            a, b = input['img_source'], input['img_target']
+            if getattr(self, 'real_A', None) is None or self.real_A.shape != a.shape or self._graph is None:
+                if self._graph is not None:
+                    raise RuntimeError("cuda_graph mode: the input shape changed after the step was captured")
+                if getattr(self, 'real_A', None) is None or self.real_A.shape != a.shape:
+                    self.real_A = torch.empty(tuple(a.shape), dtype=torch.float32, device=self.device)
+                    self.real_B = torch.empty(tuple(b.shape), dtype=torch.float32, device=self.device)
+            self.real_A.copy_(a, non_blocking=True)
+            self.real_B.copy_(b, non_blocking=True)
+            return
         self.real_A = input['img_source'].to(self.device, non_blocking=True)
         self.real_B = input['img_target'].to(self.device, non_blocking=True)
 
@@ -157,6 +190,10 @@ class CycleGANModel:
     def _pool_query(self, pool, fake):
         """Replicated pool under data parallelism: all ranks see the global batch in rank-major order
         and replay the identical random stream; each rank keeps its own slice of the result."""
+        if self._plan_dev is not None:
+            slot = self._plan_slot
+            self._plan_slot += 1
+            return pool.query_planned(fake, self._plan_dev[slot])
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             world, rank = dist.get_world_size(), dist.get_rank()
             gathered = [torch.empty_like(fake) for _ in range(world)]
@@ -199,8 +236,72 @@ class CycleGANModel:
                        + self.loss_idt_B)
         return self.loss_G
 
+    # ---------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole step (opt.cuda_graph, single process): ~3200 kernel launches per step
+    # become one graph launch. Host-side decisions are kept out of the graph: the ImagePool's random draws
+    # are made up-front (ImagePool.plan, same ``random`` calls in the same order as the eager step) and
+    # reach the device through a pinned table copied by the graph's first node; Adam reads its step count
+    # from device memory.
+    # ---------------------------------------------------------------------------------------------
+    GRAPH_WARMUP_STEPS = 3
+
+    def _draw_pool_plans(self):
+        b = self.real_A.shape[0]
+        if self._plan_host is None:
+            self._plan_host = torch.empty((8, b, 2), dtype=torch.int32).pin_memory()
+            self._plan_dev = torch.empty((8, b, 2), dtype=torch.int32, device=self.device)
+        if self._plan_event is not None:
+            self._plan_event.synchronize()      # the previous replay has consumed the pinned table
+        rows = []
+        for _ in range(4):                      # the order of backward_D_A / backward_D_B in the step
+            rows.append(self.fake_B_pool.plan(b))
+            rows.append(self.fake_A_pool.plan(b))
+        self._plan_host.copy_(torch.tensor(rows, dtype=torch.int32))
+        self._plan_slot = 0
+
+    def _graphed_step(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            raise RuntimeError("opt.cuda_graph is a single-process mode (data-parallel steps run eagerly)")
+        self._draw_pool_plans()
+        if self._graph is not None:
+            self._graph.replay()
+            self._plan_event.record()
+            return
+        self._graph_calls += 1
+        if self._graph_calls <= self.GRAPH_WARMUP_STEPS:
+            # warm-up on a side stream: autograd binds each parameter's gradient accumulator to the stream that
+            # was current when it was created, and a node bound to the legacy default stream cannot take part in
+            # a capture (cudaErrorStreamCaptureImplicit)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side_stream.wait_stream(cur)
+            with torch.cuda.stream(self._side_stream):
+                self._plan_dev.copy_(self._plan_host, non_blocking=True)
+                self._eager_step(True)
+            cur.wait_stream(self._side_stream)
+            return
+        self.optimizer_G.zero_grad()
+        self.optimizer_D.zero_grad()
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        n0 = _lib.lib().cdb_launch_count()
+        with torch.cuda.graph(graph):
+            self._plan_dev.copy_(self._plan_host, non_blocking=True)
+            self._eager_step(True)
+        self._graph_launches = _lib.lib().cdb_launch_count() - n0   # library kernels inside one replay
+        self._graph = graph
+        graph.replay()      # capture records the step, the replay performs it
+        self._plan_event = torch.cuda.Event()
+        self._plan_event.record()
+
     def optimize_parameters(self, train_or_test='train'):
-        train = train_or_test == 'train'
+        if getattr(self, '_graph_mode', False) and train_or_test == 'train':
+            return self._graphed_step()
+        return self._eager_step(train_or_test == 'train')
+
+    def _eager_step(self, train):
         self.forward()
         self.set_requires_grad([self.netD_A, self.netD_B], False)
         self.optimizer_G.zero_grad()

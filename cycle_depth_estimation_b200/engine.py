@@ -141,20 +141,47 @@ class _PackCache:
     """bf16 GEMM-operand copies of the fp32 filters, stored ON the parameter object (so they die with
     it) and validated against its storage pointer and version counters."""
 
-    def get(self, weight, rows_are_dim0, rowpack):
+    def get(self, weight, rows_are_dim0, rowpack, flipped=False):
+        """flipped: pack W[..., R-1-r, S-1-s] (row-packed data gradients, where the kernel cannot reverse taps)."""
         store = weight.__dict__.setdefault('_cdb_packed', {})
-        key = (rows_are_dim0, rowpack)
+        key = (rows_are_dim0, rowpack, flipped)
         ver = (weight.data_ptr(), weight._version, getattr(weight, '_cdb_version', 0), _pack_epoch[0])
         hit = store.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        packed = ops.pack_conv_weight(weight.detach().contiguous(), rows_are_dim0, rowpack,
+        src = weight.detach().flip(2, 3) if flipped else weight.detach()
+        packed = ops.pack_conv_weight(src.contiguous(), rows_are_dim0, rowpack,
                                       out=hit[1][0] if hit is not None else None)
         store[key] = (ver, packed)
         return packed
 
 
+    def get_folded(self, weight, dgrad):
+        """Few-output-channel layers: the S filter columns folded into the GEMM N dimension.
+        forward: W2[s*O + o, i, r, 0] = W[o, i, r, s];  data gradient: W2[s*I + i, o, r, 0] = W[o, i, R-1-r, S-1-s]."""
+        store = weight.__dict__.setdefault('_cdb_packed', {})
+        key = ('fold', dgrad)
+        ver = (weight.data_ptr(), weight._version, getattr(weight, '_cdb_version', 0), _pack_epoch[0])
+        hit = store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w = weight.detach()
+        o, i, r, sdim = w.shape
+        if dgrad:
+            w2 = w.flip(2, 3).permute(3, 1, 0, 2).reshape(sdim * i, o, r, 1)
+        else:
+            w2 = w.permute(3, 0, 1, 2).reshape(sdim * o, i, r, 1)
+        packed = ops.pack_conv_weight(w2.contiguous(), True, 0, out=hit[1][0] if hit is not None else None)
+        store[key] = (ver, packed)
+        return packed
+
+
 _pack_cache = _PackCache()
+
+
+def _foldable(k, channels, conv):
+    """S*channels output columns fit one narrow MMA tile: worth folding (7x7 with 3 channels -> N = 21)."""
+    return k > 1 and k * channels <= 32 and conv.stride[0] == 1 and conv.dilation[0] == 1
 
 
 def _out_hw(st, h, w):
@@ -313,7 +340,15 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         nk = _norm_kind(st)
         if is_last:
             out = torch.empty((n, co, ho, wo), dtype=torch.float32, device=dev)
-            ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nchw(out), conv.bias, st.act, st.slope)
+            k = conv.kernel_size[0]
+            if flat and xin.is_contiguous() and _foldable(k, co, conv):
+                # c7s1-3: R x 1 convolution with S*Cout folded output channels, then the shifted row sum
+                w2, rows2, kpad2 = _pack_cache.get_folded(conv.weight, False)
+                t = torch.empty((n, ho, xin.shape[2], ops.round_up(k * co, 8)), dtype=torch.float32, device=dev)
+                ops.conv2d_fwd(ops.geom(k, 1), xin, w2, rows2, kpad2, ops.out_view_nhwc(t, k * co))
+                ops.shift_add_nchw(t, k, co, conv.bias, st.act, st.slope, out)
+            else:
+                ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nchw(out), conv.bias, st.act, st.slope)
             run.out = out
             run.dims[st.dst] = (ho, wo, co)
             continue
@@ -407,7 +442,9 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
         # ---- dY: gradient w.r.t. the raw convolution output. For flat stages it lives inside a zero halo
         # of (k-1)*dil pixels, so that the data gradient is again a flat (flipped) convolution.
         flat_dgrad = flat and want_dx and not is_first
-        if flat_dgrad:
+        fold_dgrad = (is_first and want_dx and bool(st.reflect) and not st.transposed
+                      and _foldable(conv.kernel_size[0], run.x_shape[1], conv))
+        if flat_dgrad or fold_dgrad:
             hz = (conv.kernel_size[0] - 1) * conv.dilation[0]
             slack = 64 // cs if cs <= 16 else 0   # room for the row-packed view used by the few-channel wgrad
             dyp = torch.zeros((n, ho + 2 * hz, wo + 2 * hz + slack, cs), dtype=BF16, device=dev)
@@ -483,7 +520,17 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
             wd, rows_pad, kpad = _pack_cache.get(conv.weight, st.transposed, 0)
             if is_first:
                 cin = run.x_shape[1]
-                if st.reflect:
+                if fold_dgrad:
+                    p, k = st.reflect, conv.kernel_size[0]
+                    w2, rows2, kpad2 = _pack_cache.get_folded(conv.weight, True)
+                    tmp = torch.empty((n, cin, hi + 2 * p, wi + 2 * p), dtype=torch.float32, device=dev)
+                    t = torch.empty((n, hi + 2 * p, dyp.shape[2], ops.round_up(k * cin, 8)), dtype=torch.float32,
+                                    device=dev)
+                    ops.conv2d_fwd(ops.geom(k, 1), dyp, w2, rows2, kpad2, ops.out_view_nhwc(t, k * cin))
+                    ops.shift_add_nchw(t, k, cin, None, ACT_NONE, 0.0, tmp)
+                    gx = torch.empty((n, cin, hi, wi), dtype=torch.float32, device=dev)
+                    ops.reflect_fold_nchw(tmp, gx, p)
+                elif st.reflect:
                     p = st.reflect
                     tmp = torch.empty((n, cin, hi + 2 * p, wi + 2 * p), dtype=torch.float32, device=dev)
                     ops.conv2d_fwd(gd, dy, wd, rows_pad, kpad, ops.out_view_nchw(tmp))
@@ -496,8 +543,16 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                 src_full = run.vals[st.src]
                 hp, wp_ = src_full.shape[1], src_full.shape[2]
                 dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], src_full.shape[3], dev)
-                gflip = ops.geom(conv.kernel_size[0], conv.kernel_size[1], 1, 0, 0, conv.dilation[0], False, 0, True)
-                ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+                k = conv.kernel_size[0]
+                if cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
+                    # few output channels (c7s1-3): the zero-haloed dy carries 8 channels per pixel, so one K
+                    # block covers a whole filter row (row-packed operand, taps reversed at packing time)
+                    wr, rows_r, kpad_r = _pack_cache.get(conv.weight, st.transposed, cs, flipped=True)
+                    ops.conv2d_fwd(ops.geom(k, k, 1, 0, 0, 1, False, cs), dyp, wr, rows_r, kpad_r,
+                                   ops.out_view_nhwc(dfull, ci))
+                else:
+                    gflip = ops.geom(k, k, 1, 0, 0, conv.dilation[0], False, 0, True)
+                    ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
                 dpad[st.src] = dfull
                 if DEBUG_RECORD is not None:
                     DEBUG_RECORD[('dfull', st.src)] = dfull.clone()

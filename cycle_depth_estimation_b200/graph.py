@@ -457,8 +457,14 @@ class Tape:
         if flat_dgrad:
             hp, wp_ = xin.shape[1], xin.shape[2]
             dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], xin.shape[3], dev)
-            gflip = ops.geom(k, k, 1, 0, 0, dil, False, 0, True)
-            ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+            if cs <= 16 and k * cs <= 64 and dil == 1:
+                # few output channels: row-packed dy operand (one K block per filter row), taps reversed at packing
+                wr, rows_r, kpad_r = _pack.get(conv.weight, transposed, cs, flipped=True)
+                ops.conv2d_fwd(ops.geom(k, k, 1, 0, 0, 1, False, cs), dyp, wr, rows_r, kpad_r,
+                               ops.out_view_nhwc(dfull, ci))
+            else:
+                gflip = ops.geom(k, k, 1, 0, 0, dil, False, 0, True)
+                ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
         else:
             gd = ops.geom(k, k, stride, pad, pad, dil, not transposed, 0)
             dfull = torch.empty(tuple(xin.shape), dtype=BF16, device=dev)

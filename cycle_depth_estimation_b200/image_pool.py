@@ -44,3 +44,41 @@ class ImagePool():
                     out[i].copy_(images[i])
                     self.trace.append(('pass', -1))
         return out
+
+    # ------------------------------------------------------------------------------------------------
+    # graph-replay form: the same decisions, drawn up-front on the host, applied by one device kernel
+    # ------------------------------------------------------------------------------------------------
+    def plan(self, batch):
+        """Draws the decisions of ONE query of `batch` images from Python's ``random`` exactly as ``query`` would
+        (same calls, same order) and returns [(return_from, store_to)] with -1 = the incoming image / no store."""
+        out = []
+        for _ in range(batch):
+            if self.num_imgs < self.pool_size:
+                out.append((-1, self.num_imgs))
+                self.trace.append(('fill', self.num_imgs))
+                self.num_imgs = self.num_imgs + 1
+            else:
+                p = random.uniform(0, 1)
+                if p > 0.5:
+                    random_id = random.randint(0, self.pool_size - 1)
+                    out.append((random_id, random_id))
+                    self.trace.append(('swap', random_id))
+                else:
+                    out.append((-1, -1))
+                    self.trace.append(('pass', -1))
+        return out
+
+    def query_planned(self, images, plan_dev):
+        """``query`` with the decisions read from the int32 device table plan_dev [batch, 2] (filled from
+        ``plan``); capturable in a CUDA graph. Returns the detached batch the discriminator sees."""
+        from . import ops
+        if self.pool_size == 0:
+            return images
+        images = images.detach().contiguous()
+        if self.images is None:
+            self.images = torch.empty((self.pool_size,) + tuple(images.shape[1:]), dtype=images.dtype,
+                                      device=images.device)
+        out = torch.empty_like(images)
+        ops.image_pool_apply(images, self.images, plan_dev, out)
+        return out
+

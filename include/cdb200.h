@@ -226,6 +226,13 @@ int cdb_dropout(const CdbAct* x, const CdbAct* out, uint64_t seed, float p_drop,
 /* NHWC bf16 view -> NCHW fp32 tensor (module outputs), dst strides in elements. */
 int cdb_nhwc_to_nchw(const CdbAct* x, int32_t c_real, float* dst, int64_t d_n, int64_t d_c, int64_t d_h,
                      int64_t d_w, cdbStream_t stream);
+/* Second half of a few-output-channel convolution whose S filter columns were folded into the GEMM N dimension
+ * (c7s1-3, models/networks.py:184-186; data gradient of c7s1-64, :158): t is the fp32 NHWC result
+ * [n][p][wp][ct] of the R x 1 convolution with channel (s*cout + o);
+ *   out[n,o,p,q] = act(bias[o] + sum_s t[n,p,q+s,s*cout+o])   (fp32, strides in elements). */
+int cdb_shift_add_nchw(const float* t, int32_t n, int32_t p, int32_t q, int32_t wp, int32_t s_taps, int32_t cout,
+                       int32_t ct, const float* bias, int32_t act, float slope, float* out, int64_t o_sn,
+                       int64_t o_sc, int64_t o_sh, int64_t o_sw, cdbStream_t stream);
 
 /* ---- K6b: losses of the seg/depth step ---------------------------------------------------------------
  * torch.nn.CrossEntropyLoss(ignore_index) on [n][c][hw] logits (new_multi/model5.py:281): acc2[0] += sum of
@@ -241,6 +248,16 @@ int cdb_loss_bcedep(const float* x, const float* target, int32_t b, int32_t k, i
 /* torch.optim.Adam step (no amsgrad / weight decay) on one fp32 tensor (models/cycle_gan_model.py:66-69). */
 int cdb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                   float beta1, float beta2, float eps, int32_t step, cdbStream_t stream);
+
+/* Same update with the step count read from device memory (CUDA-graph replays of the training step). */
+int cdb_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                      float beta1, float beta2, float eps, const int32_t* step_dev, cdbStream_t stream);
+
+/* ImagePool.query (util/image_pool.py:12-32) with the host's random decisions supplied as a device table
+ * plan_dev[batch][2] = {return_from, store_to} (-1: the incoming image / nothing stored); fake, out:
+ * [batch][chw] fp32, pool: [pool_size][chw] fp32. Entries are applied in order (the reference's semantics). */
+int cdb_image_pool_apply(const float* fake, float* pool, const int32_t* plan_dev, int32_t batch, int64_t chw,
+                         float* out, cdbStream_t stream);
 
 /* ---- K7: depth metrics ---------------------------------------------------------------------------
  * new_multi/my_eval.py:7-31 (compute_errors) applied as in eval_metric :52-100 to n_img pairs of

@@ -135,3 +135,40 @@ def test_fused_adam_matches_torch_adam():
         a.step()
         b.step()
     assert rel_l2(p1, p2) < 1e-6
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """opt.cuda_graph: three eager warm-up steps, capture, replays. Same seeds => the ImagePool draws the same
+    decisions (trace identical) and the losses follow the eager run (both runs use atomics, so not bit-equal)."""
+    import argparse
+    import random
+    from cycle_depth_estimation_b200.cycle_gan_model import CycleGANModel
+
+    def run(graph):
+        opt = argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_6blocks', netD='basic',
+                                 n_layers_D=3, norm='instance', no_dropout=True, init_type='normal', init_gain=0.02,
+                                 no_lsgan=False, pool_size=5, lr=2e-4, beta1=0.5, lambda_A=10.0, lambda_B=10.0,
+                                 lambda_identity=0.5, isTrain=True, device='cuda', direction='AtoB', cuda_graph=graph)
+        torch.manual_seed(0)
+        random.seed(77)
+        model = CycleGANModel()
+        with quiet():
+            model.initialize(opt)
+        hist = []
+        for step in range(7):
+            a, b = seeded_image(2, 3, 64, 64, seed=100 + step), seeded_image(2, 3, 64, 64, seed=200 + step)
+            model.set_input({'img_source': a, 'img_target': b})
+            model.optimize_parameters('train')
+            hist.append(model.get_current_losses())
+        return hist, model.fake_A_pool.trace, model.fake_B_pool.trace, model
+
+    eager, ta, tb, _ = run(False)
+    graphed, ga, gb, model = run(True)
+    assert model._graph is not None
+    assert ta == ga and tb == gb
+    # The losses of this tiny case (batch 2, 64x64: the PatchGAN outputs 6x6 values) move by 1-3 % between two
+    # EAGER runs already (atomic summation order + Adam's sign-like first updates, tools/debug_graph.py), so the
+    # graphed run is only required to follow the eager one within 10 %; the decisions of both pools are identical.
+    for step, (e, g) in enumerate(zip(eager, graphed)):
+        for k in e:
+            assert abs(e[k] - g[k]) <= 0.1 * max(abs(e[k]), 1e-2), (step, k, e[k], g[k])
