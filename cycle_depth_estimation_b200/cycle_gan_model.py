@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import losses, networks, ops
+from .graph_step import StepGraph
 from .image_pool import ImagePool
 
 
@@ -151,8 +152,7 @@ class CycleGANModel:
                                 lr=opt.lr, betas=(opt.beta1, 0.999))
         self.optimizer_D = adam(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()),
                                 lr=opt.lr, betas=(opt.beta1, 0.999))
-        self._graph, self._graph_calls, self._plan_host, self._plan_dev = None, 0, None, None
-        self._plan_slot, self._plan_event, self._side_stream = 0, None, None
+        self._step_graph, self._plan_host, self._plan_dev, self._plan_slot = StepGraph(), None, None, 0
         self.optimizers = [self.optimizer_G, self.optimizer_D]
         self._buckets_G = GradBuckets(itertools.chain(self.netG_A.parameters(), self.netG_B.parameters()))
         self._buckets_D = GradBuckets(itertools.chain(self.netD_A.parameters(), self.netD_B.parameters()))
@@ -161,7 +161,7 @@ class CycleGANModel:
         if getattr(self, '_graph_mode', False):
             # static input buffers: a captured step keeps reading the same device addresses
             a, b = input['img_source'], input['img_target']
-            if getattr(self, 'real_A', None) is None or self.real_A.shape != a.shape or self._graph is None:
+            if getattr(self, 'real_A', None) is None or self.real_A.shape != a.shape:
                 if self._graph is not None:
                     raise RuntimeError("cuda_graph mode: the input shape changed after the step was captured")
                 if getattr(self, 'real_A', None) is None or self.real_A.shape != a.shape:
@@ -243,15 +243,14 @@ class CycleGANModel:
     # reach the device through a pinned table copied by the graph's first node; Adam reads its step count
     # from device memory.
     # ---------------------------------------------------------------------------------------------
-    GRAPH_WARMUP_STEPS = 3
+    GRAPH_WARMUP_STEPS = StepGraph.WARMUP_STEPS
 
     def _draw_pool_plans(self):
         b = self.real_A.shape[0]
         if self._plan_host is None:
             self._plan_host = torch.empty((8, b, 2), dtype=torch.int32).pin_memory()
             self._plan_dev = torch.empty((8, b, 2), dtype=torch.int32, device=self.device)
-        if self._plan_event is not None:
-            self._plan_event.synchronize()      # the previous replay has consumed the pinned table
+        self._step_graph.wait_previous()        # the previous replay has consumed the pinned table
         rows = []
         for _ in range(4):                      # the order of backward_D_A / backward_D_B in the step
             rows.append(self.fake_B_pool.plan(b))
@@ -259,42 +258,26 @@ class CycleGANModel:
         self._plan_host.copy_(torch.tensor(rows, dtype=torch.int32))
         self._plan_slot = 0
 
+    @property
+    def _graph(self):
+        return self._step_graph.graph
+
+    @property
+    def _graph_launches(self):
+        return self._step_graph.launches
+
     def _graphed_step(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             raise RuntimeError("opt.cuda_graph is a single-process mode (data-parallel steps run eagerly)")
         self._draw_pool_plans()
-        if self._graph is not None:
-            self._graph.replay()
-            self._plan_event.record()
-            return
-        self._graph_calls += 1
-        if self._graph_calls <= self.GRAPH_WARMUP_STEPS:
-            # warm-up on a side stream: autograd binds each parameter's gradient accumulator to the stream that
-            # was current when it was created, and a node bound to the legacy default stream cannot take part in
-            # a capture (cudaErrorStreamCaptureImplicit)
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream()
-            cur = torch.cuda.current_stream()
-            self._side_stream.wait_stream(cur)
-            with torch.cuda.stream(self._side_stream):
-                self._plan_dev.copy_(self._plan_host, non_blocking=True)
-                self._eager_step(True)
-            cur.wait_stream(self._side_stream)
-            return
-        self.optimizer_G.zero_grad()
-        self.optimizer_D.zero_grad()
-        from . import _lib
-        graph = torch.cuda.CUDAGraph()
-        torch.cuda.synchronize()
-        n0 = _lib.lib().cdb_launch_count()
-        with torch.cuda.graph(graph):
+        if self._step_graph.graph is None and self._step_graph.calls >= StepGraph.WARMUP_STEPS:
+            self.optimizer_G.zero_grad()        # gradients must be (re)allocated inside the capture
+            self.optimizer_D.zero_grad()
+
+        def step():
             self._plan_dev.copy_(self._plan_host, non_blocking=True)
             self._eager_step(True)
-        self._graph_launches = _lib.lib().cdb_launch_count() - n0   # library kernels inside one replay
-        self._graph = graph
-        graph.replay()      # capture records the step, the replay performs it
-        self._plan_event = torch.cuda.Event()
-        self._plan_event.record()
+        self._step_graph.run(step)
 
     def optimize_parameters(self, train_or_test='train'):
         if getattr(self, '_graph_mode', False) and train_or_test == 'train':

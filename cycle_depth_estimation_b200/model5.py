@@ -21,6 +21,7 @@ import torch
 
 from . import losses, networks5_ds
 from .cycle_gan_model import FusedAdam, GradBuckets
+from .graph_step import StepGraph
 from .image_pool import ImagePool
 from .networks5_ds import get_masks, init_net
 
@@ -40,7 +41,13 @@ class Seg_Depth:
         self.net_G_1 = self._build(networks5_ds.G_1(), getattr(opt, 'g1_checkpoint', None), itype, igain)
         self.net_G_2 = self._build(networks5_ds.General_net(), getattr(opt, 'g2_checkpoint', None), itype, igain)
         self.net_R_D = init_net(networks5_ds.R_dep(), itype, igain)
-        adam = FusedAdam if getattr(opt, 'fused_adam', True) else torch.optim.Adam
+        # opt.cuda_graph (single process): the whole step — eight optimizer updates included — replays as one graph
+        self._graph_mode = bool(getattr(opt, 'cuda_graph', False))
+        self._step_graph = StepGraph()
+        if getattr(opt, 'fused_adam', True):
+            adam = lambda ps, **kw: FusedAdam(ps, device_step=self._graph_mode, **kw)
+        else:
+            adam = torch.optim.Adam
         mk = lambda net, f: adam(net.parameters(), lr=opt.lr / f, betas=(opt.beta1, 0.999))
         self.optimizer_G_1, self.optimizer_G_2, self.optimizer_R_D = mk(self.net_G_1, 5), mk(self.net_G_2, 3), \
             mk(self.net_R_D, 2)
@@ -66,14 +73,24 @@ class Seg_Depth:
 
     def set_input(self, input, train_or_test='train'):
         dev = torch.device('cuda')
-        self.real_img = input['img_real'].to(dev, non_blocking=True)
-        self.syn_img = input['img_syn'].to(dev, non_blocking=True)
         self.is_Train = train_or_test == 'train'
+        fields = [('real_img', input['img_real']), ('syn_img', input['img_syn']),
+                  ('syn_seg_l', input['seg_l_syn'].squeeze(1)), ('syn_dep_l', input['dep_l_syn'].squeeze(1)),
+                  ('syn_dep_ls', input['depth_l_s'].float())]
         if self.is_Train:
-            self.real_seg_l = input['seg_l_real'].squeeze(1).to(dev, non_blocking=True)
-        self.syn_seg_l = input['seg_l_syn'].squeeze(1).to(dev, non_blocking=True)
-        self.syn_dep_l = input['dep_l_syn'].squeeze(1).to(dev, non_blocking=True)
-        self.syn_dep_ls = input['depth_l_s'].float().to(dev, non_blocking=True)
+            fields.append(('real_seg_l', input['seg_l_real'].squeeze(1)))
+        for name, src in fields:
+            if self._graph_mode:
+                # static buffers: the captured step keeps reading the same device addresses
+                cur = getattr(self, name, None)
+                if cur is None or cur.shape != src.shape or cur.dtype != src.dtype:
+                    if self._step_graph.graph is not None:
+                        raise RuntimeError("cuda_graph mode: the input shape changed after the step was captured")
+                    cur = torch.empty(tuple(src.shape), dtype=src.dtype, device=dev)
+                    setattr(self, name, cur)
+                cur.copy_(src, non_blocking=True)
+            else:
+                setattr(self, name, src.to(dev, non_blocking=True))
 
     def set_requires_grad(self, nets, requires_grad=False):
         if not isinstance(nets, list):
@@ -85,11 +102,9 @@ class Seg_Depth:
 
     @staticmethod
     def _sky_mask(seg_l):
-        """model5.py:524-526: 0 where the label is 17 (sky), 1 elsewhere."""
-        sky_m = seg_l.clone()
-        sky_m[sky_m != 17] = 1
-        sky_m[seg_l == 17] = 0
-        return sky_m
+        """model5.py:524-526: 0 where the label is 17 (sky), 1 elsewhere (written without boolean-mask
+        assignment, which synchronises with the host and cannot be captured in a CUDA graph)."""
+        return (seg_l != 17).to(seg_l.dtype)
 
     # ------------------------------------------------------------------ :585-638
     def backward_G_2(self):
@@ -178,6 +193,19 @@ class Seg_Depth:
 
     # ------------------------------------------------------------------ :640-696
     def optimize_parameters(self, train_or_test='train'):
+        if self._graph_mode and train_or_test == 'train':
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                raise RuntimeError("opt.cuda_graph is a single-process mode (data-parallel steps run eagerly)")
+            sg = self._step_graph
+            if sg.graph is None and sg.calls >= StepGraph.WARMUP_STEPS:
+                for o in (self.optimizer_G_1, self.optimizer_G_2, self.optimizer_R_D, self.optimizer_FD1,
+                          self.optimizer_FD2, self.optimizer_FD3):
+                    o.zero_grad()               # gradients must be (re)allocated inside the capture
+            return sg.run(lambda: self._eager_step('train'))
+        return self._eager_step(train_or_test)
+
+    def _eager_step(self, train_or_test='train'):
         train = train_or_test == 'train'
         self.set_requires_grad(self.net_G_2, True)
         self.optimizer_G_2.zero_grad()

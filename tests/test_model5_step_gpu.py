@@ -73,3 +73,29 @@ def test_seg_depth_step_losses():
                           + O5.gan_mse(O5.discriminator(fd, model.syn_feats[i].detach()), False))
                 assert abs(got[k] - float(tf)) <= 3e-2 * abs(float(tf)), (k, got[k], float(tf), ref[k], env[k])
     assert model.syn_dep_ref.shape == (2, 192, 256) and model.real_dep_ref.shape == (2, 192, 256)
+
+
+def test_seg_depth_cuda_graph_step_follows_the_eager_step():
+    """opt.cuda_graph: 3 eager warm-up steps, capture, replays. The stable losses must follow the eager run."""
+    from cycle_depth_estimation_b200.model5 import Seg_Depth
+
+    def run(graph):
+        torch.manual_seed(0)
+        model = Seg_Depth()
+        with quiet():
+            model.initialize(argparse.Namespace(lr=2e-4, beta1=0.5, pool_size=50, cuda_graph=graph))
+        hist = []
+        for step in range(6):
+            model.set_input(_inputs(1, 192, 256, 300 + step), 'train')
+            model.optimize_parameters('train')
+            hist.append(model.get_current_losses())
+        return hist, model
+
+    eager, _ = run(False)
+    graphed, model = run(True)
+    assert model._step_graph.graph is not None and model._step_graph.launches > 1000
+    for step, (e, g) in enumerate(zip(eager, graphed)):
+        for k in ('G2', 'G1', 'RD_syn', 'dep_ref'):
+            assert abs(e[k] - g[k]) <= 5e-2 * max(abs(e[k]), 1e-2), (step, k, e[k], g[k])
+        # RD_real contains 0.2 x the three (chaotic, see the module docstring) feature-discriminator terms
+        assert abs(e['RD_real'] - g['RD_real']) <= 0.2 * abs(e['RD_real']), (step, e['RD_real'], g['RD_real'])
