@@ -294,6 +294,7 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
     run.stats = [None] * len(plan.stages)
     run.training = training
     run.out = None
+    arena = ops.ZeroArena(dev)
 
     # ---- value 0: the image, converted to NHWC bf16 with the first conv's padding materialised
     st0 = plan.stages[0]
@@ -384,7 +385,7 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         bias = conv.bias if use_running else None
         if not use_running:
             groups = n if nk == NORM_INSTANCE else 1
-            stats = torch.zeros((groups, co, 2), dtype=torch.float32, device=dev)
+            stats = arena.take((groups, co, 2))
         if nk == NORM_INSTANCE:
             ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(y, co), bias, ACT_NONE, 0.0, stats)
         else:
@@ -418,6 +419,7 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
     grads = {}
     stages = plan.stages
     # gradient contributions per value: padded conv-dgrad result and skip (residual) gradient
+    arena = ops.ZeroArena(dev)
     dpad = [None] * plan.n_values   # full buffer incl. halo (gradient w.r.t. the padded value)
     dskip = [None] * plan.n_values
     gx = None
@@ -466,7 +468,7 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
             use_running = nk == NORM_BATCH and not run.training and st.norm.track_running_stats
             groups = n if nk == NORM_INSTANCE else 1
             need_b = (nk != NORM_NONE and not use_running) or (nk == NORM_NONE and want_b) or affine
-            bstats = torch.zeros((groups, co, 2), dtype=torch.float32, device=dev) if need_b else None
+            bstats = arena.take((groups, co, 2)) if need_b else None
             desc = ops.norm_desc(nk, st.act, st.slope, float(st.norm.eps) if st.norm is not None else 0.0, co, halo,
                                  run.stats[idx], st.norm.weight if affine else None,
                                  st.norm.bias if affine else None,
@@ -485,7 +487,7 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                 grads[conv.bias] = bstats[0, :, 0].contiguous()
             elif want_b:
                 if use_running:
-                    bs = torch.zeros((1, co, 2), dtype=torch.float32, device=dev)
+                    bs = arena.take((1, co, 2))
                     ops.channel_stats(dy, co, False, bs)
                     grads[conv.bias] = bs[0, :, 0].contiguous()
                 else:

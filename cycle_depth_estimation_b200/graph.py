@@ -71,6 +71,7 @@ class Tape:
         self.param_grads = {}
         self.needs = {}            # param -> bool, filled in before the backward replay
         self.seed_counter = [0]
+        self.arena = ops.ZeroArena(device)
 
     # ---------------------------------------------------------------- bookkeeping
     def _on_backward(self, fn):
@@ -151,7 +152,7 @@ class Tape:
         if f32grad and self.record:
             v.grad32 = torch.zeros((n, h, w, ops.round_up(c, 8)), dtype=torch.float32, device=self.dev)
         if stats:
-            v.stats = torch.zeros((1, c, 2), dtype=torch.float32, device=self.dev)
+            v.stats = self.arena.take((1, c, 2))
         return v
 
     # ---------------------------------------------------------------- module boundary
@@ -321,7 +322,7 @@ class Tape:
             bias = conv.bias if (use_running or act_first) else None
             if not use_running:
                 groups = n if nk == NORM_INSTANCE else 1
-                stats = torch.zeros((groups, co, 2), dtype=torch.float32, device=self.dev)
+                stats = self.arena.take((groups, co, 2))
             ops.conv2d_fwd_ex(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(y, co), bias,
                               act if act_first else ACT_NONE, slope, stats, stats_batch=(nk == NORM_BATCH))
             affine = getattr(norm, "affine", False)
@@ -395,7 +396,7 @@ class Tape:
                 if need_kernel:
                     if dy is None:
                         dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
-                    bstats = torch.zeros((1, co, 2), dtype=torch.float32, device=dev) if want_b else None
+                    bstats = self.arena.take((1, co, 2)) if want_b else None
                     desc = ops.norm_desc(NORM_NONE, act, slope, 0.0, co, halo_fold)
                     if act in (ACT_TANH, ACT_SIGMOID):
                         raise NotImplementedError("tanh / sigmoid inside a network (only at fp32 outputs)")
@@ -408,7 +409,7 @@ class Tape:
                 if dy is None:
                     dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
                 groups = n if nk == NORM_INSTANCE else 1
-                bstats = torch.zeros((groups, co, 2), dtype=torch.float32, device=dev)
+                bstats = self.arena.take((groups, co, 2))
                 desc = self._norm_desc(nk, norm, act, slope, co, halo_fold, stats, use_running,
                                        flags=NORM_FLAG_ACT_FIRST if act_first else 0)
                 gsum = None
@@ -419,7 +420,7 @@ class Tape:
                     self.add_grad(res, gsum if gsum is not None else dout)
                 if want_b:
                     if use_running or act_first:
-                        bs = torch.zeros((1, co, 2), dtype=torch.float32, device=dev)
+                        bs = self.arena.take((1, co, 2))
                         ops.channel_stats(dy, co, False, bs)
                         self.add_param_grad(conv.bias, bs[0, :, 0].contiguous())
                     else:
@@ -494,7 +495,7 @@ class Tape:
                 stats = x.stats
             else:
                 groups = n if nk == NORM_INSTANCE else 1
-                stats = torch.zeros((groups, c, 2), dtype=torch.float32, device=self.dev)
+                stats = self.arena.take((groups, c, 2))
                 ops.channel_stats(x.t, c, nk == NORM_INSTANCE, stats)
         outv = out if out is not None else self.new_val(n, h, w, c, halo, halo_kind)
         desc = self._norm_desc(nk, norm, act, slope, c, outv.halo if outv.halo_kind == 'reflect' else 0, stats,
@@ -513,7 +514,7 @@ class Tape:
                 groups = n if nk == NORM_INSTANCE else 1
                 bstats = None
                 if nk != NORM_NONE and not use_running or affine:
-                    bstats = torch.zeros((groups, c, 2), dtype=torch.float32, device=self.dev)
+                    bstats = self.arena.take((groups, c, 2))
                 fold = outv.halo if outv.halo_kind == 'reflect' else 0
                 flags = NORM_FLAG_ACCUM_F32 if x.grad32 is not None else 0
                 desc_b = self._norm_desc(nk, norm, act, slope, c, fold, stats, use_running, flags=flags)
@@ -568,7 +569,7 @@ class Tape:
         c = s.c
         na, ha, wa, _ = att.t.shape
         assert att.c == c and na == n
-        sums = torch.zeros((n, c, 2), dtype=torch.float32, device=self.dev)
+        sums = self.arena.take((n, c, 2))
         ops.channel_stats(att.t, c, True, sums)
         inv = 1.0 / float(ha * wa)
         outv = out if out is not None else self.new_val(n, h, w, c, halo, halo_kind)
@@ -579,7 +580,7 @@ class Tape:
                 if g is None:
                     return
                 ds = torch.empty(tuple(s.t.shape), dtype=BF16, device=self.dev)
-                dsum = torch.zeros((n, c), dtype=torch.float32, device=self.dev)
+                dsum = self.arena.take((n, c))
                 ops.gate_bwd(g, s.t, sums, c, inv, ds, dsum)
                 self.add_grad(s, ds)
                 if base is not None:
