@@ -230,9 +230,10 @@ def b200_arm(args):
             m.initialize(make_opt("cuda", use_graph))
         return m
 
-    # single process: the whole step is replayed as ONE CUDA graph (cycle_gan_model.py); data-parallel runs and
-    # --no-cuda-graph use eager launches. A failed capture falls back to eager and says so in the JSON line.
-    use_graph = world == 1 and not args.no_cuda_graph
+    # The whole step is replayed as ONE CUDA graph (cycle_gan_model.py) — under data parallelism the NCCL
+    # all-reduces / all-gathers are captured with it; --no-cuda-graph issues eager launches. A failed
+    # single-process capture restarts the process without graphs.
+    use_graph = not args.no_cuda_graph
     graph_note = "cuda graph replay of the whole step" if use_graph else "eager launches"
     model = build(use_graph)
     if use_graph:
@@ -248,6 +249,8 @@ def b200_arm(args):
                   file=sys.stderr)
             # a failed capture leaves the CUDA context / RNG in capture state: restart the process without graphs
             sys.stderr.flush()
+            if world > 1:
+                raise
             os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-cuda-graph"])
 
     def barrier():
@@ -305,10 +308,21 @@ def b200_arm(args):
            "ms_per_step": ms_e2e}
     abort = lib.cdb_device_abort_flag()
 
-    if rank != 0:
+    def finish():
+        """Data-parallel teardown. With a captured step (NCCL kernels inside the graph) alive, a further barrier /
+        destroy_process_group was observed to block on this stack; every timed region above already ended with a
+        barrier, so the ranks simply flush and leave (process exit releases the communicator)."""
         if world > 1:
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            if use_graph:
+                os._exit(0)
             dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        finish()
         return
     # ---- generator inference (BASELINE configs[0]) and the dominant kernel, rank 0 only
     with torch.no_grad():
@@ -351,10 +365,7 @@ def b200_arm(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-
+    finish()
 
 
 # ---------------------------------------------------------------------------------------------------

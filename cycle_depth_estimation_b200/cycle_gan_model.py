@@ -193,6 +193,13 @@ class CycleGANModel:
         if self._plan_dev is not None:
             slot = self._plan_slot
             self._plan_slot += 1
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                world, rank = dist.get_world_size(), dist.get_rank()
+                gathered = torch.empty((world,) + tuple(fake.shape), dtype=fake.dtype, device=fake.device)
+                dist.all_gather_into_tensor(gathered, fake.detach().contiguous())
+                out = pool.query_planned(gathered.view((-1,) + tuple(fake.shape[1:])), self._plan_dev[slot])
+                b = fake.shape[0]
+                return out[rank * b:(rank + 1) * b]
             return pool.query_planned(fake, self._plan_dev[slot])
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             world, rank = dist.get_world_size(), dist.get_rank()
@@ -247,6 +254,8 @@ class CycleGANModel:
 
     def _draw_pool_plans(self):
         b = self.real_A.shape[0]
+        if dist.is_available() and dist.is_initialized():
+            b *= dist.get_world_size()          # replicated pools see the global batch in rank-major order
         if self._plan_host is None:
             self._plan_host = torch.empty((8, b, 2), dtype=torch.int32).pin_memory()
             self._plan_dev = torch.empty((8, b, 2), dtype=torch.int32, device=self.device)
@@ -267,8 +276,6 @@ class CycleGANModel:
         return self._step_graph.launches
 
     def _graphed_step(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise RuntimeError("opt.cuda_graph is a single-process mode (data-parallel steps run eagerly)")
         self._draw_pool_plans()
         if self._step_graph.graph is None and self._step_graph.calls >= StepGraph.WARMUP_STEPS:
             self.optimizer_G.zero_grad()        # gradients must be (re)allocated inside the capture

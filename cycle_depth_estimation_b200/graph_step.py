@@ -51,7 +51,9 @@ class StepGraph:
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
         n0 = _lib.lib().cdb_launch_count()
-        with torch.cuda.graph(graph):
+        # thread_local: other threads (NCCL's watchdog under data parallelism) may keep calling CUDA APIs that
+        # the default global capture mode forbids while this thread captures
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             step_fn()
         self.launches = _lib.lib().cdb_launch_count() - n0
         self.graph = graph
