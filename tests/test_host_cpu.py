@@ -92,3 +92,48 @@ def test_gan_loss_buffers_in_state_dict():
     crit = N.GANLoss(use_lsgan=True)
     assert set(crit.state_dict()) == {'real_label', 'fake_label'}
     assert crit.get_target_tensor(torch.zeros(2, 1, 3, 3), True).shape == (2, 1, 3, 3)
+
+
+def test_image_pool_plan_draws_the_same_decisions_as_query():
+    """ImagePool.plan (the up-front decisions of the CUDA-graph step) consumes Python's ``random`` exactly like
+    ImagePool.query: same trace, same RNG state afterwards."""
+    import random
+    import torch
+    from cycle_depth_estimation_b200.image_pool import ImagePool
+    random.seed(4321)
+    a = ImagePool(5)
+    for q in range(12):
+        a.query(torch.zeros((3, 1, 2, 2)))
+    state_a = random.getstate()
+    random.seed(4321)
+    b = ImagePool(5)
+    plans = [b.plan(3) for _ in range(12)]
+    assert a.trace == b.trace and random.getstate() == state_a
+    flat = [p for plan in plans for p in plan]
+    for (kind, idx), (ret, sto) in zip(a.trace, flat):
+        assert (ret, sto) == {'fill': (-1, idx), 'swap': (idx, idx), 'pass': (-1, -1)}[kind]
+
+
+def test_zero_arena_hands_out_disjoint_zero_views():
+    import torch
+    from cycle_depth_estimation_b200 import ops
+    arena = ops.ZeroArena(torch.device('cpu'))
+    a, b = arena.take((2, 3, 2)), arena.take((1, 5))
+    big = arena.take((ops.ZeroArena.CHUNK + 8,))
+    a += 1
+    assert float(b.sum()) == 0.0 and float(big.sum()) == 0.0 and a.shape == (2, 3, 2) and big.numel() == ops.ZeroArena.CHUNK + 8
+
+
+def test_unet_levels_and_networks5_module_trees():
+    from cycle_depth_estimation_b200 import networks as N, networks5_ds as N5
+    net = N.UnetGenerator(3, 3, 8, 64, N.get_norm_layer('batch'), True)
+    lv = net._levels()
+    assert len(lv) == 8 and lv[0][1] is None and lv[-1][1] is None and lv[-1][3] is not None
+    assert [l[4] is not None for l in lv] == [False, False, False, False, True, True, True, False]
+    d = N5._Discriminator(input_nc=128)
+    assert d.model[1] is d.model[10] and 'model.10.weight' in d.state_dict()
+    assert sum(p.numel() for p in N5.G_1().parameters()) == 615808
+    assert sum(p.numel() for p in N5.General_net().parameters()) == 22808448
+    assert sum(p.numel() for p in N5.R_dep().parameters()) == 52765086
+    with __import__('pytest').raises(RuntimeError):
+        N5.G_1()(__import__('torch').zeros(1, 3, 32, 32))     # CPU tensors are refused: no fallback path
