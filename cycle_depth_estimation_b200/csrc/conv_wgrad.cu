@@ -315,7 +315,8 @@ static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g
   pl->k_tiles = pl->tiles_w * pl->tiles_h * pl->tiles_n;
   pl->n_taps = g->rowpack ? g->r : g->r * g->s;
   const int items = pl->n_taps * pl->m_tiles * pl->n_tiles;
-  int splits = (2 * sm_count()) / (items > 0 ? items : 1);
+  static const int waves = getenv("CDB_WGRAD_WAVES") ? atoi(getenv("CDB_WGRAD_WAVES")) : 1;
+  int splits = (waves * sm_count()) / (items > 0 ? items : 1);
   if (splits < 1) splits = 1;
   int max_splits = pl->k_tiles / 8;
   if (max_splits < 1) max_splits = 1;
