@@ -489,8 +489,9 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   CDB_REQUIRE(!(g->flip && (g->transposed || g->rowpack)), CDB_ERR_UNSUPPORTED, "conv2d_fwd: flip with transposed/rowpack");
   // Stride-1 convolutions over a contiguous buffer with materialised padding take the flat kernel
   // (A rows shared by the S taps of a filter row, two accumulators per weight tile).
-  if (!g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw == x->c &&
-      x->sh == (int64_t)x->w * x->c && x->sn == (int64_t)x->h * x->w * x->c &&
+  // (the buffer may be a channel prefix of a wider concatenation buffer: pixel pitch sw >= c, regular rows)
+  if (!g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw >= x->c &&
+      x->sh == (int64_t)x->w * x->sw && x->sn == (int64_t)x->h * x->w * x->sw &&
       y->h <= x->h - (g->r - 1) * g->dil && y->w <= x->w - (g->s - 1) * g->dil && y->n == x->n &&
       (g->s - 1) * g->dil <= 64 && (int64_t)y->h * x->w >= 256 && !env_flag("CDB_DISABLE_FLAT", 0)) {
     return launch_flat_conv(g, x, wpacked, w_rows_pad, w_kpad, y, ep, g->flip, env_flag("CDB_FLAT_BASE_OFFSET", 0),

@@ -671,3 +671,53 @@ extern "C" int cdb_shift_add_nchw(const float* t, int32_t n, int32_t p, int32_t 
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
+
+// ---- zero frame: clears every pixel of a padded buffer OUTSIDE the interior rectangle (the materialised zero
+// padding of the next convolution / the halo of a data-gradient operand) instead of memsetting the whole buffer
+namespace cdb {
+__global__ void __launch_bounds__(256)
+zero_frame_kernel(PView full, int top, int left, int ih, int iw, int64_t frame_px, int64_t total, int cvn) {
+  const int W = full.w, H = full.h;
+  const int64_t top_band = (int64_t)top * W, mid_band = (int64_t)ih * (W - iw);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvn);
+    int64_t t = idx / cvn;
+    const int64_t j = t % frame_px;
+    const int n = (int)(t / frame_px);
+    int h, w;
+    if (j < top_band) {
+      h = (int)(j / W);
+      w = (int)(j % W);
+    } else if (j < top_band + mid_band) {
+      const int64_t jj = j - top_band;
+      const int r = (int)(jj / (W - iw)), cidx = (int)(jj % (W - iw));
+      h = top + r;
+      w = cidx < left ? cidx : cidx + iw;
+    } else {
+      const int64_t jj = j - top_band - mid_band;
+      h = top + ih + (int)(jj / W);
+      w = (int)(jj % W);
+    }
+    (void)H;
+    *reinterpret_cast<uint4*>(bfw(full, n, h, w, cv * 8)) = z;
+  }
+}
+}  // namespace cdb
+
+extern "C" int cdb_zero_frame(const CdbAct* full, int32_t top, int32_t left, int32_t inner_h, int32_t inner_w,
+                              cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(full, "zero_frame buffer"))) return rc;
+  CDB_REQUIRE(top >= 0 && left >= 0 && inner_h >= 0 && inner_w >= 0 && top + inner_h <= full->h &&
+                  left + inner_w <= full->w,
+              CDB_ERR_BAD_DESC, "zero_frame: interior outside the buffer");
+  const int64_t frame_px = (int64_t)full->h * full->w - (int64_t)inner_h * inner_w;
+  const int64_t total = frame_px * full->n * (full->c / 8);
+  if (total == 0) return CDB_OK;
+  zero_frame_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(full), top, left, inner_h, inner_w, frame_px, total,
+                                                        full->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}

@@ -358,7 +358,7 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         if zh:
             if halo:
                 raise NotImplementedError("value with both a reflect and a zero halo")
-            dbuf = torch.zeros((n, ho + 2 * zh, wo + 2 * zh, cs), dtype=BF16, device=dev)
+            dbuf = ops.empty_zero_halo(n, ho, wo, cs, zh, 0, dev)
             dinner = dbuf[:, zh:zh + ho, zh:zh + wo, :]
         else:
             dbuf = torch.empty((n, ho + 2 * halo, wo + 2 * halo, cs), dtype=BF16, device=dev)
@@ -449,7 +449,7 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
         if flat_dgrad or fold_dgrad:
             hz = (conv.kernel_size[0] - 1) * conv.dilation[0]
             slack = 64 // cs if cs <= 16 else 0   # room for the row-packed view used by the few-channel wgrad
-            dyp = torch.zeros((n, ho + 2 * hz, wo + 2 * hz + slack, cs), dtype=BF16, device=dev)
+            dyp = ops.empty_zero_halo(n, ho, wo, cs, hz, slack, dev)
             dy = dyp[:, hz:hz + ho, hz:hz + wo, :]
         else:
             dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)

@@ -62,6 +62,14 @@ def _act_of(m):
     return engine._act_of(m)
 
 
+def _regular_pitch(t):
+    """[N,H,W,C] view whose pixels are evenly pitched (contiguous, or a channel prefix of a wider buffer): the
+    flat convolution kernel addresses it as a 2-D matrix [N*H*W, C] with row pitch stride(2)."""
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    return sc == 1 and sw >= c and sh == w * sw and sn == h * w * sw
+
+
 class Tape:
     def __init__(self, training, device, record):
         self.training = training
@@ -139,7 +147,7 @@ class Tape:
     def new_val(self, n, h, w, c, halo=0, halo_kind=None, slack_w=0):
         cs = ops.round_up(c, 8)
         if halo and halo_kind == 'zero':
-            buf = torch.zeros((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=BF16, device=self.dev)
+            buf = ops.empty_zero_halo(n, h, w, cs, halo, slack_w, self.dev)
         else:
             buf = torch.empty((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=BF16, device=self.dev)
         t = buf[:, halo:halo + h, halo:halo + w, :]
@@ -279,7 +287,7 @@ class Tape:
         rowpack = x.rowpack
         g = ops.geom(k, k, stride, pad, pad, dil, transposed, rowpack)
         wp, rows_pad, kpad = _pack.get(conv.weight, not transposed, rowpack)
-        flat = (not transposed and stride == 1 and not rowpack and pad == 0 and xin.is_contiguous())
+        flat = (not transposed and stride == 1 and not rowpack and pad == 0 and _regular_pitch(xin))
         if norm is None:
             nk = NORM_NONE
         elif isinstance(norm, nn.InstanceNorm2d):
@@ -370,7 +378,7 @@ class Tape:
         if flat_dgrad:
             hz = (k - 1) * dil
             slack = 64 // cs if cs <= 16 else 0
-            dyp = torch.zeros((n, ho + 2 * hz, wo + 2 * hz + slack, cs), dtype=BF16, device=dev)
+            dyp = ops.empty_zero_halo(n, ho, wo, cs, hz, slack, dev)
             dy = dyp[:, hz:hz + ho, hz:hz + wo, :]
         else:
             dyp = None
@@ -466,6 +474,10 @@ class Tape:
             else:
                 gflip = ops.geom(k, k, 1, 0, 0, dil, False, 0, True)
                 ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+        elif k == 1 and stride == 1 and pad == 0 and not transposed and _regular_pitch(dy):
+            # the data gradient of a 1x1 convolution is a 1x1 convolution: flat kernel (plain GEMM, BM = 256)
+            dfull = ops.alloc_flat_output(n, hi, wi, wi, ops.round_up(ci, 8), dev)
+            ops.conv2d_fwd(ops.geom(1, 1), dy, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
         else:
             gd = ops.geom(k, k, stride, pad, pad, dil, not transposed, 0)
             dfull = torch.empty(tuple(xin.shape), dtype=BF16, device=dev)

@@ -428,3 +428,16 @@ class ZeroArena:
         out = self.buf[self.off:self.off + n].view(shape)
         self.off += need
         return out
+
+
+def zero_frame(full, top, left, inner_h, inner_w):
+    """Zeroes the pixels of the padded NHWC bf16 buffer `full` outside the interior rectangle."""
+    _require_cuda(full)
+    check(_lib.lib().cdb_zero_frame(_v(full), top, left, inner_h, inner_w, _stream()))
+
+
+def empty_zero_halo(n, h, w, cs, halo, slack_w, device):
+    """Uninitialised [n, h+2*halo, w+2*halo+slack_w, cs] bf16 buffer whose frame around the h x w interior is zero."""
+    buf = torch.empty((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=torch.bfloat16, device=device)
+    zero_frame(buf, halo, halo, h, w)
+    return buf

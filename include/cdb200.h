@@ -226,6 +226,11 @@ int cdb_dropout(const CdbAct* x, const CdbAct* out, uint64_t seed, float p_drop,
 /* NHWC bf16 view -> NCHW fp32 tensor (module outputs), dst strides in elements. */
 int cdb_nhwc_to_nchw(const CdbAct* x, int32_t c_real, float* dst, int64_t d_n, int64_t d_c, int64_t d_h,
                      int64_t d_w, cdbStream_t stream);
+/* Clears every pixel of the padded bf16 NHWC buffer `full` outside the interior rectangle
+ * [top, top+inner_h) x [left, left+inner_w): the materialised zero padding (nn.Conv2d(padding=p)) of the consuming
+ * convolution, written once by the producer instead of a memset of the whole buffer. */
+int cdb_zero_frame(const CdbAct* full, int32_t top, int32_t left, int32_t inner_h, int32_t inner_w, cdbStream_t stream);
+
 /* Second half of a few-output-channel convolution whose S filter columns were folded into the GEMM N dimension
  * (c7s1-3, models/networks.py:184-186; data gradient of c7s1-64, :158): t is the fp32 NHWC result
  * [n][p][wp][ct] of the R x 1 convolution with channel (s*cout + o);
