@@ -5,6 +5,8 @@
 // consecutive threads own consecutive channel vectors of a pixel, so every warp request is a run of
 // full 128-byte lines.  Per-channel coefficients are computed once per thread and reused over the
 // pixels the thread walks.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace cdb {
@@ -506,6 +508,176 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused InstanceNorm backward for images of <= 4096 pixels (the 64x64 residual-block layers and the
+// PatchGAN layers): ONE pass over HBM instead of reduce + apply.
+//   A thread-block cluster of 8 CTAs owns (image n, 32 channels); CTA r owns 1/8 of the pixels and keeps
+//   its y and g = fold(dout) + dskip vectors in REGISTERS (8 x 16 B each per thread, all loads issued
+//   up-front).  Per-channel sums are reduced inside the CTA through shared memory and across the cluster
+//   through distributed shared memory; the apply phase then runs from registers.
+// DRAM traffic = y + dout (+ dskip) read once + dy (+ gsum) written once = the algorithmic minimum (the
+// two-kernel form re-reads y and dout from DRAM in its second pass, profiles/r01_ncu_full_kernels_r01c.json).
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedCluster = 8;
+constexpr int kFusedVecs = 8;  // pixel vectors per thread
+
+template <int ACT>
+__global__ void __cluster_dims__(kFusedCluster, 1, 1) __launch_bounds__(256, 2)
+norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ uint4 fused_smem[];       // y vectors [8][256] then g vectors [8][256] (thread-private slots)
+  uint4* sy = fused_smem;
+  uint4* sg = fused_smem + kFusedVecs * 256;
+  __shared__ float red[16 * 256];
+  __shared__ float part[64];    // this CTA's partial (s1, s2) for its 32 channels: [vector][channel][2]
+  __shared__ float tot[64];
+  const int v = threadIdx.x & 3, lane = threadIdx.x >> 2;   // 4 channel vectors x 64 pixel lanes
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int cvec = blockIdx.y * 4 + v;
+  const int n = blockIdx.z;
+  const int pixels = p.H * p.W;
+  const int p0 = rank * ppc, p1 = min(pixels, p0 + ppc);
+  const int W = p.W, H = p.H, pad = p.pad;
+  float mean[8], rstd[8];
+  {
+    float scale[8], shift[8];
+    norm_coeffs(p.norm, 0, p.stats, nullptr, nullptr, nullptr, nullptr, n, p.C, cvec * 8, p.inv_count, p.eps,
+                scale, shift, mean, rstd);
+  }
+  const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
+  const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
+  const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  // two batches of four pixels: 8-12 independent 16-byte loads in flight per thread
+#pragma unroll
+  for (int ub = 0; ub < kFusedVecs; ub += 4) {
+    uint4 yr[4], gr[4], sr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = p0 + lane + (ub + k) * 64;
+      const int h = px / W, w = px - h * W;
+      if (px < p1) {
+        yr[k] = ld16(yb + h * p.y.sh + w * p.y.sw);
+        if (p.has_dout) gr[k] = ld16(db + h * p.dout.sh + w * p.dout.sw);
+        if (p.has_dskip) sr[k] = ld16(sb + h * p.dskip.sh + w * p.dskip.sw);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+    const int u = ub + k;
+    const int px = p0 + lane + u * 64;
+    if (px >= p1) continue;
+    const int h = px / W, w = px - h * W;
+    float g[8], f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    if (p.has_dout) {
+      unpack8(gr[k], g);
+      if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad)) add_folded_extras(p, db, h, w, g);
+    }
+    if (p.has_dskip) {
+      float t[8];
+      unpack8(sr[k], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += t[j];
+    }
+    sg[u * 256 + threadIdx.x] = pack8(g);   // the summed gradient (rounded to bf16 once) for the apply phase / gsum
+    sy[u * 256 + threadIdx.x] = yr[k];
+    unpack8(yr[k], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (f[j] - mean[j]) * rstd[j];
+      float ga = g[j];
+      if (ACT == CDB_ACT_RELU) ga = xhat > 0.f ? ga : 0.f;
+      else if (ACT == CDB_ACT_LEAKY) ga = xhat > 0.f ? ga : ga * p.slope;
+      s1[j] += ga;
+      s2[j] += ga * xhat;
+    }
+    }
+  }
+  // ---- CTA reduction over the 64 pixel lanes (same layout as the two-pass kernel: vt = 4)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[(j * 2) * 256 + threadIdx.x] = s1[j];
+    red[(j * 2 + 1) * 256 + threadIdx.x] = s2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int vv = threadIdx.x & 3, comp = threadIdx.x >> 2;   // comp = channel * 2 + {0: s1, 1: s2}
+    float acc = 0.f;
+    for (int l = 0; l < 64; ++l) acc += red[comp * 256 + l * 4 + vv];
+    part[vv * 16 + comp] = acc;
+  }
+  cluster.sync();
+  // ---- cluster reduction through distributed shared memory
+  if (threadIdx.x < 64) {
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < kFusedCluster; ++r) acc += cluster.map_shared_rank(part, r)[threadIdx.x];
+    tot[threadIdx.x] = acc * p.inv_count;
+  }
+  cluster.sync();   // also keeps every CTA's `part` alive until all ranks have read it
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m1[j] = tot[v * 16 + j * 2];
+    m2[j] = tot[v * 16 + j * 2 + 1];
+  }
+  // ---- apply from registers
+  __nv_bfloat16* ob = p.dy.ptr + n * p.dy.sn + cvec * 8;
+  __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
+#pragma unroll
+  for (int u = 0; u < kFusedVecs; ++u) {
+    const int px = p0 + lane + u * 64;
+    if (px >= p1) continue;
+    const int h = px / W, w = px - h * W;
+    float g[8], f[8], o[8];
+    const uint4 gv = sg[u * 256 + threadIdx.x];
+    unpack8(gv, g);
+    unpack8(sy[u * 256 + threadIdx.x], f);
+    if (gb != nullptr) st16(gb + h * p.gsum.sh + w * p.gsum.sw, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (f[j] - mean[j]) * rstd[j];
+      float ga = g[j];
+      if (ACT == CDB_ACT_RELU) ga = xhat > 0.f ? ga : 0.f;
+      else if (ACT == CDB_ACT_LEAKY) ga = xhat > 0.f ? ga : ga * p.slope;
+      o[j] = rstd[j] * (ga - m1[j] - xhat * m2[j]);
+    }
+    st16(ob + h * p.dy.sh + w * p.dy.sw, pack8(o));
+  }
+}
+
+static bool fused_in_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32) {
+  if (getenv("CDB_NORM_NO_FUSED")) return false;
+  const int pixels = p.H * p.W;
+  return d->norm == CDB_NORM_INSTANCE && !d->use_running && d->gamma == nullptr && d->beta == nullptr && !accum_f32 &&
+         p.pre_act == CDB_ACT_NONE && p.C % 32 == 0 && pixels <= kFusedCluster * kFusedVecs * 64 && pixels >= 64 &&
+         p.y.sh < (1 << 28);
+}
+
+static void launch_norm_bwd_fused(const NormBwdParams& p, int n, cudaStream_t stream) {
+  const int pixels = p.H * p.W;
+  const int ppc = ceil_div(pixels, kFusedCluster);
+  dim3 grid(kFusedCluster, p.C / 32, n);
+  const size_t smem = 2 * kFusedVecs * 256 * sizeof(uint4);   // 64 KB of thread-private y / g slots
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_LEAKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  switch (p.act) {
+    case CDB_ACT_RELU: norm_bwd_fused_in_kernel<CDB_ACT_RELU><<<grid, 256, smem, stream>>>(p, ppc); break;
+    case CDB_ACT_LEAKY: norm_bwd_fused_in_kernel<CDB_ACT_LEAKY><<<grid, 256, smem, stream>>>(p, ppc); break;
+    default: norm_bwd_fused_in_kernel<CDB_ACT_NONE><<<grid, 256, smem, stream>>>(p, ppc); break;
+  }
+}
+
 template <bool kApply, bool AFFINE>
 static void launch_norm_bwd_act(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
   switch (p.act) {
@@ -673,6 +845,11 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.bstats = bstats;
   p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 2);
   dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
+  if (fused_in_eligible(d, p, accum_f32)) {
+    launch_norm_bwd_fused(p, y->n, stream);
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
   if (need_reduce || (bstats && d->norm == CDB_NORM_NONE)) {
     // norm none + bstats: the reduction yields the bias gradient (sum of ga) in component 0
     launch_norm_bwd<false>(p, grid, stream);
