@@ -42,6 +42,11 @@ class CdbNormDesc(C.Structure):
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
 
 
+class CdbAdamEntry(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
+
+
 _lib = None
 
 

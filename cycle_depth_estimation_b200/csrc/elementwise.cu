@@ -233,6 +233,53 @@ __global__ void pool_apply_kernel(const float* __restrict__ fake, float* __restr
   }
 }
 
+// Multi-tensor Adam: up to kAdamMaxEntries parameter tensors per launch, their pointers passed in the (large,
+// __grid_constant__) kernel parameter block — no pointer table in device memory, so the launch is valid in a
+// CUDA graph as is. Block b finds its (tensor, chunk) by binary search over the cumulative chunk counts.
+constexpr int kAdamMaxEntries = 384;
+constexpr int kAdamChunk = 16384;
+struct AdamMultiParams {
+  int32_t n_entries, step;
+  float lr, b1, b2, eps;
+  const int32_t* step_dev;
+  CdbAdamEntry e[kAdamMaxEntries];
+  int32_t cum[kAdamMaxEntries + 1];
+};
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMultiParams q) {
+  int lo = 0, hi = q.n_entries;            // largest t with cum[t] <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (q.cum[mid] <= static_cast<int>(blockIdx.x)) lo = mid;
+    else hi = mid;
+  }
+  const CdbAdamEntry& en = q.e[lo];
+  const int64_t begin = static_cast<int64_t>(blockIdx.x - q.cum[lo]) * kAdamChunk;
+  const int64_t end = begin + kAdamChunk < en.numel ? begin + kAdamChunk : en.numel;
+  float bc1, bc2_sqrt;
+  if (q.step_dev != nullptr) {
+    const float st = static_cast<float>(*q.step_dev);
+    bc1 = 1.f - powf(q.b1, st);
+    bc2_sqrt = sqrtf(1.f - powf(q.b2, st));
+  } else {
+    bc1 = static_cast<float>(1.0 - pow(static_cast<double>(q.b1), static_cast<double>(q.step)));
+    bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(q.b2), static_cast<double>(q.step))));
+  }
+  const float step_size = q.lr / bc1;
+  float* __restrict__ p = en.param;
+  const float* __restrict__ g = en.grad;
+  float* __restrict__ m = en.exp_avg;
+  float* __restrict__ v = en.exp_avg_sq;
+  for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
+    const float gi = g[i];
+    const float mi = m[i] + (1.f - q.b1) * (gi - m[i]);
+    const float vi = q.b2 * v[i] + (1.f - q.b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + q.eps));
+  }
+}
+
 static int grid_for(int64_t n, int per_thread = 4) {
   int64_t b = (n + 256 * per_thread - 1) / (256 * per_thread);
   const int cap = sm_count() * 8;
@@ -366,5 +413,35 @@ extern "C" int cdb_image_pool_apply(const float* fake, float* pool, const int32_
   CDB_REQUIRE(fake && pool && plan_dev && out && batch > 0 && chw > 0, CDB_ERR_BAD_DESC, "image_pool_apply: bad argument");
   pool_apply_kernel<<<grid_for(chw, 1), 256, 0, stream>>>(fake, pool, plan_dev, batch, chw, out);
   CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entries, float lr, float beta1, float beta2,
+                              float eps, int32_t step, const int32_t* step_dev, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(entries_host && n_entries > 0 && (step >= 1 || step_dev), CDB_ERR_BAD_DESC, "adam_multi: bad argument");
+  static thread_local AdamMultiParams q;
+  for (int base = 0; base < n_entries; base += kAdamMaxEntries) {
+    const int n = n_entries - base < kAdamMaxEntries ? n_entries - base : kAdamMaxEntries;
+    q.n_entries = n;
+    q.step = step;
+    q.lr = lr;
+    q.b1 = beta1;
+    q.b2 = beta2;
+    q.eps = eps;
+    q.step_dev = step_dev;
+    int blocks = 0;
+    for (int i = 0; i < n; ++i) {
+      const CdbAdamEntry& en = entries_host[base + i];
+      CDB_REQUIRE(en.param && en.grad && en.exp_avg && en.exp_avg_sq && en.numel > 0, CDB_ERR_BAD_DESC,
+                  "adam_multi: bad entry %d", base + i);
+      q.e[i] = en;
+      q.cum[i] = blocks;
+      blocks += (int)((en.numel + kAdamChunk - 1) / kAdamChunk);
+    }
+    q.cum[n] = blocks;
+    adam_multi_kernel<<<blocks, 256, 0, stream>>>(q);
+    CDB_LAUNCH_OK();
+  }
   return CDB_OK;
 }

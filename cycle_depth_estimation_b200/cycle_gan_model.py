@@ -52,6 +52,7 @@ class FusedAdam:
             self._step_dev.add_(1)
         for g in self.param_groups:
             b1, b2 = g['betas']
+            groups = {}
             for p in g['params']:
                 if p.grad is None:
                     continue
@@ -60,14 +61,16 @@ class FusedAdam:
                     st = {'step': 0, 'exp_avg': torch.zeros_like(p), 'exp_avg_sq': torch.zeros_like(p)}
                     self.state[p] = st
                 st['step'] += 1
+                if p.grad.dtype != torch.float32 or not p.data.is_contiguous():
+                    raise TypeError("FusedAdam: contiguous fp32 parameters and gradients expected")
                 grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                if self.device_step:
-                    # every parameter of this optimizer takes its first step together, so one counter serves all
-                    ops.adam_step_dev(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'],
-                                      self._step_dev)
-                else:
-                    ops.adam_step(p.data, grad, st['exp_avg'], st['exp_avg_sq'], g['lr'], b1, b2, g['eps'],
-                                  st['step'])
+                groups.setdefault(st['step'], []).append((p.data, grad, st['exp_avg'], st['exp_avg_sq']))
+            # one multi-tensor launch per distinct step count (normally exactly one)
+            for step, items in groups.items():
+                ops.adam_multi(items, g['lr'], b1, b2, g['eps'], step, self._step_dev if self.device_step else None)
+            for p in g['params']:
+                if p.grad is None:
+                    continue
                 # the kernel writes through raw pointers, which autograd's version counter cannot
                 # see; the packed-weight cache also keys on this explicit counter
                 p._cdb_version = getattr(p, '_cdb_version', 0) + 1

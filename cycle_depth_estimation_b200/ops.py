@@ -441,3 +441,17 @@ def empty_zero_halo(n, h, w, cs, halo, slack_w, device):
     buf = torch.empty((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=torch.bfloat16, device=device)
     zero_frame(buf, halo, halo, h, w)
     return buf
+
+
+def adam_multi(items, lr, beta1, beta2, eps, step, step_dev=None):
+    """items: [(param, grad, exp_avg, exp_avg_sq)] contiguous fp32 CUDA tensors sharing the same step count.
+    One launch per 384 tensors (cdb_adam_multi); step_dev (int32 device tensor) makes it graph-replay safe."""
+    n = len(items)
+    if n == 0:
+        return
+    arr = (_lib.CdbAdamEntry * n)()
+    for i, (p, g, m, v) in enumerate(items):
+        e = arr[i]
+        e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.numel = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()
+    check(_lib.lib().cdb_adam_multi(arr, n, C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
+                                    int(step), _p(step_dev), _stream()))

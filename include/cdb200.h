@@ -258,6 +258,19 @@ int cdb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int cdb_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                       float beta1, float beta2, float eps, const int32_t* step_dev, cdbStream_t stream);
 
+/* Multi-tensor form: every parameter tensor of an optimizer in one launch per 384 tensors.
+ * entries_host is a HOST array (the pointers travel in the kernel parameter block, so the launch is graph-safe);
+ * step >= 1 gives host-side bias corrections, step_dev != NULL reads the step count from device memory. */
+typedef struct CdbAdamEntry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} CdbAdamEntry;
+int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entries, float lr, float beta1, float beta2, float eps,
+                   int32_t step, const int32_t* step_dev, cdbStream_t stream);
+
 /* ImagePool.query (util/image_pool.py:12-32) with the host's random decisions supplied as a device table
  * plan_dev[batch][2] = {return_from, store_to} (-1: the incoming image / nothing stored); fake, out:
  * [batch][chw] fp32, pool: [pool_size][chw] fp32. Entries are applied in order (the reference's semantics). */
