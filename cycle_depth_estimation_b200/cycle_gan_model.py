@@ -193,7 +193,7 @@ class CycleGANModel:
     def _pool_query(self, pool, fake):
         """Replicated pool under data parallelism: all ranks see the global batch in rank-major order
         and replay the identical random stream; each rank keeps its own slice of the result."""
-        if self._plan_dev is not None:
+        if getattr(self, '_plan_dev', None) is not None:
             slot = self._plan_slot
             self._plan_slot += 1
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
