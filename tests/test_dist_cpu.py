@@ -42,7 +42,8 @@ def _worker(rank, world, port, q):
         for step in range(12):
             fake = torch.full((2, 1, 2, 2), float(100 * step + 10 * rank)) + torch.arange(2.).view(2, 1, 1, 1)
             outs.append(model._pool_query(pool, fake).clone())
-        q.put((rank, ok_grad, torch.stack(outs), list(pool.trace)))
+        # plain lists: a tensor would travel through the worker's fd-sharing socket, which is gone once it exits
+        q.put((rank, ok_grad, torch.stack(outs).tolist(), list(pool.trace)))
     finally:
         dist.destroy_process_group()
 
@@ -55,6 +56,7 @@ def test_grad_buckets_and_replicated_pool_world2():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    res = [(r[0], r[1], torch.tensor(r[2]), r[3]) for r in res]
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
