@@ -66,6 +66,7 @@ def lib():
     L.cdb_launch_count.restype = C.c_longlong
     L.cdb_conv2d_wgrad_workspace.restype = C.c_size_t
     L.cdb_depth_metrics_workspace.restype = C.c_size_t
+    L.cdb_validation_workspace.restype = C.c_size_t
     _lib = L
     return L
 

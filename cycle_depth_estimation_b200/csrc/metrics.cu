@@ -239,3 +239,163 @@ extern "C" int cdb_depth_metrics(const uint8_t* gt, const uint8_t* pred, int32_t
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side validation path: what new_multi/train5.py:97-110 + util/util.py:51-65 +
+// my_eval.py:52-56 do through a PNG round trip, without leaving the GPU:
+//   u   = uint8((x + 1) / 2 * 255)                      tensor2im (float32 arithmetic, C truncation / wrap)
+//   p8  = cvRound(u / max_img(u) * 255)                 train5.py:100,110 + cv2.imwrite of a float64 image
+//   out = cv2.resize(p8, (W_gt, H_gt))                  INTER_LINEAR on uint8 = OpenCV's 11-bit fixed point
+// The resize reproduces OpenCV bit for bit (pinned against cv2 in tests/test_validation_path.py): column
+// weights clamp to {1, 0} at the borders, row weights keep their fraction and clamp the two row INDICES;
+// horizontal pass in int32 (x2048), vertical pass ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2.
+// ------------------------------------------------------------------------------------------------
+namespace cdb {
+
+__global__ void __launch_bounds__(256)
+pred_quant_kernel(const float* __restrict__ x, int64_t pixels, uint8_t* __restrict__ u8, int* __restrict__ img_max) {
+  const int img = blockIdx.y;
+  const float* src = x + img * pixels;
+  uint8_t* dst = u8 + img * pixels;
+  int mx = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    // (x + 1) / 2.0 * 255.0 evaluated in float32 with separate roundings, then numpy's float32 -> uint8 cast
+    const float v = __fmul_rn(__fdiv_rn(__fadd_rn(src[i], 1.0f), 2.0f), 255.0f);
+    const int q = static_cast<int>(static_cast<long long>(v)) & 255;   // truncation, wrap modulo 256
+    dst[i] = static_cast<uint8_t>(q);
+    mx = max(mx, q);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&img_max[img], mx);
+}
+
+__global__ void __launch_bounds__(256)
+pred_normalise_kernel(uint8_t* __restrict__ u8, int64_t pixels, const int* __restrict__ img_max) {
+  const int img = blockIdx.y;
+  uint8_t* p = u8 + img * pixels;
+  const double m = static_cast<double>(img_max[img]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < pixels; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = __dmul_rn(__ddiv_rn(static_cast<double>(p[i]), m), 255.0);
+    int r = __double2int_rn(v);          // cvRound: round half to even; saturate_cast<uchar>
+    r = r < 0 ? 0 : (r > 255 ? 255 : r);
+    p[i] = static_cast<uint8_t>(r);
+  }
+}
+
+// ofs[d], alpha[d][2] for one axis. clamp_weights: OpenCV clamps the WEIGHTS along x (fx = 0 at the borders)
+// and only the INDICES along y.
+__global__ void resize_table_kernel(int ssize, int dsize, int clamp_weights, int* __restrict__ ofs,
+                                    short* __restrict__ alpha, int* __restrict__ dmax) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= dsize) return;
+  const double scale = static_cast<double>(ssize) / static_cast<double>(dsize);
+  float f = static_cast<float>(__dsub_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), 0.5));
+  int s = static_cast<int>(floorf(f));
+  f = __fsub_rn(f, static_cast<float>(s));
+  if (clamp_weights) {
+    if (s < 0) {
+      f = 0.f;
+      s = 0;
+    }
+    if (s + 1 >= ssize) {
+      atomicMin(dmax, d);
+      if (s >= ssize - 1) {
+        f = 0.f;
+        s = ssize - 1;
+      }
+    }
+  }
+  ofs[d] = s;
+  alpha[2 * d] = static_cast<short>(__float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f)));
+  alpha[2 * d + 1] = static_cast<short>(__float2int_rn(__fmul_rn(f, 2048.f)));
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+__global__ void __launch_bounds__(256)
+resize_linear_u8_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                        const int* __restrict__ xofs, const short* __restrict__ xa, const int* __restrict__ yofs,
+                        const short* __restrict__ ya, const int* __restrict__ xmax_p) {
+  const int img = blockIdx.z;
+  const uint8_t* s = src + static_cast<int64_t>(img) * sh * sw;
+  uint8_t* o = dst + static_cast<int64_t>(img) * dh * dw;
+  const int xmax = *xmax_p;
+  const int64_t total = static_cast<int64_t>(dh) * dw;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int dx = static_cast<int>(idx % dw), dy = static_cast<int>(idx / dw);
+    const int sx = xofs[dx];
+    const int sy = yofs[dy];
+    const int y0 = min(max(sy, 0), sh - 1), y1 = min(max(sy + 1, 0), sh - 1);
+    int h0, h1;
+    if (dx >= xmax) {
+      h0 = static_cast<int>(s[y0 * sw + sx]) * 2048;
+      h1 = static_cast<int>(s[y1 * sw + sx]) * 2048;
+    } else {
+      const int a0 = xa[2 * dx], a1 = xa[2 * dx + 1];
+      const int x1 = min(sx + 1, sw - 1);
+      h0 = s[y0 * sw + sx] * a0 + s[y0 * sw + x1] * a1;
+      h1 = s[y1 * sw + sx] * a0 + s[y1 * sw + x1] * a1;
+    }
+    const int b0 = ya[2 * dy], b1 = ya[2 * dy + 1];
+    int r = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    r = r < 0 ? 0 : (r > 255 ? 255 : r);
+    o[idx] = static_cast<uint8_t>(r);
+  }
+}
+
+}  // namespace cdb
+
+extern "C" size_t cdb_validation_workspace(int32_t n_img, int32_t dh, int32_t dw) {
+  // per-image max (int) | xmax (int) | xofs[dw] yofs[dh] (int) | xalpha[2 dw] ybeta[2 dh] (short)
+  size_t ints = (size_t)n_img + 1 + dw + dh;
+  size_t shorts = 2 * (size_t)dw + 2 * (size_t)dh;
+  return ((ints * 4 + shorts * 2 + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" int cdb_depth_pred_to_u8(const float* pred, int32_t n_img, int32_t h, int32_t w, uint8_t* out_u8,
+                                    void* workspace, size_t ws_bytes, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(pred && out_u8 && workspace && n_img > 0 && h > 0 && w > 0 && ws_bytes >= (size_t)n_img * 4,
+              CDB_ERR_BAD_DESC, "depth_pred_to_u8: bad argument");
+  int* img_max = static_cast<int*>(workspace);
+  CDB_CUDA_OK(cudaMemsetAsync(img_max, 0, sizeof(int) * n_img, stream));
+  const int64_t pixels = (int64_t)h * w;
+  int chunks = (int)((pixels + 256 * 16 - 1) / (256 * 16));
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, n_img);
+  pred_quant_kernel<<<grid, 256, 0, stream>>>(pred, pixels, out_u8, img_max);
+  CDB_LAUNCH_OK();
+  pred_normalise_kernel<<<grid, 256, 0, stream>>>(out_u8, pixels, img_max);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_resize_linear_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, uint8_t* dst,
+                                    int32_t dh, int32_t dw, void* workspace, size_t ws_bytes, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(src && dst && workspace && n_img > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0, CDB_ERR_BAD_DESC,
+              "resize_linear_u8: bad argument");
+  CDB_REQUIRE(ws_bytes >= cdb_validation_workspace(n_img, dh, dw), CDB_ERR_WORKSPACE, "resize_linear_u8: workspace");
+  CDB_REQUIRE(!(sw == 2 * dw && sh == 2 * dh), CDB_ERR_UNSUPPORTED,
+              "resize_linear_u8: exact 2x decimation (OpenCV switches to INTER_AREA there)");
+  int* ints = static_cast<int*>(workspace) + n_img;   // after the per-image maxima of cdb_depth_pred_to_u8
+  int* xmax = ints;
+  int* xofs = ints + 1;
+  int* yofs = xofs + dw;
+  short* xa = reinterpret_cast<short*>(yofs + dh);
+  short* ya = xa + 2 * dw;
+  set_int_kernel<<<1, 1, 0, stream>>>(xmax, dw);
+  CDB_LAUNCH_OK();
+  resize_table_kernel<<<ceil_div(dw, 128), 128, 0, stream>>>(sw, dw, 1, xofs, xa, xmax);
+  CDB_LAUNCH_OK();
+  resize_table_kernel<<<ceil_div(dh, 128), 128, 0, stream>>>(sh, dh, 0, yofs, ya, xmax);
+  CDB_LAUNCH_OK();
+  const int64_t total = (int64_t)dh * dw;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  resize_linear_u8_kernel<<<dim3(blocks, 1, n_img), 256, 0, stream>>>(src, sh, sw, dst, dh, dw, xofs, xa, yofs, ya, xmax);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}

@@ -75,3 +75,18 @@ def eval_metric(gt_p='/home/dut-ai/Documents/depth_selection/val_selection_cropp
     acc = np.zeros((max(n, 1000), 7), np.float32)
     acc[:n] = results
     return tuple(acc[:, k].sum() / n for k in range(7))
+
+
+def eval_metric_from_predictions(pred_dep, gts):
+    """The validation loop of new_multi/train5.py:85-110 without its PNG round trip: ``pred_dep`` is the network's
+    depth output (fp32 CUDA [n,h,w], [-1,1] convention, ``real_dep_ref``), ``gts`` the uint8 ground-truth images
+    [n,H,W].  Quantisation (tensor2im + max-normalisation + PNG rounding), cv2.resize to the ground-truth size
+    (bit-exact INTER_LINEAR) and the metrics all run on the device.  Returns (7 float32 means, per-image [n,7])."""
+    device = pred_dep.device
+    g = _as_u8_cuda(gts, device)
+    if g.dim() == 2:
+        g = g[None]
+    p8 = ops.depth_pred_to_u8(pred_dep.detach().contiguous().float())
+    if tuple(p8.shape[1:]) != tuple(g.shape[1:]):
+        p8 = ops.resize_linear_u8(p8, int(g.shape[1]), int(g.shape[2]))
+    return eval_metric_arrays(g, p8)

@@ -455,3 +455,35 @@ def adam_multi(items, lr, beta1, beta2, eps, step, step_dev=None):
         e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.numel = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()
     check(_lib.lib().cdb_adam_multi(arr, n, C.c_float(lr), C.c_float(beta1), C.c_float(beta2), C.c_float(eps),
                                     int(step), _p(step_dev), _stream()))
+
+
+def _validation_ws(n, dh, dw, device):
+    need = _lib.lib().cdb_validation_workspace(n, dh, dw)
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=device)
+    off = (-ws.data_ptr()) % 256
+    return ws, off, need
+
+
+def depth_pred_to_u8(pred):
+    """pred fp32 CUDA [n,h,w] in the network's [-1,1] convention -> uint8 [n,h,w] as the reference writes it to
+    PNG (util/util.py:64-65 + new_multi/train5.py:100,110)."""
+    _require_cuda(pred)
+    assert pred.dtype == torch.float32 and pred.dim() == 3 and pred.is_contiguous()
+    n, h, w = pred.shape
+    ws, off, need = _validation_ws(n, h, w, pred.device)
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=pred.device)
+    check(_lib.lib().cdb_depth_pred_to_u8(_p(pred), n, h, w, _p(out), C.c_void_p(ws.data_ptr() + off), C.c_size_t(need),
+                                          _stream()))
+    return out
+
+
+def resize_linear_u8(src, dh, dw):
+    """cv2.resize(src, (dw, dh)) (INTER_LINEAR, uint8, bit-exact) for a stack src uint8 CUDA [n,sh,sw]."""
+    _require_cuda(src)
+    assert src.dtype == torch.uint8 and src.dim() == 3 and src.is_contiguous()
+    n, sh, sw = src.shape
+    ws, off, need = _validation_ws(n, dh, dw, src.device)
+    out = torch.empty((n, dh, dw), dtype=torch.uint8, device=src.device)
+    check(_lib.lib().cdb_resize_linear_u8(_p(src), n, sh, sw, _p(out), dh, dw, C.c_void_p(ws.data_ptr() + off),
+                                          C.c_size_t(need), _stream()))
+    return out

@@ -285,6 +285,19 @@ size_t cdb_depth_metrics_workspace(int32_t n_img);
 int cdb_depth_metrics(const uint8_t* gt, const uint8_t* pred, int32_t n_img, int32_t h, int32_t w,
                       double* out8_per_img, void* workspace, size_t ws_bytes, cdbStream_t stream);
 
+/* ---- device-side validation path -------------------------------------------------------
+ * What new_multi/train5.py:97-110 does through PNG files, on the device:
+ * cdb_depth_pred_to_u8:  u = uint8((x+1)/2*255) (util/util.py:64-65), then round(u / max_image(u) * 255)
+ *   (train5.py:100,110 + cv2.imwrite of the float64 image) for n_img predictions pred[n][h][w] (fp32).
+ * cdb_resize_linear_u8:  cv2.resize(pred, (dw, dh)) of my_eval.py:55 on uint8 images, bit-exact with OpenCV's
+ *   INTER_LINEAR fixed-point arithmetic (2x exact decimation, where OpenCV switches to INTER_AREA, is refused).
+ * workspace: cdb_validation_workspace() bytes, 256-byte aligned; its first n_img ints hold the per-image maxima. */
+size_t cdb_validation_workspace(int32_t n_img, int32_t dh, int32_t dw);
+int cdb_depth_pred_to_u8(const float* pred, int32_t n_img, int32_t h, int32_t w, uint8_t* out_u8, void* workspace,
+                         size_t ws_bytes, cdbStream_t stream);
+int cdb_resize_linear_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
+                         int32_t dw, void* workspace, size_t ws_bytes, cdbStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

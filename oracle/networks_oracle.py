@@ -338,3 +338,30 @@ class Pix2PixStepOracle:
             self.opt_G.step()
         self.fake_B = fake_B
         return {k: float(v.detach()) for k, v in L.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# validation path of new_multi/train5.py:85-110 (PNG round trip restated in memory)
+# ------------------------------------------------------------------------------------------------
+def prediction_png_u8(dep):
+    """What ends up in the prediction PNG for one depth map ``dep`` (float array [H,W], network convention
+    [-1,1]): util/util.py:59-65 (tensor2im: float32 arithmetic, astype(uint8)), new_multi/train5.py:100
+    (``img / img.max()``), :110 (``* 255`` and cv2.imwrite of the float64 array: saturate_cast<uchar> = round
+    half to even)."""
+    image_numpy = np.asarray(dep, dtype=np.float32)
+    image_numpy = (image_numpy + 1) / 2.0 * 255.0
+    with np.errstate(invalid='ignore'):
+        img = image_numpy.astype(np.uint8)
+    arr = img / img.max() * 255
+    return np.clip(np.rint(arr), 0, 255).astype(np.uint8)
+
+
+def eval_metric_from_predictions(deps, gts):
+    """new_multi/train5.py:97-110 + my_eval.py:52-108 for in-memory inputs: PNG quantisation, cv2.resize to the
+    ground-truth size (my_eval.py:55, OpenCV INTER_LINEAR), then the metrics."""
+    import cv2
+    preds = []
+    for dep, gt in zip(deps, gts):
+        p8 = prediction_png_u8(dep)
+        preds.append(cv2.resize(p8, (gt.shape[1], gt.shape[0])))
+    return eval_metric_arrays(list(gts), preds)
