@@ -78,14 +78,9 @@ class Tape:
         self.back = []
         self.param_grads = {}
         self.needs = {}            # param -> bool, filled in before the backward replay
-        self.seed_counter = [0]
         self.arena = ops.ZeroArena(device)
 
     # ---------------------------------------------------------------- bookkeeping
-    def _on_backward(self, fn):
-        if self.record:
-            self.back.append(fn)
-
     def add_param_grad(self, p, g):
         if p is None or not self.needs.get(p, False):
             return
