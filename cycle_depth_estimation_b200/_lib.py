@@ -47,6 +47,11 @@ class CdbAdamEntry(C.Structure):
                 ("numel", C.c_int64)]
 
 
+class CdbPackEntry(C.Structure):
+    _fields_ = [("w4", C.c_void_p), ("out", C.c_void_p), ("d0", C.c_int32), ("d1", C.c_int32), ("r", C.c_int32),
+                ("s", C.c_int32), ("rows_are_dim0", C.c_int32), ("rowpack", C.c_int32)]
+
+
 _lib = None
 
 

@@ -282,6 +282,61 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// Multi-tensor packing: every cached bf16 operand of an optimizer's filters re-packed by ONE launch (the filter
+// pointers and geometries travel in the kernel parameter block; graph-safe). Same element mapping as
+// pack_weight_kernel; block b finds its (entry, chunk) by binary search over cumulative chunk counts.
+constexpr int kPackMaxEntries = 320;
+constexpr int kPackChunk = 8192;
+struct PackEntryDev {
+  const float* w;
+  __nv_bfloat16* out;
+  int32_t d0, d1, R, S, rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad, n_taps, pad_;
+};
+struct PackMultiParams {
+  int32_t n_entries, pad_;
+  PackEntryDev e[kPackMaxEntries];
+  int32_t cum[kPackMaxEntries + 1];
+};
+
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_constant__ PackMultiParams q) {
+  int lo = 0, hi = q.n_entries;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (q.cum[mid] <= static_cast<int>(blockIdx.x)) lo = mid;
+    else hi = mid;
+  }
+  const PackEntryDev& en = q.e[lo];
+  const int64_t ktotal = static_cast<int64_t>(en.n_taps) * en.kpad;
+  const int64_t total = static_cast<int64_t>(en.rows_pad) * ktotal;
+  const int64_t begin = static_cast<int64_t>(blockIdx.x - q.cum[lo]) * kPackChunk;
+  const int64_t end = begin + kPackChunk < total ? begin + kPackChunk : total;
+  for (int64_t idx = begin + threadIdx.x; idx < end; idx += 256) {
+    const int row = static_cast<int>(idx / ktotal);
+    const int kk = static_cast<int>(idx % ktotal);
+    const int tap = kk / en.kpad;
+    int k = kk % en.kpad;
+    int r, sc;
+    bool ok = row < en.rows;
+    if (en.rowpack) {
+      r = tap;
+      sc = k / en.rowpack;
+      k = k % en.rowpack;
+      ok = ok && sc < en.S && k < en.kdim;
+    } else {
+      r = tap / en.S;
+      sc = tap % en.S;
+      ok = ok && k < en.kdim;
+    }
+    float v = 0.f;
+    if (ok) {
+      const int i0 = en.rows_are_dim0 ? row : k;
+      const int i1 = en.rows_are_dim0 ? k : row;
+      v = en.w[((static_cast<int64_t>(i0) * en.d1 + i1) * en.R + r) * en.S + sc];
+    }
+    en.out[idx] = __float2bfloat16(v);
+  }
+}
+
 struct WgPlan {
   int m_is_s;  // M side = S tensor
   int cM, cN, mpad, npad, bn, m_tiles, n_tiles;
@@ -353,6 +408,49 @@ extern "C" int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int
   pack_weight_kernel<<<blocks, 256, 0, stream>>>(w4, static_cast<__nv_bfloat16*>(out), d0, d1, r, s,
                                                  rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad, n_taps);
   CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_pack_conv_weights_multi(const CdbPackEntry* entries_host, int32_t n_entries, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(entries_host && n_entries > 0, CDB_ERR_BAD_DESC, "pack_conv_weights_multi: bad argument");
+  static thread_local PackMultiParams q;
+  for (int base = 0; base < n_entries; base += kPackMaxEntries) {
+    const int n = n_entries - base < kPackMaxEntries ? n_entries - base : kPackMaxEntries;
+    q.n_entries = n;
+    int blocks = 0;
+    for (int i = 0; i < n; ++i) {
+      const CdbPackEntry& h = entries_host[base + i];
+      CDB_REQUIRE(h.w4 && h.out, CDB_ERR_BAD_DESC, "pack_conv_weights_multi: null pointer in entry %d", base + i);
+      PackEntryDev& e = q.e[i];
+      e.w = h.w4;
+      e.out = static_cast<__nv_bfloat16*>(h.out);
+      e.d0 = h.d0;
+      e.d1 = h.d1;
+      e.R = h.r;
+      e.S = h.s;
+      e.rows_are_dim0 = h.rows_are_dim0;
+      e.rowpack = h.rowpack;
+      e.rows = h.rows_are_dim0 ? h.d0 : h.d1;
+      e.kdim = h.rows_are_dim0 ? h.d1 : h.d0;
+      e.rows_pad = round_up(e.rows, 16);
+      if (h.rowpack) {
+        CDB_REQUIRE(h.s * h.rowpack <= 64 && e.kdim <= h.rowpack, CDB_ERR_BAD_DESC,
+                    "pack_conv_weights_multi: rowpack geometry in entry %d", base + i);
+        e.kpad = 64;
+        e.n_taps = h.r;
+      } else {
+        e.kpad = round_up(e.kdim, 64);
+        e.n_taps = h.r * h.s;
+      }
+      q.cum[i] = blocks;
+      const int64_t total = (int64_t)e.rows_pad * e.n_taps * e.kpad;
+      blocks += (int)((total + kPackChunk - 1) / kPackChunk);
+    }
+    q.cum[n] = blocks;
+    pack_weight_multi_kernel<<<blocks, 256, 0, stream>>>(q);
+    CDB_LAUNCH_OK();
+  }
   return CDB_OK;
 }
 

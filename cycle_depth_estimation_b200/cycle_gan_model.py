@@ -16,6 +16,7 @@ from collections import OrderedDict
 import torch
 import torch.distributed as dist
 
+from . import engine as engine_mod
 from . import losses, networks, ops
 from .graph_step import StepGraph
 from .image_pool import ImagePool
@@ -68,12 +69,17 @@ class FusedAdam:
             # one multi-tensor launch per distinct step count (normally exactly one)
             for step, items in groups.items():
                 ops.adam_multi(items, g['lr'], b1, b2, g['eps'], step, self._step_dev if self.device_step else None)
+            updated = []
             for p in g['params']:
                 if p.grad is None:
                     continue
                 # the kernel writes through raw pointers, which autograd's version counter cannot
                 # see; the packed-weight cache also keys on this explicit counter
                 p._cdb_version = getattr(p, '_cdb_version', 0) + 1
+                updated.append(p)
+            # bf16 GEMM operands of the updated filters: one multi-tensor re-pack instead of one launch per
+            # filter and layout at their next use
+            engine_mod._pack_cache.refresh(updated)
 
 
 class GradBuckets:

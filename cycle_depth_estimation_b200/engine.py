@@ -176,6 +176,25 @@ class _PackCache:
         return packed
 
 
+    def refresh(self, params):
+        """After an optimizer step: re-packs every cached plain layout of `params` with ONE multi-tensor launch
+        and stamps the cache entries with the parameters' new versions (flipped / folded layouts of the two 7x7
+        layers are left to the lazy path)."""
+        items, stamps = [], []
+        for w in params:
+            store = w.__dict__.get('_cdb_packed')
+            if not store or w.dim() != 4:
+                continue
+            ver = (w.data_ptr(), w._version, getattr(w, '_cdb_version', 0), _pack_epoch[0])
+            for key, (old_ver, packed) in store.items():
+                if len(key) == 3 and key[0] != 'fold' and not key[2] and old_ver != ver and w.is_contiguous():
+                    items.append((w.detach(), key[0], key[1], packed[0]))
+                    stamps.append((store, key, ver, packed))
+        ops.pack_conv_weights_multi(items)
+        for store, key, ver, packed in stamps:
+            store[key] = (ver, packed)
+
+
 _pack_cache = _PackCache()
 
 

@@ -487,3 +487,17 @@ def resize_linear_u8(src, dh, dw):
     check(_lib.lib().cdb_resize_linear_u8(_p(src), n, sh, sw, _p(out), dh, dw, C.c_void_p(ws.data_ptr() + off),
                                           C.c_size_t(need), _stream()))
     return out
+
+
+def pack_conv_weights_multi(items):
+    """items: [(w4 fp32 contiguous [d0,d1,R,S], rows_are_dim0, rowpack, out bf16 packed buffer)]: one launch."""
+    n = len(items)
+    if n == 0:
+        return
+    arr = (_lib.CdbPackEntry * n)()
+    for i, (w4, rows_are_dim0, rowpack, out) in enumerate(items):
+        e = arr[i]
+        d0, d1, r, s = w4.shape
+        e.w4, e.out, e.d0, e.d1, e.r, e.s = w4.data_ptr(), out.data_ptr(), d0, d1, r, s
+        e.rows_are_dim0, e.rowpack = 1 if rows_are_dim0 else 0, rowpack
+    check(_lib.lib().cdb_pack_conv_weights_multi(arr, n, _stream()))

