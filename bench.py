@@ -197,6 +197,34 @@ def time_dominant_kernel(peaks, iters=40):
             "us_per_launch": ms * 1e3, "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
 
 
+def time_tf32_kernel(iters=20):
+    """The same 3x3 256->256 convolution through the TF32 variant (tcgen05 kind::tf32, fp32 NHWC in/out): reported
+    in `config` next to the bf16 roofline. Peak: nominal dense TF32 (B200_PROFILING.md: 1.1 PFLOP/s) — there is no
+    measured TF32 entry in MEASURED_PEAKS.json."""
+    from cycle_depth_estimation_b200 import ops
+    d = DOMINANT
+    n, c, hw, k = d["n"], d["c"], d["hw"], d["k"]
+    x = ops.round_tf32_(torch.randn((n, hw + 2, hw + 2, c), device="cuda"))
+    w = (torch.randn((c, c, k, k), device="cuda") * 0.02).contiguous()
+    wp, rows_pad, kpad = ops.pack_conv_weight_tf32(w, True)
+    y = torch.empty((n, hw, hw, c), dtype=torch.float32, device="cuda")
+    g = ops.geom(k, k)
+    ov = ops.out_view_nhwc(y, c)
+    for _ in range(3):
+        ops.conv2d_fwd(g, x, wp, rows_pad, kpad, ov)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.conv2d_fwd(g, x, wp, rows_pad, kpad, ov)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * n * hw * hw * c * c * k * k / (ms * 1e-3) / 1e12
+    return {"kernel": "igemm_flat_kernel (kind::tf32)", "us_per_launch": ms * 1e3, "tflops": tf,
+            "frac_of_nominal_tf32_peak": tf / 1100.0, "peak_source": "nominal dense TF32 1.1 PFLOP/s (fallback)"}
+
+
 def b200_arm(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,6 +365,7 @@ def b200_arm(args):
         torch.cuda.synchronize()
         g_ms = e0.elapsed_time(e1) / 20
     roof = time_dominant_kernel(peaks)
+    tf32 = time_tf32_kernel()
     step_tflops = TFLOP_PER_SAMPLE * batch / (ms_step * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -358,6 +387,7 @@ def b200_arm(args):
             "step_frac_of_sustained_bf16_peak": step_tflops / peaks["bf16_sustained"],
             "g_forward_img_per_s_batch1": 1e3 / g_ms,
             "g_forward_tflops_batch1": G_FWD_GFLOP / g_ms,
+            "tf32_variant_r256_conv": tf32,
             "device_abort_flag": abort,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

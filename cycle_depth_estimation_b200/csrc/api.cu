@@ -52,6 +52,11 @@ static EncodeTiledFn encode_tiled_fn() {
 
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap_swz(out, dt, rank, base, dims, strides_bytes, box, 0);
+}
+
+int make_tmap_swz(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int atom32) {
   EncodeTiledFn fn = encode_tiled_fn();
   CDB_REQUIRE(fn != nullptr, CDB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -65,7 +70,8 @@ int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, co
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(out, dt, static_cast<cuuint32_t>(rank), base, gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return fail(CDB_ERR_BAD_DESC,

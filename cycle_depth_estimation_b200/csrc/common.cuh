@@ -47,6 +47,11 @@ int* device_abort_flag_ptr();
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box);
 
+// Same with the swizzle mode selectable: atom32 != 0 -> 128-byte swizzle with 32-byte atomicity (32-byte chunks
+// XORed with the row index mod 4), the only shared-memory layout tcgen05 accepts for MN-major TF32 operands.
+int make_tmap_swz(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int atom32);
+
 int sm_count();
 void note_launch();
 

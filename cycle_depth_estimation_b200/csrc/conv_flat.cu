@@ -33,6 +33,8 @@ struct FlatParams {
   int32_t halo_rows;                 // extra rows after the BM block (multiple of 8)
   int32_t a_stages, b_stages;
   int32_t cout, cstore, out_dtype, act, stats_on, stats_batch, use_base_offset, sleep_ns, rotate, fast_out, out_rows_per_img;
+  int32_t tf32, kelems;              // TF32 variant: fp32 operands, 32 channels per 128-byte K block (else 64 bf16)
+  int32_t vec_out, round_out;        // fp32 NHWC output: float4 stores; round stored values to TF32
   float slope;
   const float* bias;
   void* out;
@@ -146,8 +148,8 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
             const uint32_t dst = a_ring + sa * a_bytes;
             const int row0 = img * p.rows_per_img + f0 + r * p.dil * p.wp;
             mbar_arrive_expect_tx(full, a_bytes);
-            tma_load_2d(&maps.a_big, full, dst, c * 64, row0);
-            if (p.halo_rows > 0) tma_load_2d(&maps.a_small, full, dst + kFlatBM * 128, c * 64, row0 + kFlatBM);
+            tma_load_2d(&maps.a_big, full, dst, c * p.kelems, row0);
+            if (p.halo_rows > 0) tma_load_2d(&maps.a_small, full, dst + kFlatBM * 128, c * p.kelems, row0 + kFlatBM);
             if (++sa == p.a_stages) {
               sa = 0;
               pa ^= 1u;
@@ -159,7 +161,7 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
               }
               const uint32_t bfull = smem_u32(&bar_bfull[sb]);
               const int t = r * p.S + s;
-              const int wk = (p.flip ? (n_taps - 1 - t) : t) * p.kpad + c * 64;
+              const int wk = (p.flip ? (n_taps - 1 - t) : t) * p.kpad + c * p.kelems;
               mbar_arrive_expect_tx(bfull, b_bytes);
               tma_load_2d(&maps.b, bfull, b_ring + sb * b_bytes, wk, n0);
               if (++sb == p.b_stages) {
@@ -174,7 +176,8 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
+      const bool tf32 = p.tf32 != 0;
+      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int local = 0;
@@ -206,11 +209,20 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
               const uint64_t da0 = make_smem_desc_unaligned(a0, 16, 1024, kLayoutSW128, p.use_base_offset);
               const uint64_t da1 = make_smem_desc_unaligned(a0 + 128u * 128u, 16, 1024, kLayoutSW128, p.use_base_offset);
               const uint64_t db = make_smem_desc(b_ring + sb * b_bytes, 16, 1024, kLayoutSW128);
+              if (tf32) {  // same 32-byte K step per instruction: 8 tf32 instead of 16 bf16
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t acc = (first && k == 0) ? 0u : 1u;
-                umma_f16(d0, da0 + 2u * k, db + 2u * k, idesc, acc);
-                umma_f16(d1, da1 + 2u * k, db + 2u * k, idesc, acc);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                  umma_tf32(d0, da0 + 2u * k, db + 2u * k, idesc, acc);
+                  umma_tf32(d1, da1 + 2u * k, db + 2u * k, idesc, acc);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = (first && k == 0) ? 0u : 1u;
+                  umma_f16(d0, da0 + 2u * k, db + 2u * k, idesc, acc);
+                  umma_f16(d1, da1 + 2u * k, db + 2u * k, idesc, acc);
+                }
               }
               first = false;
               umma_commit(smem_u32(&bar_bempty[sb]));
@@ -389,11 +401,24 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
                 if (ch < cstore) o[ch * p.o_sc] = __float2bfloat16(fv[j]);
               }
             } else {
-              float* o = static_cast<float*>(p.out) + obase;
+              if (p.round_out) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int ch = n0 + c0 + j;
-                if (ch < cstore) o[ch * p.o_sc] = fv[j];
+                for (int j = 0; j < 16; ++j) fv[j] = round_tf32(fv[j]);
+              }
+              float* o = static_cast<float*>(p.out) + obase;
+              if (p.vec_out) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const int ch = n0 + c0 + j;
+                  if (ch < cstore)
+                    *reinterpret_cast<float4*>(o + ch) = make_float4(fv[j], fv[j + 1], fv[j + 2], fv[j + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int ch = n0 + c0 + j;
+                  if (ch < cstore) o[ch * p.o_sc] = fv[j];
+                }
               }
             }
           }
@@ -420,7 +445,12 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   prm.R = g->r;
   prm.S = g->s;
   prm.dil = g->dil;
-  prm.k_chunks = w_kpad / 64;
+  const bool tf32 = x->dtype == CDB_F32;
+  const uint64_t esz = tf32 ? 4 : 2;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  prm.tf32 = tf32 ? 1 : 0;
+  prm.kelems = tf32 ? 32 : 64;
+  prm.k_chunks = w_kpad / prm.kelems;
   prm.kpad = w_kpad;
   prm.flip = flip;
   prm.wp = x->w;
@@ -449,6 +479,11 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   prm.stats = ep ? ep->stats : nullptr;
   prm.stats_on = prm.stats != nullptr;
   prm.stats_batch = (ep && (ep->flags & CDB_EP_STATS_BATCH)) ? 1 : 0;
+  prm.round_out = (ep && (ep->flags & CDB_EP_ROUND_TF32)) ? 1 : 0;
+  prm.vec_out = (y->dtype == CDB_F32 && y->sc == 1 && y->cstore % 4 == 0 && y->sn % 4 == 0 && y->sh % 4 == 0 &&
+                 y->sw % 4 == 0 && (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0)
+                    ? 1
+                    : 0;
   prm.use_base_offset = use_base_offset;
   prm.out = y->ptr;
   prm.o_sn = y->sn;
@@ -462,20 +497,20 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   const uint64_t total_rows = (uint64_t)x->n * x->h * x->w;
   {
     uint64_t dims[2] = {(uint64_t)x->c, total_rows};
-    uint64_t str[1] = {(uint64_t)x->sw * 2};
-    uint32_t box[2] = {64u, 256u};
-    int rc = make_tmap(&maps.a_big, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x->ptr, dims, str, box);
+    uint64_t str[1] = {(uint64_t)x->sw * esz};
+    uint32_t box[2] = {(uint32_t)prm.kelems, 256u};
+    int rc = make_tmap(&maps.a_big, dt, 2, x->ptr, dims, str, box);
     if (rc) return rc;
-    uint32_t box2[2] = {64u, (uint32_t)(prm.halo_rows > 0 ? prm.halo_rows : 8)};
-    rc = make_tmap(&maps.a_small, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x->ptr, dims, str, box2);
+    uint32_t box2[2] = {(uint32_t)prm.kelems, (uint32_t)(prm.halo_rows > 0 ? prm.halo_rows : 8)};
+    rc = make_tmap(&maps.a_small, dt, 2, x->ptr, dims, str, box2);
     if (rc) return rc;
   }
   {
     const int ktotal = g->r * g->s * w_kpad;
     uint64_t dims[2] = {(uint64_t)ktotal, (uint64_t)w_rows_pad};
-    uint64_t str[1] = {(uint64_t)ktotal * 2};
-    uint32_t box[2] = {64u, (uint32_t)prm.bn};
-    int rc = make_tmap(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, str, box);
+    uint64_t str[1] = {(uint64_t)ktotal * esz};
+    uint32_t box[2] = {(uint32_t)prm.kelems, (uint32_t)prm.bn};
+    int rc = make_tmap(&maps.b, dt, 2, const_cast<void*>(wpacked), dims, str, box);
     if (rc) return rc;
   }
   // Fast output path: bf16 NHWC whose rows follow the INPUT pitch (sh = wp * cstore, sw = cstore) with

@@ -42,6 +42,10 @@ struct IgemmParams {
   int32_t stats_on;
   int32_t stats_batch;  // 1: one statistics group for the whole batch (BatchNorm)
   int32_t fast_out;
+  int32_t tf32;      // operands are fp32 in memory, multiplied as TF32 (kind::tf32); K block = 32 channels
+  int32_t kelems;    // channels per 128-byte K block: 64 (bf16) or 32 (tf32)
+  int32_t vec_out;   // fp32 NHWC output with 16-byte aligned pixels: float4 stores
+  int32_t round_out; // round the fp32 output to TF32 (nearest) so that the next TF32 convolution reads exact operands
   const float* bias;
   void* out;
   int64_t o_sn, o_sh, o_sw, o_sc;
@@ -136,8 +140,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t sa = smem_base + stage * stage_bytes;
             mbar_arrive_expect_tx(full, stage_bytes);
-            tma_load_4d(amap, full, sa, c * 64, q0 + tap.dw, p0 + tap.dh, img0);
-            tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * 64, n0);
+            tma_load_4d(amap, full, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
+            tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * p.kelems, n0);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -149,7 +153,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
+      const bool tf32 = p.tf32 != 0;
+      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -169,9 +174,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
           const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024, kLayoutSW128);
+          // one instruction consumes 32 bytes of K per row in both precisions: 16 bf16 or 8 tf32
+          if (tf32) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == p.stages) {
             stage = 0;
@@ -335,11 +347,23 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 if (ch < cstore) o[ch * p.o_sc] = __float2bfloat16(f[j]);
               }
             } else {
-              float* o = static_cast<float*>(p.out) + obase;
+              if (p.round_out) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int ch = n0 + c0 + j;
-                if (ch < cstore) o[ch * p.o_sc] = f[j];
+                for (int j = 0; j < 16; ++j) f[j] = round_tf32(f[j]);
+              }
+              float* o = static_cast<float*>(p.out) + obase;
+              if (p.vec_out) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const int ch = n0 + c0 + j;
+                  if (ch < cstore) *reinterpret_cast<float4*>(o + ch) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int ch = n0 + c0 + j;
+                  if (ch < cstore) o[ch * p.o_sc] = f[j];
+                }
               }
             }
           }
@@ -381,24 +405,31 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
                         int w_ktotal, IgemmParams& prm, cudaStream_t stream) {
   IgemmMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const uint32_t abox[4] = {64u, (uint32_t)prm.tile_w, (uint32_t)prm.tile_h, (uint32_t)prm.tile_n};
+  const uint64_t esz = prm.tf32 ? 4 : 2;
+  const CUtensorMapDataType dt = prm.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  prm.kelems = prm.tf32 ? 32 : 64;
+  const uint32_t abox[4] = {(uint32_t)prm.kelems, (uint32_t)prm.tile_w, (uint32_t)prm.tile_h, (uint32_t)prm.tile_n};
   for (int i = 0; i < 4; ++i) {
     const SrcView& v = views[i < n_views ? i : 0];
     uint64_t dims[4] = {(uint64_t)v.dims[0], (uint64_t)v.dims[1], (uint64_t)v.dims[2], (uint64_t)v.dims[3]};
-    uint64_t str[3] = {(uint64_t)v.strides[0] * 2, (uint64_t)v.strides[1] * 2, (uint64_t)v.strides[2] * 2};
+    uint64_t str[3] = {(uint64_t)v.strides[0] * esz, (uint64_t)v.strides[1] * esz, (uint64_t)v.strides[2] * esz};
     for (int d = 0; d < 4; ++d)
       if (dims[d] == 0) dims[d] = 1;
-    int rc = make_tmap(&maps.a[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, dims, str, abox);
+    int rc = make_tmap(&maps.a[i], dt, 4, v.ptr, dims, str, abox);
     if (rc != CDB_OK) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)w_ktotal, (uint64_t)w_rows_pad};
-    uint64_t str[1] = {(uint64_t)w_ktotal * 2};
-    uint32_t box[2] = {64u, (uint32_t)prm.bn};
-    int rc = make_tmap(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpacked), dims, str, box);
+    uint64_t str[1] = {(uint64_t)w_ktotal * esz};
+    uint32_t box[2] = {(uint32_t)prm.kelems, (uint32_t)prm.bn};
+    int rc = make_tmap(&maps.b, dt, 2, const_cast<void*>(wpacked), dims, str, box);
     if (rc != CDB_OK) return rc;
   }
   prm.fast_out = (prm.out_dtype == CDB_BF16 && prm.o_sc == 1) ? 1 : 0;
+  prm.vec_out = (prm.out_dtype == CDB_F32 && prm.o_sc == 1 && prm.cstore % 4 == 0 && prm.o_sn % 4 == 0 &&
+                 prm.o_sh % 4 == 0 && prm.o_sw % 4 == 0 && (reinterpret_cast<uintptr_t>(prm.out) & 15) == 0)
+                    ? 1
+                    : 0;
   if (prm.fast_out) {
     const int bw = prm.tile_w < 32 ? prm.tile_w : 32;
     const int bh = prm.tile_h < 32 / bw ? prm.tile_h : 32 / bw;
@@ -431,10 +462,12 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
 
 static int check_act(const CdbAct* x, const char* name) {
   CDB_REQUIRE(x && x->ptr, CDB_ERR_BAD_DESC, "%s: null tensor", name);
-  CDB_REQUIRE(x->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "%s: only bf16 activations are supported", name);
-  CDB_REQUIRE(x->c % 8 == 0 && x->sw % 8 == 0 && x->sh % 8 == 0 && x->sn % 8 == 0 &&
+  CDB_REQUIRE(x->dtype == CDB_BF16 || x->dtype == CDB_F32, CDB_ERR_UNSUPPORTED, "%s: bf16 or fp32 (TF32) activations",
+              name);
+  const int q = x->dtype == CDB_BF16 ? 8 : 4;  // elements per 16 bytes
+  CDB_REQUIRE(x->c % q == 0 && x->sw % q == 0 && x->sh % q == 0 && x->sn % q == 0 &&
                   (reinterpret_cast<uintptr_t>(x->ptr) & 15) == 0,
-              CDB_ERR_ALIGNMENT, "%s: channels/strides must be multiples of 8 elements and ptr 16B aligned", name);
+              CDB_ERR_ALIGNMENT, "%s: channels/strides must be multiples of 16 bytes and ptr 16B aligned", name);
   return CDB_OK;
 }
 
@@ -460,8 +493,11 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   CDB_REQUIRE(g->stride == 1 || g->stride == 2, CDB_ERR_UNSUPPORTED, "conv2d_fwd: stride %d", g->stride);
   CDB_REQUIRE(g->dil >= 1 && (g->dil == 1 || g->stride == 1), CDB_ERR_UNSUPPORTED, "conv2d_fwd: dilation with stride");
   CDB_REQUIRE(y->c >= 1 && y->cstore >= y->c, CDB_ERR_BAD_DESC, "conv2d_fwd: bad output channels");
-  CDB_REQUIRE(w_rows_pad % 16 == 0 && w_rows_pad >= y->c && w_kpad % 64 == 0, CDB_ERR_BAD_DESC,
+  const bool tf32 = x->dtype == CDB_F32;
+  const size_t xesz = tf32 ? 4 : 2;
+  CDB_REQUIRE(w_rows_pad % 16 == 0 && w_rows_pad >= y->c && w_kpad % (tf32 ? 32 : 64) == 0, CDB_ERR_BAD_DESC,
               "conv2d_fwd: packed weight geometry");
+  CDB_REQUIRE(!(tf32 && g->rowpack), CDB_ERR_UNSUPPORTED, "conv2d_fwd: rowpack is bf16 only");
   if (y->dtype == CDB_BF16 && y->sc == 1)
     CDB_REQUIRE(y->sn % 8 == 0 && y->sh % 8 == 0 && y->sw % 8 == 0 && y->cstore % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(y->ptr) & 15) == 0,
@@ -483,14 +519,16 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   prm.stats = ep ? ep->stats : nullptr;
   prm.stats_on = prm.stats != nullptr;
   prm.stats_batch = (ep && (ep->flags & CDB_EP_STATS_BATCH)) ? 1 : 0;
-  prm.k_chunks = w_kpad / 64;
+  prm.tf32 = tf32 ? 1 : 0;
+  prm.round_out = (ep && (ep->flags & CDB_EP_ROUND_TF32)) ? 1 : 0;
+  prm.k_chunks = w_kpad / (tf32 ? 32 : 64);
   prm.dom_n = y->n;
 
   CDB_REQUIRE(!(g->flip && (g->transposed || g->rowpack)), CDB_ERR_UNSUPPORTED, "conv2d_fwd: flip with transposed/rowpack");
   // Stride-1 convolutions over a contiguous buffer with materialised padding take the flat kernel
   // (A rows shared by the S taps of a filter row, two accumulators per weight tile).
   // (the buffer may be a channel prefix of a wider concatenation buffer: pixel pitch sw >= c, regular rows)
-  if (!g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw >= x->c &&
+  if (!(tf32 && env_flag("CDB_TF32_DISABLE_FLAT", 0)) && !g->transposed && !g->rowpack && st == 1 && g->pad_h == 0 && g->pad_w == 0 && x->sw >= x->c &&
       x->sh == (int64_t)x->w * x->sw && x->sn == (int64_t)x->h * x->w * x->sw &&
       y->h <= x->h - (g->r - 1) * g->dil && y->w <= x->w - (g->s - 1) * g->dil && y->n == x->n &&
       (g->s - 1) * g->dil <= 64 && (int64_t)y->h * x->w >= 256 && !env_flag("CDB_DISABLE_FLAT", 0)) {
@@ -532,7 +570,7 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
       for (int a = 0; a < st; ++a)
         for (int b = 0; b < st; ++b) {
           SrcView& v = views[a * st + b];
-          v.ptr = static_cast<__nv_bfloat16*>(x->ptr) + a * x->sh + b * x->sw;
+          v.ptr = static_cast<char*>(x->ptr) + (a * x->sh + b * x->sw) * (int64_t)xesz;
           v.dims[0] = x->c;
           v.dims[1] = (x->w - b + st - 1) / st;
           v.dims[2] = (x->h - a + st - 1) / st;

@@ -31,6 +31,8 @@ struct WgParams {
   int32_t shift_on_a;                 // 1: the tap shift applies to the M-side operand
   int32_t stages;
   int32_t mpad, npad;
+  int32_t tf32;                       // fp32 operands multiplied as TF32: 32 channels per 128-byte chunk row
+  int32_t cpc;                        // channels per chunk: 64 (bf16) or 32 (tf32)
   float* ws;                          // [splits][taps][mpad][npad]
   int* abort_flag;
   WgTap taps[kWgMaxTaps];
@@ -54,8 +56,10 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = 2u * kChunkBytes;
-  const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / 64u;
+  const uint32_t cpc = static_cast<uint32_t>(p.cpc);
+  const uint32_t a_chunks = 128u / cpc;
+  const uint32_t a_bytes = a_chunks * kChunkBytes;
+  const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / cpc;
   const uint32_t stage_bytes = a_bytes + b_chunks * kChunkBytes;
   const int total_items = p.n_taps * p.m_tiles * p.n_tiles * p.splits;
   const int k_tiles_total = p.tiles_n * p.tiles_h * p.tiles_w;
@@ -122,10 +126,10 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * stage_bytes;
           mbar_arrive_expect_tx(full, stage_bytes);
-          for (int j = 0; j < 2; ++j)
-            tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * 64, q0 + a_dw, p0 + a_dh, img0);
+          for (uint32_t j = 0; j < a_chunks; ++j)
+            tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * cpc, q0 + a_dw, p0 + a_dh, img0);
           for (uint32_t j = 0; j < b_chunks; ++j)
-            tma_load_4d(bmap, full, sa + a_bytes + j * kChunkBytes, nt * p.bn + j * 64, q0 + b_dw,
+            tma_load_4d(bmap, full, sa + a_bytes + j * kChunkBytes, nt * p.bn + j * cpc, q0 + b_dw,
                         p0 + b_dh, img0);
           if (++stage == p.stages) {
             stage = 0;
@@ -136,7 +140,8 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn));
+      const bool tf32 = p.tf32 != 0;
+      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -160,11 +165,23 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 k-rows.
-          const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
+          // (descriptors built in the branch below)
+          if (tf32) {
+            // MN-major TF32: 128B swizzle with 32-byte atoms (4 k-rows x 128 B per atom): LBO = distance between
+            // 32-channel chunks, SBO = 512 B between the two 4-row groups of one K = 8 instruction.
+            // (pinned on B200 with tools/probe_tf32_wgrad.py: any other LBO/SBO assignment gives O(1) errors)
+            const uint64_t ta = make_smem_desc(sa, kChunkBytes, 512, kLayoutSW128Base32);
+            const uint64_t tb = make_smem_desc(sa + a_bytes, kChunkBytes, 512, kLayoutSW128Base32);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
-            umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k)  // 8 pixels (= 8 rows x 128 B) per instruction
+              umma_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+          } else {
+            const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+            const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
+              umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == p.stages) {
             stage = 0;
@@ -249,7 +266,8 @@ __global__ void wgrad_finalize_kernel(const float* __restrict__ ws, float* __res
 }
 
 // fp32 W4[d0][d1][R][S] -> bf16 packed[rows_pad][taps*kpad] (see cdb_pack_conv_weight).
-__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int d0,
+template <typename OutT>
+__global__ void pack_weight_kernel(const float* __restrict__ w, OutT* __restrict__ out, int d0,
                                    int d1, int R, int S, int rows_are_dim0, int rowpack, int rows,
                                    int kdim, int rows_pad, int kpad, int n_taps) {
   const int64_t ktotal = static_cast<int64_t>(n_taps) * kpad;
@@ -278,8 +296,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
       const int i1 = rows_are_dim0 ? k : row;
       v = w[((static_cast<int64_t>(i0) * d1 + i1) * R + r) * S + s];
     }
-    out[idx] = __float2bfloat16(v);
+    if constexpr (sizeof(OutT) == 4) out[idx] = round_tf32(v);
+    else out[idx] = __float2bfloat16(v);
   }
+}
+
+__global__ void round_tf32_kernel(float* __restrict__ buf, int64_t numel) {
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < numel;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    buf[idx] = round_tf32(buf[idx]);
 }
 
 // Multi-tensor packing: every cached bf16 operand of an optimizer's filters re-packed by ONE launch (the filter
@@ -344,6 +369,8 @@ struct WgPlan {
 };
 
 static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g_act, WgPlan* pl) {
+  // TF32: fp32 operands take twice the shared memory per channel -> N tile of at most 128 channels (3 stages)
+  const bool tf32 = s_act->dtype == CDB_F32;
   const int cS = s_act->c;
   const int cG = g->rowpack ? 64 : g_act->c;
   auto cost = [](int cm, int cn) { return (int64_t)round_up(cm, 128) * round_up(cn, 64); };
@@ -353,7 +380,8 @@ static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g
   pl->mpad = round_up(pl->cM, 128);
   pl->m_tiles = pl->mpad / 128;
   const int n64 = round_up(pl->cN, 64);
-  pl->bn = n64 < 256 ? n64 : 256;
+  const int bn_max = tf32 ? 128 : 256;
+  pl->bn = n64 < bn_max ? n64 : bn_max;
   pl->n_tiles = ceil_div(n64, pl->bn);
   pl->npad = pl->n_tiles * pl->bn;
   // 64-pixel K tiles over the S domain
@@ -405,8 +433,37 @@ extern "C" int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int
   const int64_t total = (int64_t)rows_pad * n_taps * kpad;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_weight_kernel<<<blocks, 256, 0, stream>>>(w4, static_cast<__nv_bfloat16*>(out), d0, d1, r, s,
-                                                 rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad, n_taps);
+  pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(w4, static_cast<__nv_bfloat16*>(out), d0, d1, r, s,
+                                                                rows_are_dim0, rowpack, rows, kdim, rows_pad, kpad,
+                                                                n_taps);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_pack_conv_weight_tf32(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
+                                         int32_t rows_are_dim0, void* out, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(w4 && out, CDB_ERR_BAD_DESC, "pack_conv_weight_tf32: null argument");
+  const int rows = rows_are_dim0 ? d0 : d1;
+  const int kdim = rows_are_dim0 ? d1 : d0;
+  const int rows_pad = round_up(rows, 16);
+  const int kpad = round_up(kdim, 32), n_taps = r * s;
+  const int64_t total = (int64_t)rows_pad * n_taps * kpad;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weight_kernel<float><<<blocks, 256, 0, stream>>>(w4, static_cast<float*>(out), d0, d1, r, s, rows_are_dim0, 0,
+                                                        rows, kdim, rows_pad, kpad, n_taps);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_round_tf32(float* buf, int64_t numel, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(buf || numel == 0, CDB_ERR_BAD_DESC, "round_tf32: null argument");
+  if (numel <= 0) return CDB_OK;
+  int64_t blocks = (numel + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  round_tf32_kernel<<<(int)blocks, 256, 0, stream>>>(buf, numel);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
@@ -479,7 +536,21 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
                                 size_t ws_bytes, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(g && x && dy && dw4 && workspace, CDB_ERR_BAD_DESC, "conv2d_wgrad: null argument");
-  CDB_REQUIRE(x->dtype == CDB_BF16 && dy->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: bf16 only");
+  CDB_REQUIRE(x->dtype == dy->dtype && (x->dtype == CDB_BF16 || x->dtype == CDB_F32), CDB_ERR_UNSUPPORTED,
+              "conv2d_wgrad: x and dy must both be bf16 or both fp32 (TF32)");
+  const bool tf32 = x->dtype == CDB_F32;
+  const uint64_t esz = tf32 ? 4 : 2;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int cpc = tf32 ? 32 : 64;
+  CDB_REQUIRE(!(tf32 && g->rowpack), CDB_ERR_UNSUPPORTED, "conv2d_wgrad: rowpack is bf16 only");
+  {
+    const int q = tf32 ? 4 : 8;
+    const CdbAct* both[2] = {x, dy};
+    for (const CdbAct* t : both)
+      CDB_REQUIRE(t->ptr && t->c % q == 0 && t->sw % q == 0 && t->sh % q == 0 && t->sn % q == 0 &&
+                      (reinterpret_cast<uintptr_t>(t->ptr) & 15) == 0,
+                  CDB_ERR_ALIGNMENT, "conv2d_wgrad: channels/strides must be multiples of 16 bytes and ptr 16B aligned");
+  }
   CDB_REQUIRE(g->stride == 1 || g->stride == 2, CDB_ERR_UNSUPPORTED, "conv2d_wgrad: stride %d", g->stride);
   // rowpack applies to the SHIFTED tensor: x for Conv2d, dy for the transposed form (used for layers with
   // very few output channels: dy then carries 8 channels per pixel and one K block covers a filter row).
@@ -494,11 +565,11 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
 
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
-  const uint32_t box[4] = {64u, (uint32_t)pl.tile_w, (uint32_t)pl.tile_h, (uint32_t)pl.tile_n};
+  const uint32_t box[4] = {(uint32_t)cpc, (uint32_t)pl.tile_w, (uint32_t)pl.tile_h, (uint32_t)pl.tile_n};
   {
     uint64_t dims[4] = {(uint64_t)s_act->c, (uint64_t)s_act->w, (uint64_t)s_act->h, (uint64_t)s_act->n};
-    uint64_t str[3] = {(uint64_t)s_act->sw * 2, (uint64_t)s_act->sh * 2, (uint64_t)s_act->sn * 2};
-    int rc = make_tmap(&maps.fixed, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s_act->ptr, dims, str, box);
+    uint64_t str[3] = {(uint64_t)s_act->sw * esz, (uint64_t)s_act->sh * esz, (uint64_t)s_act->sn * esz};
+    int rc = make_tmap_swz(&maps.fixed, dt, 4, s_act->ptr, dims, str, box, tf32 ? 1 : 0);
     if (rc) return rc;
   }
   WgParams prm;
@@ -528,9 +599,10 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
                           (uint64_t)((g_act->h - a + st - 1) / st), (uint64_t)g_act->n};
       for (int d = 0; d < 4; ++d)
         if (dims[d] == 0) dims[d] = 1;
-      uint64_t str[3] = {(uint64_t)g_act->sw * st * 2, (uint64_t)g_act->sh * st * 2, (uint64_t)g_act->sn * 2};
-      int rc = make_tmap(&maps.shift[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                         static_cast<__nv_bfloat16*>(g_act->ptr) + a * g_act->sh + b * g_act->sw, dims, str, box);
+      uint64_t str[3] = {(uint64_t)g_act->sw * st * esz, (uint64_t)g_act->sh * st * esz, (uint64_t)g_act->sn * esz};
+      int rc = make_tmap_swz(&maps.shift[i], dt, 4,
+                             static_cast<char*>(g_act->ptr) + (a * g_act->sh + b * g_act->sw) * (int64_t)esz, dims,
+                             str, box, tf32 ? 1 : 0);
       if (rc) return rc;
     }
     for (int r = 0; r < g->r; ++r)
@@ -558,9 +630,11 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.shift_on_a = pl.m_is_s ? 0 : 1;
   prm.mpad = pl.mpad;
   prm.npad = pl.npad;
+  prm.tf32 = tf32 ? 1 : 0;
+  prm.cpc = cpc;
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
-  const int stage_bytes = 2 * kChunkBytes + (pl.bn / 64) * kChunkBytes;
+  const int stage_bytes = (128 / cpc) * kChunkBytes + (pl.bn / cpc) * kChunkBytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;

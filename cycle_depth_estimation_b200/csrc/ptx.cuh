@@ -215,6 +215,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// fp32 -> TF32 (10-bit mantissa), round to nearest, ties away from zero; result is an fp32 bit pattern with the
+// low 13 mantissa bits clear, i.e. exactly what kind::tf32 multiplies (the tensor core ignores those bits).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -234,6 +242,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 constexpr uint32_t kLayoutSW128 = 2;
+// 128B swizzle with 32-byte atomicity (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 rows x 128 B;
+// required for MN-major 32-bit (TF32) operands.
+constexpr uint32_t kLayoutSW128Base32 = 1;
 // Same, for a start address that is not aligned to the 1024-byte swizzle pattern: the descriptor's
 // "matrix base offset" (bits [49,52)) carries (start >> 7) & 7.
 __device__ __forceinline__ uint64_t make_smem_desc_unaligned(uint32_t saddr, uint32_t lbo_bytes,

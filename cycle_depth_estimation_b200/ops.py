@@ -99,12 +99,40 @@ def pack_conv_weight(w4, rows_are_dim0, rowpack=0, out=None):
     return out, rows_pad, kpad
 
 
-def conv2d_fwd(g, x, wpacked, rows_pad, kpad, out, bias=None, act=ACT_NONE, slope=0.0, stats=None):
-    """x: NHWC bf16 view; out: CdbOut. See cdb_conv2d_fwd."""
+EP_STATS_BATCH, EP_ROUND_TF32 = 1, 2
+
+
+def pack_conv_weight_tf32(w4, rows_are_dim0, out=None):
+    """fp32 [d0,d1,R,S] -> fp32 (TF32-rounded) packed GEMM operand [rows_pad, taps*kpad], kpad = round_up(k, 32);
+    returns (packed, rows_pad, kpad). Operand of the TF32 variant of conv2d_fwd (x fp32)."""
+    _require_cuda(w4)
+    w4 = w4.detach()
+    assert w4.dtype == torch.float32 and w4.is_contiguous()
+    d0, d1, r, s = w4.shape
+    rows_pad = round_up(d0 if rows_are_dim0 else d1, 16)
+    kpad = round_up(d1 if rows_are_dim0 else d0, 32)
+    if out is None:
+        out = torch.empty((rows_pad, r * s * kpad), dtype=torch.float32, device=w4.device)
+    check(_lib.lib().cdb_pack_conv_weight_tf32(C.c_void_p(w4.data_ptr()), d0, d1, r, s, 1 if rows_are_dim0 else 0,
+                                               C.c_void_p(out.data_ptr()), _stream()))
+    return out, rows_pad, kpad
+
+
+def round_tf32_(t):
+    """In-place round-to-nearest of a contiguous fp32 CUDA tensor to TF32 precision."""
+    _require_cuda(t)
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    check(_lib.lib().cdb_round_tf32(C.c_void_p(t.data_ptr()), C.c_int64(t.numel()), _stream()))
+    return t
+
+
+def conv2d_fwd(g, x, wpacked, rows_pad, kpad, out, bias=None, act=ACT_NONE, slope=0.0, stats=None, flags=0):
+    """x: NHWC bf16 view (or fp32: TF32 variant, wpacked from pack_conv_weight_tf32); out: CdbOut. See cdb_conv2d_fwd."""
     _require_cuda(x, wpacked)
     xv = act_view(x)
+    assert wpacked.dtype == x.dtype, "packed weights must match the activation precision (bf16 / fp32-TF32)"
     ep = CdbEpilogue(bias.data_ptr() if bias is not None else None, act, slope,
-                     stats.data_ptr() if stats is not None else None, 0)
+                     stats.data_ptr() if stats is not None else None, flags)
     check(_lib.lib().cdb_conv2d_fwd(C.byref(g), C.byref(xv), C.c_void_p(wpacked.data_ptr()), rows_pad, kpad,
                                     C.byref(out), C.byref(ep), _stream()))
 
@@ -122,7 +150,7 @@ def _workspace(nbytes, device):
 
 
 def conv2d_wgrad(g, x, dy, dw4, accumulate=False):
-    """dw4 (fp32 [d0,d1,R,S]) (+)= filter gradient. x, dy: NHWC bf16 views."""
+    """dw4 (fp32 [d0,d1,R,S]) (+)= filter gradient. x, dy: NHWC bf16 views (both fp32: TF32 variant)."""
     _require_cuda(x, dy, dw4)
     assert dw4.dtype == torch.float32 and dw4.is_contiguous()
     xv, dyv = act_view(x), act_view(dy)

@@ -90,7 +90,10 @@ typedef struct CdbEpilogue {
   int64_t flags;     /* CDB_EP_* */
 } CdbEpilogue;
 /* stats is ONE group [c][2] for the whole batch (BatchNorm) instead of one per image */
-enum { CDB_EP_STATS_BATCH = 1 };
+enum { CDB_EP_STATS_BATCH = 1,
+       /* fp32 outputs only: round the stored value to TF32 (nearest), so that a following TF32 convolution
+        * multiplies exactly what was stored */
+       CDB_EP_ROUND_TF32 = 2 };
 
 /* ---- library ------------------------------------------------------------------------------ */
 int cdb_version(void);
@@ -107,6 +110,11 @@ int cdb_device_abort_flag(void);
  * aten.convolution_backward.  wpacked: bf16 [rows_pad][taps*kpad] from cdb_pack_conv_weight. */
 int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, int32_t w_rows_pad,
                    int32_t w_kpad, const CdbOut* y, const CdbEpilogue* ep, cdbStream_t stream);
+/* TF32 variant (the reference's arithmetic is fp32): x->dtype == CDB_F32 selects tcgen05 kind::tf32 —
+ * x is an fp32 NHWC view (channels and strides multiples of 4), wpacked the fp32 operand of
+ * cdb_pack_conv_weight_tf32 (w_kpad a multiple of 32), fp32 accumulation, y fp32 or bf16.  The tensor core
+ * ignores the low 13 mantissa bits of its operands; cdb_pack_conv_weight_tf32 / cdb_round_tf32 / CDB_EP_ROUND_TF32
+ * round to nearest beforehand.  rowpack is not available in this precision. */
 
 /* Packs an fp32 4-D filter W4[d0][d1][R][S] (Conv2d: OIHW, ConvTranspose2d: IOHW) into the bf16
  * GEMM B operand [rows_pad][taps*kpad]:  packed[row][tap*kpad + k] = W4[row][k][r][s] when
@@ -114,6 +122,12 @@ int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, i
  * rows_pad = round_up(rows,16), kpad = round_up(k,64).  out must hold rows_pad*taps*kpad bf16. */
 int cdb_pack_conv_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
                          int32_t rows_are_dim0, int32_t rowpack, void* out, cdbStream_t stream);
+
+/* Same packing with fp32 storage rounded to TF32: out holds rows_pad*taps*kpad floats, kpad = round_up(k,32). */
+int cdb_pack_conv_weight_tf32(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s,
+                              int32_t rows_are_dim0, void* out, cdbStream_t stream);
+/* In-place round-to-nearest of an fp32 buffer to TF32 precision (activations entering the TF32 path). */
+int cdb_round_tf32(float* buf, int64_t numel, cdbStream_t stream);
 
 /* Multi-tensor form: re-packs many filters in one launch (after an optimizer step; entries_host is a HOST array,
  * the pointers travel in the kernel parameter block). Same layout as cdb_pack_conv_weight per entry. */
@@ -132,6 +146,7 @@ int cdb_pack_conv_weights_multi(const CdbPackEntry* entries_host, int32_t n_entr
  * g->rowpack refers to the shifted tensor (x, or dy when transposed), see CdbConvGeom.
  * workspace: cdb_conv2d_wgrad_workspace() bytes of fp32 split-K partials. */
 size_t cdb_conv2d_wgrad_workspace(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy);
+/* x and dy both CDB_F32 selects the TF32 variant (kind::tf32, MN-major fp32 operands; no rowpack). */
 int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const CdbAct* dy, float* dw4,
                      int32_t d0, int32_t d1, int32_t accumulate, void* workspace, size_t ws_bytes,
                      cdbStream_t stream);

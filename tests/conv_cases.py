@@ -85,6 +85,123 @@ def conv_fwd_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=Fals
     return res
 
 
+TOL_TF32 = 1e-3  # north-star gate for the TF32 variant (relative L2 against the fp32 reference)
+
+
+def nhwc_f32(x_nchw, cstore=None):
+    n, c, h, w = x_nchw.shape
+    cs = cstore or ops.round_up(c, 4)
+    out = torch.zeros((n, h, w, cs), dtype=torch.float32, device=x_nchw.device)
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1)
+    return out
+
+
+def conv_fwd_tf32_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=False, out_pad=0, out_mode="nhwc",
+                       bias=False, act=ops.ACT_NONE, stats=False, seed=0, flip=False, round_x=True, round_out=False):
+    """TF32 variant of K1/K2: full-precision fp32 operands in, reference evaluated in float64 on the UNROUNDED
+    operands, so the error is the whole TF32 error (operand rounding + fp32 accumulation)."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((n, cin, h, w), generator=gen, device="cuda")
+    if transposed:
+        w4 = torch.randn((cin, cout, k, k), generator=gen, device="cuda") * 0.05
+        ref = F.conv_transpose2d(x.double(), w4.double(), None, stride, pad, out_pad, 1, dil)
+    else:
+        w4 = torch.randn((cout, cin, k, k), generator=gen, device="cuda") * 0.05
+        ref = F.conv2d(x.double(), w4.double().flip(2, 3) if flip else w4.double(), None, stride, pad, dil)
+    b = None
+    if bias:
+        b = torch.randn(cout, generator=gen, device="cuda")
+        ref = ref + b.double().view(1, -1, 1, 1)
+    if act == ops.ACT_LEAKY:
+        ref = F.leaky_relu(ref, 0.2)
+    elif act == ops.ACT_TANH:
+        ref = torch.tanh(ref)
+    p, q = ref.shape[2], ref.shape[3]
+    xs = nhwc_f32(x)
+    if round_x:
+        ops.round_tf32_(xs)
+    wp, rows_pad, kpad = ops.pack_conv_weight_tf32(w4.contiguous(), rows_are_dim0=not transposed)
+    g = ops.geom(k, k, stride, pad, pad, dil, transposed, 0, flip)
+    st = torch.zeros((n, cout, 2), dtype=torch.float32, device="cuda") if stats else None
+    flags = ops.EP_ROUND_TF32 if round_out else 0
+    if out_mode == "nhwc":
+        cs = ops.round_up(cout, 4)
+        y = torch.full((n, p, q, cs), float("nan"), dtype=torch.float32, device="cuda")
+        ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nhwc(y, cout), b, act, 0.2, st, flags)
+        got = y[..., :cout].permute(0, 3, 1, 2)
+        pad_ok = bool((y[..., cout:] == 0).all()) if cs > cout else True
+    else:
+        y = torch.full((n, cout, p, q), float("nan"), dtype=torch.float32, device="cuda")
+        ops.conv2d_fwd(g, xs, wp, rows_pad, kpad, ops.out_view_nchw(y), b, act, 0.2, st, flags)
+        got = y
+        pad_ok = True
+    torch.cuda.synchronize()
+    err = rel_l2(got, ref)
+    res = {"err": err, "tol": TOL_TF32, "ok": err <= TOL_TF32 and pad_ok and bool(torch.isfinite(got).all())}
+    if round_out:  # every stored value must already be a TF32 number (low 13 mantissa bits clear)
+        res["rounded"] = bool(((got.contiguous().view(torch.int32) & 0x1FFF) == 0).all())
+        res["ok"] = res["ok"] and res["rounded"]
+    if stats:
+        s_ref = torch.stack([ref.sum((2, 3)), (ref * ref).sum((2, 3))], -1)
+        res["stats_err"] = rel_l2(st, s_ref)
+        res["ok"] = res["ok"] and res["stats_err"] < 1e-3
+    return res
+
+
+def conv_wgrad_tf32_case(n, cin, cout, h, w, k, stride=1, pad=0, dil=1, transposed=False, out_pad=0,
+                         accumulate=False, seed=0):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((n, cin, h, w), generator=gen, device="cuda")
+    xd = x.double()
+    if transposed:
+        w4 = torch.zeros((cin, cout, k, k), device="cuda", dtype=torch.float64, requires_grad=True)
+        y = F.conv_transpose2d(xd, w4, None, stride, pad, out_pad, 1, dil)
+    else:
+        w4 = torch.zeros((cout, cin, k, k), device="cuda", dtype=torch.float64, requires_grad=True)
+        y = F.conv2d(xd, w4, None, stride, pad, dil)
+    dy = torch.randn(tuple(y.shape), generator=gen, device="cuda") * 0.1
+    y.backward(dy.double())
+    ref = w4.grad
+    xs, dys = ops.round_tf32_(nhwc_f32(x)), ops.round_tf32_(nhwc_f32(dy))
+    g = ops.geom(k, k, stride, pad, pad, dil, transposed, 0)
+    base = (torch.randn(ref.shape, generator=gen, device="cuda") if accumulate
+            else torch.zeros(ref.shape, device="cuda"))
+    dw = base.clone()
+    ops.conv2d_wgrad(g, xs, dys, dw, accumulate)
+    torch.cuda.synchronize()
+    err = rel_l2(dw - base if accumulate else dw, ref)
+    return {"err": err, "tol": TOL_TF32, "ok": err <= TOL_TF32}
+
+
+TF32_FWD_CASES = {
+    "tf32_gemm_1x1_c64_n16": dict(n=1, cin=64, cout=16, h=8, w=16, k=1),
+    "tf32_gemm_1x1_c128_n256": dict(n=2, cin=128, cout=256, h=16, w=32, k=1),
+    "tf32_gemm_1x1_c96_n512_truncated_x": dict(n=1, cin=96, cout=512, h=16, w=16, k=1, round_x=False),
+    "tf32_r256_zero_pad_stats": dict(n=2, cin=256, cout=256, h=64, w=64, k=3, pad=1, stats=True, round_out=True),
+    "tf32_r256_prepadded_nchw": dict(n=1, cin=256, cout=256, h=66, w=66, k=3, out_mode="nchw"),
+    "tf32_flat_flip_c128_bias_leaky": dict(n=2, cin=128, cout=128, h=40, w=50, k=3, flip=True, bias=True, act=ops.ACT_LEAKY, round_out=True),
+    "tf32_flat_4x4_c256_512_stats": dict(n=2, cin=256, cout=512, h=34, w=34, k=4, stats=True),
+    "tf32_conv3x3_s2_64_128": dict(n=2, cin=64, cout=128, h=32, w=32, k=3, stride=2, pad=1),
+    "tf32_conv4x4_s2_patchgan": dict(n=2, cin=64, cout=128, h=64, w=64, k=4, stride=2, pad=1, bias=True, act=ops.ACT_LEAKY),
+    "tf32_conv4x4_s1_cout1": dict(n=2, cin=512, cout=1, h=31, w=31, k=4, pad=1, bias=True, out_mode="nchw"),
+    "tf32_conv3x3_dil2": dict(n=1, cin=64, cout=64, h=12, w=40, k=3, pad=2, dil=2),
+    "tf32_conv7x7_cout3_tanh": dict(n=1, cin=64, cout=3, h=70, w=70, k=7, bias=True, act=ops.ACT_TANH, out_mode="nchw"),
+    "tf32_conv_cin3_image": dict(n=1, cin=3, cout=64, h=38, w=38, k=7),
+    "tf32_convT3x3_s2": dict(n=2, cin=256, cout=128, h=16, w=16, k=3, stride=2, pad=1, transposed=True, out_pad=1),
+    "tf32_convT4x4_s2": dict(n=2, cin=128, cout=64, h=8, w=8, k=4, stride=2, pad=1, transposed=True),
+    "tf32_dgrad_flip_3x3_pad2": dict(n=1, cin=256, cout=256, h=64, w=64, k=3, pad=2, flip=True),
+}
+
+TF32_WGRAD_CASES = {
+    "tf32_wgrad_3x3_256": dict(n=2, cin=256, cout=256, h=34, w=34, k=3),
+    "tf32_wgrad_3x3_pad1_128_64": dict(n=2, cin=128, cout=64, h=32, w=32, k=3, pad=1, accumulate=True),
+    "tf32_wgrad_4x4_s2": dict(n=2, cin=64, cout=128, h=32, w=32, k=4, stride=2, pad=1),
+    "tf32_wgrad_4x4_s1_cout1": dict(n=2, cin=512, cout=1, h=31, w=31, k=4, pad=1),
+    "tf32_wgrad_convT3x3_s2": dict(n=2, cin=256, cout=128, h=16, w=16, k=3, stride=2, pad=1, transposed=True, out_pad=1),
+    "tf32_wgrad_cin3_7x7": dict(n=2, cin=3, cout=64, h=38, w=38, k=7),
+}
+
+
 def conv_rowpack_case(n, cin, cout, h, w, k, stride, rowpack, seed=0):
     """Image-input layers: x holds `rowpack` channels per pixel, padding materialised by the caller."""
     gen = torch.Generator(device="cuda").manual_seed(seed)

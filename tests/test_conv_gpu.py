@@ -32,3 +32,14 @@ def test_conv_wgrad(name):
 @pytest.mark.parametrize("name", sorted(cc.WGRAD_FEWCOUT_CASES))
 def test_conv_wgrad_few_output_channels(name):
     _assert_ok(cc.conv_wgrad_fewcout_case(**cc.WGRAD_FEWCOUT_CASES[name]))
+
+
+@pytest.mark.parametrize("name", sorted(cc.TF32_FWD_CASES))
+def test_conv_fwd_tf32(name):
+    """TF32 variant (kind::tf32) of conv / transposed conv / flipped data gradient: relative L2 <= 1e-3 vs float64."""
+    _assert_ok(cc.conv_fwd_tf32_case(**cc.TF32_FWD_CASES[name]))
+
+
+@pytest.mark.parametrize("name", sorted(cc.TF32_WGRAD_CASES))
+def test_conv_wgrad_tf32(name):
+    _assert_ok(cc.conv_wgrad_tf32_case(**cc.TF32_WGRAD_CASES[name]))
