@@ -158,6 +158,67 @@ __global__ void __launch_bounds__(256) pw_avgpool_bwd_kernel(PView g, PView dx, 
   }
 }
 
+// ---- out = alpha * x (skip connections scaled by a constant, models/encoder_decoder.py:198-205; its own backward)
+__global__ void __launch_bounds__(256) pw_scale_kernel(PView x, PView o, float alpha, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, o.w, o.h)
+    float t[8];
+    ld8(x, n, h, w, c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] *= alpha;
+    st8(o, n, h, w, c, t);
+  }
+}
+
+// ---- nn.Upsample(scale_factor=2, mode='nearest') (models/encoder_decoder.py:193) and its backward (2x2 sums)
+__global__ void __launch_bounds__(256) pw_nearest_fwd_kernel(PView x, PView o, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, o.w, o.h)
+    *reinterpret_cast<uint4*>(bfw(o, n, h, w, c)) = *reinterpret_cast<const uint4*>(bf(x, n, h >> 1, w >> 1, c));
+  }
+}
+__global__ void __launch_bounds__(256) pw_nearest_bwd_kernel(PView g, PView dx, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, dx.w, dx.h)
+    float acc[8], t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        ld8(g, n, 2 * h + a, 2 * w + b, c, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += t[j];
+      }
+    st8(dx, n, h, w, c, acc);
+  }
+}
+
+// ---- nn.Tanh() inside a network (models/encoder_decoder.py:112: the output blocks feed the next decoder level):
+// out = tanh(x);  dx = g * (1 - out^2)
+__global__ void __launch_bounds__(256) pw_tanh_fwd_kernel(PView x, PView o, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, o.w, o.h)
+    float t[8];
+    ld8(x, n, h, w, c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = tanhf(t[j]);
+    st8(o, n, h, w, c, t);
+  }
+}
+__global__ void __launch_bounds__(256) pw_tanh_bwd_kernel(PView y, PView g, PView dx, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, dx.w, dx.h)
+    float t[8], u[8];
+    ld8(y, n, h, w, c, t);
+    ld8(g, n, h, w, c, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] *= 1.f - t[j] * t[j];
+    st8(dx, n, h, w, c, u);
+  }
+}
+
 // ---- channel attention gate: out = [base +] sigmoid(att_sum[n][c][0] * inv_hw) * s
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
@@ -490,6 +551,69 @@ extern "C" int cdb_avgpool2_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_
   const int64_t total = vec_total(dx);
   if (total == 0) return CDB_OK;
   pw_avgpool_bwd_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(dout), pview(dx), total, dx->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_scale(const CdbAct* x, float alpha, const CdbAct* out, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(x, "scale x")) || (rc = pw_check(out, "scale out"))) return rc;
+  CDB_REQUIRE(same_shape(x, out), CDB_ERR_BAD_DESC, "scale: shapes differ");
+  const int64_t total = vec_total(out);
+  if (total == 0) return CDB_OK;
+  pw_scale_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), alpha, total, out->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_nearest2x_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(x, "nearest2x x")) || (rc = pw_check(out, "nearest2x out"))) return rc;
+  CDB_REQUIRE(out->n == x->n && out->c == x->c && out->h == 2 * x->h && out->w == 2 * x->w, CDB_ERR_BAD_DESC,
+              "nearest2x: output must be [n, 2h, 2w, c]");
+  const int64_t total = vec_total(out);
+  if (total == 0) return CDB_OK;
+  pw_nearest_fwd_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), total, out->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_nearest2x_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(dout, "nearest2x_bwd dout")) || (rc = pw_check(dx, "nearest2x_bwd dx"))) return rc;
+  CDB_REQUIRE(dout->n == dx->n && dout->c == dx->c && dout->h == 2 * dx->h && dout->w == 2 * dx->w, CDB_ERR_BAD_DESC,
+              "nearest2x_bwd: dout must be [n, 2h, 2w, c]");
+  const int64_t total = vec_total(dx);
+  if (total == 0) return CDB_OK;
+  pw_nearest_bwd_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(dout), pview(dx), total, dx->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_tanh_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(x, "tanh x")) || (rc = pw_check(out, "tanh out"))) return rc;
+  CDB_REQUIRE(same_shape(x, out), CDB_ERR_BAD_DESC, "tanh: shapes differ");
+  const int64_t total = vec_total(out);
+  if (total == 0) return CDB_OK;
+  pw_tanh_fwd_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), total, out->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_tanh_bwd(const CdbAct* out, const CdbAct* g, const CdbAct* dx, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(out, "tanh_bwd out")) || (rc = pw_check(g, "tanh_bwd g")) || (rc = pw_check(dx, "tanh_bwd dx")))
+    return rc;
+  CDB_REQUIRE(same_shape(out, g) && same_shape(out, dx), CDB_ERR_BAD_DESC, "tanh_bwd: shapes differ");
+  const int64_t total = vec_total(dx);
+  if (total == 0) return CDB_OK;
+  pw_tanh_bwd_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(out), pview(g), pview(dx), total, dx->c / 8);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

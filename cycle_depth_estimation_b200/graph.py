@@ -113,8 +113,16 @@ class Tape:
             return None, None
         halo_items = [g for g, ch in items if ch]
         plain = [g for g, ch in items if not ch]
-        if len(halo_items) > 1:
-            raise NotImplementedError("two gradient contributions covering the halo of one value")
+        while len(halo_items) > 1:
+            # several consumers read the reflect-padded buffer (models/encoder_decoder.py:196-197: a decoder level and
+            # its output block): fold the halo of the extra contributions into interior-shaped tensors first
+            if v.halo_kind != 'reflect':
+                raise NotImplementedError("two halo-covering gradient contributions of a zero-padded value")
+            g = halo_items.pop()
+            folded = torch.empty(tuple(v.t.shape), dtype=BF16, device=self.dev)
+            desc = ops.norm_desc(NORM_NONE, ACT_NONE, 0.0, 0.0, v.c, v.halo)
+            ops.norm_act_bwd(desc, v.t, folded, g, None, None, None)
+            plain.append(folded)
         dout = halo_items[0] if halo_items else None
         while len(plain) > (1 if dout is not None else 2):
             a, b = plain.pop(), plain.pop()
@@ -538,9 +546,11 @@ class Tape:
         return outv
 
     # ---------------------------------------------------------------- pooling / resampling / gates
-    def avgpool2(self, x, out=None):
+    def avgpool2(self, x, out=None, halo=0, halo_kind=None):
         n, h, w, _ = x.t.shape
-        outv = out if out is not None else self.new_val(n, h // 2, w // 2, x.c)
+        outv = out if out is not None else self.new_val(n, h // 2, w // 2, x.c, halo, halo_kind)
+        if out is None and halo and halo_kind != 'zero':
+            raise NotImplementedError("avgpool2 writes the interior only (zero halo)")
         ops.avgpool2_fwd(x.t, outv.t)
         self._fill_stats(outv)
         if self.record:
@@ -598,11 +608,13 @@ class Tape:
             self.back.append(backward)
         return outv
 
-    def prelu(self, x, prelu_module, halo=0, halo_kind=None):
+    def prelu(self, x, prelu_module, halo=0, halo_kind=None, out=None):
         if prelu_module.weight.numel() != 1:
             raise NotImplementedError("per-channel PReLU")
+        if out is None and halo and halo_kind != 'zero':
+            raise NotImplementedError("prelu writes the interior only (zero halo)")
         n, h, w, _ = x.t.shape
-        outv = self.new_val(n, h, w, x.c, halo, halo_kind)
+        outv = out if out is not None else self.new_val(n, h, w, x.c, halo, halo_kind)
         ops.prelu_fwd(x.t, prelu_module.weight, outv.t)
         if self.record:
             def backward():
@@ -616,6 +628,55 @@ class Tape:
                 self.add_grad(x, dx)
                 if want:
                     self.add_param_grad(prelu_module.weight, ds)
+            self.back.append(backward)
+        return outv
+
+    def scale(self, x, alpha, out=None):
+        """out = alpha * x (the down-weighted skip connections of models/encoder_decoder.py:196-205)."""
+        n, h, w, _ = x.t.shape
+        outv = out if out is not None else self.new_val(n, h, w, x.c)
+        ops.scale(x.t, float(alpha), outv.t)
+        if self.record:
+            def backward():
+                g = self.total_grad(outv)
+                if g is None:
+                    return
+                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                ops.scale(g, float(alpha), dx)
+                self.add_grad(x, dx)
+            self.back.append(backward)
+        return outv
+
+    def nearest2x(self, x, out=None):
+        """nn.Upsample(scale_factor=2, mode='nearest') (models/encoder_decoder.py:193)."""
+        n, h, w, _ = x.t.shape
+        outv = out if out is not None else self.new_val(n, 2 * h, 2 * w, x.c)
+        ops.nearest2x_fwd(x.t, outv.t)
+        if self.record:
+            def backward():
+                g = self.total_grad(outv)
+                if g is None:
+                    return
+                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                ops.nearest2x_bwd(g, dx)
+                self.add_grad(x, dx)
+            self.back.append(backward)
+        return outv
+
+    def tanh(self, x):
+        """nn.Tanh() on a value that stays inside the network (the intermediate output blocks of
+        models/encoder_decoder.py:103-117 feed the next decoder level)."""
+        n, h, w, _ = x.t.shape
+        outv = self.new_val(n, h, w, x.c)
+        ops.tanh_fwd(x.t, outv.t)
+        if self.record:
+            def backward():
+                g = self.total_grad(outv)
+                if g is None:
+                    return
+                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                ops.tanh_bwd(outv.t, g, dx)
+                self.add_grad(x, dx)
             self.back.append(backward)
         return outv
 

@@ -360,6 +360,31 @@ def bilinear2x_bwd(dout, dx):
     check(_lib.lib().cdb_bilinear2x_bwd(_v(dout), _v(dx), _stream()))
 
 
+def scale(x, alpha, out):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_scale(_v(x), C.c_float(alpha), _v(out), _stream()))
+
+
+def nearest2x_fwd(x, out):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_nearest2x_fwd(_v(x), _v(out), _stream()))
+
+
+def nearest2x_bwd(dout, dx):
+    _require_cuda(dout, dx)
+    check(_lib.lib().cdb_nearest2x_bwd(_v(dout), _v(dx), _stream()))
+
+
+def tanh_fwd(x, out):
+    _require_cuda(x, out)
+    check(_lib.lib().cdb_tanh_fwd(_v(x), _v(out), _stream()))
+
+
+def tanh_bwd(out, g, dx):
+    _require_cuda(out, g, dx)
+    check(_lib.lib().cdb_tanh_bwd(_v(out), _v(g), _v(dx), _stream()))
+
+
 def prelu_fwd(x, slope, out):
     _require_cuda(x, slope, out)
     check(_lib.lib().cdb_prelu_fwd(_v(x), _p(slope), _v(out), _stream()))

@@ -240,6 +240,14 @@ int cdb_gate_bcast(const float* dsum, const float* att_sum, int32_t c_real, floa
 /* nn.UpsamplingBilinear2d(scale_factor=2) == align_corners=True (networks5_ds.py:637,713). */
 int cdb_bilinear2x_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream);
 int cdb_bilinear2x_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_t stream);
+/* SURVEY 8(f) row f3 (models/encoder_decoder.py): out = alpha * x (scaled skip connections :198-205);
+ * nn.Upsample(scale_factor=2, mode='nearest') (:193) and its backward (dx = 2x2 sums of dout);
+ * nn.Tanh() inside a network (:112, the output blocks feed the next decoder level): dx = g * (1 - out^2). */
+int cdb_scale(const CdbAct* x, float alpha, const CdbAct* out, cdbStream_t stream);
+int cdb_nearest2x_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream);
+int cdb_nearest2x_bwd(const CdbAct* dout, const CdbAct* dx, cdbStream_t stream);
+int cdb_tanh_fwd(const CdbAct* x, const CdbAct* out, cdbStream_t stream);
+int cdb_tanh_bwd(const CdbAct* out, const CdbAct* g, const CdbAct* dx, cdbStream_t stream);
 /* nn.PReLU() with one learnable slope read from device memory (networks5_ds.py:498,551); *dslope += .. */
 int cdb_prelu_fwd(const CdbAct* x, const float* slope, const CdbAct* out, cdbStream_t stream);
 int cdb_prelu_bwd(const CdbAct* x, const CdbAct* g, const float* slope, const CdbAct* dx, float* dslope,

@@ -157,6 +157,27 @@ def make_networks5(N5):
     return fx
 
 
+def make_encoder_decoder(ED):
+    """Outputs and input gradients of the reference's own _UNetEncoder / _UNetDecoder (models/encoder_decoder.py,
+    CPU, training-mode BatchNorm, ngf=8) on name-keyed synthetic weights with the shared PReLU tied."""
+    from oracle import encoder_decoder_oracle as OE
+    from oracle import networks5_oracle as O5
+    enc, dec = ED._UNetEncoder(input_nc=3, ngf=8), ED._UNetDecoder(output_nc=5, ngf=8)
+    enc.load_state_dict(OE.tie_prelu(O5.synth_state_dict(enc.state_dict(), 11)), strict=True)
+    dec.load_state_dict(OE.tie_prelu(O5.synth_state_dict(dec.state_dict(), 12)), strict=True)
+    enc.train()
+    dec.train()
+    x = image(1, 3, 96, 96, 51).requires_grad_(True)
+    feats = enc(x)
+    outs = dec(feats)
+    gout = image(1, 5, 96, 96, 52)
+    (outs[-1] * gout).sum().backward()
+    return dict(x=x.detach(), gout=gout, feats=[f.detach() for f in feats], outs=[o.detach() for o in outs[1:]],
+                gx=x.grad, enc_keys=list(enc.state_dict().keys()), dec_keys=list(dec.state_dict().keys()),
+                g_enc_slope=enc.conv1[3].weight.grad.clone(), g_dec_slope=dec.deconv_center.model[3].weight.grad.clone(),
+                g_dec_out1=dec.output1.model[1].weight.grad.clone())
+
+
 def main():
     if not available():
         raise SystemExit("reference not found at %s" % REF)
@@ -171,6 +192,8 @@ def main():
         sys.path.insert(0, ROOT)
     N5 = load_ref("ref_networks5_ds", "new_multi/networks5_ds.py")
     torch.save(make_networks5(N5), os.path.join(OUT, "networks5.pt"))
+    ED = load_ref("ref_encoder_decoder", "models/encoder_decoder.py")
+    torch.save(make_encoder_decoder(ED), os.path.join(OUT, "encoder_decoder.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
