@@ -119,6 +119,8 @@ class GradBuckets:
 
 
 class CycleGANModel:
+    D_ITERS = 4     # discriminator updates per generator update (the fork's schedule, models/cycle_gan_model.py:151)
+
     def name(self):
         return 'CycleGANModel'
 
@@ -266,11 +268,11 @@ class CycleGANModel:
         if dist.is_available() and dist.is_initialized():
             b *= dist.get_world_size()          # replicated pools see the global batch in rank-major order
         if self._plan_host is None:
-            self._plan_host = torch.empty((8, b, 2), dtype=torch.int32).pin_memory()
-            self._plan_dev = torch.empty((8, b, 2), dtype=torch.int32, device=self.device)
+            self._plan_host = torch.empty((2 * self.D_ITERS, b, 2), dtype=torch.int32).pin_memory()
+            self._plan_dev = torch.empty((2 * self.D_ITERS, b, 2), dtype=torch.int32, device=self.device)
         self._step_graph.wait_previous()        # the previous replay has consumed the pinned table
         rows = []
-        for _ in range(4):                      # the order of backward_D_A / backward_D_B in the step
+        for _ in range(self.D_ITERS):           # the order of backward_D_A / backward_D_B in the step
             rows.append(self.fake_B_pool.plan(b))
             rows.append(self.fake_A_pool.plan(b))
         self._plan_host.copy_(torch.tensor(rows, dtype=torch.int32))
@@ -309,7 +311,7 @@ class CycleGANModel:
             self.loss_G.backward()
             self._buckets_G.all_reduce()
             self.optimizer_G.step()
-        for _ in range(4):
+        for _ in range(self.D_ITERS):
             self.set_requires_grad([self.netD_A, self.netD_B], True)
             self.optimizer_D.zero_grad()
             self.loss_D_A = self.backward_D_A()

@@ -5,6 +5,8 @@ Plain-PyTorch fp32 functional restatement of the U-Net task network of the refer
 
 * ``unet_encoder``   models/encoder_decoder.py:122-162 (+ _EncoderBlock :30-46, _InceptionBlock :47-82)
 * ``unet_decoder``   models/encoder_decoder.py:164-208 (+ _DecoderUpBlock :84-101, _OutputBlock :103-117)
+* ``SegCycleStepOracle``   models/seg_cycle.py:87-180 (Seg_basic, backward_G with the four task losses, ONE
+  discriminator update per generator update)
 
 The reference creates ONE ``nn.PReLU`` per network and hands it to every block (:134,:175): the slope is read from
 the network's first PReLU key (``ENC_SLOPE`` / ``DEC_SLOPE``); ``tie_prelu`` makes a state_dict consistent with that.
@@ -104,3 +106,70 @@ def unet_decoder(sd, feats, training=True, weight=0.1):
     output2 = _out_block(sd, 'output2.', cat2)
     output1 = _out_block(sd, 'output1.', torch.cat([deconv2, _up2(output2)], 1))
     return [center_in, output4, output3, output2, output1]
+
+
+# ------------------------------------------------------------------------------------------------
+# SegCycle training step (models/seg_cycle.py)
+# ------------------------------------------------------------------------------------------------
+from oracle.networks_oracle import CycleGANStepOracle, gan_loss, l1  # noqa: E402
+
+
+class SegCycleStepOracle(CycleGANStepOracle):
+    """Restated glue of SegCycle (models/seg_cycle.py:87-180): the CycleGAN step with four CrossEntropy(ignore 255)
+    task losses added to loss_G (:129-136, :150-151) — (encoderA, decoderA) on real_A and (encoderB, decoderA) on
+    fake_B against lab_A, (encoderB, decoderB) on real_B and (encoderA, decoderB) on fake_A against lab_B — Adam
+    over the generators AND the task networks (:69-73) and a single discriminator update (:167-176)."""
+
+    def __init__(self, sd_G_A, sd_G_B, sd_D_A, sd_D_B, sd_encA, sd_encB, sd_decA, sd_decB, lr=2e-4, beta1=0.5, **kw):
+        super().__init__(sd_G_A, sd_G_B, sd_D_A, sd_D_B, lr=lr, beta1=beta1, d_iters=1, **kw)
+        mk = lambda sd: tie_prelu({k: v.detach().clone().requires_grad_(v.is_floating_point() and 'running_' not in k)
+                                   for k, v in sd.items()})
+        self.encA, self.encB, self.decA, self.decB = mk(sd_encA), mk(sd_encB), mk(sd_decA), mk(sd_decB)
+        seen, params = set(), []
+        for d in (self.G_A, self.G_B, self.encA, self.encB, self.decA, self.decB):
+            for p in d.values():
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
+        self.opt_G = torch.optim.Adam(params, lr=lr, betas=(beta1, 0.999))
+
+    def _seg(self, enc, dec, x, gt):
+        out = unet_decoder(dec, unet_encoder(enc, x))
+        return F.cross_entropy(out[-1], gt.squeeze(1), ignore_index=255)
+
+    def step(self, real_A, real_B, lab_A, lab_B, train=True, apply_updates=True):
+        fake_B = self._g(self.G_A, real_A)
+        rec_A = self._g(self.G_B, fake_B)
+        fake_A = self._g(self.G_B, real_B)
+        rec_B = self._g(self.G_A, fake_A)
+        self._set_requires_grad([self.D_A, self.D_B], False)
+        self.opt_G.zero_grad()
+        L = self.losses
+        L['idt_A'] = l1(self._g(self.G_A, real_B), real_B) * self.lambda_B * self.lambda_idt
+        L['idt_B'] = l1(self._g(self.G_B, real_A), real_A) * self.lambda_A * self.lambda_idt
+        L['segAreal'] = self._seg(self.encA, self.decA, real_A, lab_A)
+        L['segAfake'] = self._seg(self.encB, self.decA, fake_B, lab_A)
+        L['segBreal'] = self._seg(self.encB, self.decB, real_B, lab_B)
+        L['segBfake'] = self._seg(self.encA, self.decB, fake_A, lab_B)
+        L['G_A'] = gan_loss(self._d(self.D_A, fake_B), True)
+        L['G_B'] = gan_loss(self._d(self.D_B, fake_A), True)
+        L['cycle_A'] = l1(rec_A, real_A) * self.lambda_A
+        L['cycle_B'] = l1(rec_B, real_B) * self.lambda_B
+        loss_G = (L['G_A'] + L['G_B'] + L['cycle_A'] + L['cycle_B'] + L['idt_A'] + L['idt_B'] + L['segAfake']
+                  + L['segAreal'] + L['segBfake'] + L['segBreal'])
+        L['G'] = loss_G
+        if train:
+            loss_G.backward()
+            if apply_updates:
+                self.opt_G.step()
+        self._set_requires_grad([self.D_A, self.D_B], True)
+        self.opt_D.zero_grad()
+        L['D_A'] = self._d_loss(self.D_A, real_B, self.fake_B_pool.query(fake_B))
+        L['D_B'] = self._d_loss(self.D_B, real_A, self.fake_A_pool.query(fake_A))
+        if train:
+            L['D_A'].backward()
+            L['D_B'].backward()
+            if apply_updates:
+                self.opt_D.step()
+        self.fake_A, self.fake_B, self.rec_A, self.rec_B = fake_A, fake_B, rec_A, rec_B
+        return {k: float(v) for k, v in L.items()}
