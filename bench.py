@@ -502,7 +502,33 @@ def secondary_cpu_baseline(wl, batch):
         return {"value": 1.0 / (dt * batch), "unit": "iters/s (scaled to batch %d)" % batch, "cores": cores,
                 "kind": "port", "sample": "one batch-1 step at 192x640 (torch CPU fp32, no warm-up), scaled linearly to "
                                           "batch %d" % batch}
+    if wl == "segcycle":
+        from oracle import encoder_decoder_oracle as OE
+        from cycle_depth_estimation_b200 import encoder_decoder as E
+        from cycle_depth_estimation_b200 import networks as N
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            gs = [N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+            ds = [N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+        tn = [E._UNetEncoder(3), E._UNetEncoder(3), E._UNetDecoder(22), E._UNetDecoder(28)]
+        oracle = OE.SegCycleStepOracle(*[m.state_dict() for m in gs + ds + tn])
+        a, b2 = synthetic_batch(1, 256, 1234)
+        la, lb = _seg_labels(1, 256, 22, 5), _seg_labels(1, 256, 28, 6)
+        t0 = time.perf_counter()
+        oracle.step(a, b2, la, lb)
+        dt = time.perf_counter() - t0
+        return {"value": 1.0 / (dt * batch), "unit": "iters/s (scaled to batch %d)" % batch, "cores": cores,
+                "kind": "port", "sample": "one batch-1 step at 256x256 (torch CPU fp32, no warm-up), scaled linearly to "
+                                          "batch %d" % batch}
     return None
+
+
+def _seg_labels(n, size, classes, seed):
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.randint(0, classes, (n, 1, size, size), generator=g)
+    lab[torch.rand((n, 1, size, size), generator=g) < 0.02] = 255
+    return lab
 
 
 def secondary_arm(args):
@@ -579,6 +605,37 @@ def secondary_arm(args):
         workload = ("new_multi model5 step: G_1 + General_net + R_dep + 3 feature discriminators, CE + L1 + BCEDep + "
                     "LSGAN, 8 optimizer updates; batch %d at 192x640 (BASELINE configs[3])" % b)
         h2d, d2h = int(sum(v.numel() * v.element_size() for v in data.values())), 32
+    elif wl == "segcycle":
+        from cycle_depth_estimation_b200.seg_cycle import SegCycle
+        b = args.batch
+        model = SegCycle()
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.initialize(make_opt("cuda", not args.no_cuda_graph))
+        extra["launch_mode"] = "eager launches" if args.no_cuda_graph else "cuda graph replay of the whole step"
+        a, bb = synthetic_batch(b, args.size, 1234)
+        data = {'img_source': a, 'img_target': bb, 'lab_source': _seg_labels(b, args.size, 22, 5),
+                'lab_target': _seg_labels(b, args.size, 28, 6)}
+        host = {k: v.pin_memory() for k, v in data.items()}
+        dev = {k: v.cuda() for k, v in data.items()}
+
+        def step():
+            model.set_input(dev)
+            model.optimize_parameters('train')
+
+        def step_e2e():
+            model.set_input(host)
+            model.optimize_parameters('train')
+            return model.get_current_losses()
+        ms = _time_steps(step, args.steps, max(args.warmup, 5))
+        ms_e2e = _time_steps(step_e2e, args.steps, 1)
+        # FlopCounterMode over the reference modules on the meta device: CycleGAN step with ONE D update 1.879
+        # TFLOP/sample (15.034 / 8) + the four task-network passes fwd+bwd 0.923 TFLOP/sample
+        tflop = (1.879 + 0.9235) * b * (args.size / 256.0) ** 2
+        metric, unit = "segcycle_train_iters_per_s", "iters/s (batch-%d training steps at %dx%d)" % (b, args.size, args.size)
+        workload = ("SegCycle step (models/seg_cycle.py, SURVEY 8(f) f3): CycleGAN resnet_9blocks + PatchGANs + two "
+                    "U-Net task networks (encoder A/B, decoder 22/28 classes), LSGAN + L1 + 4 CrossEntropy, Adam, one D "
+                    "update; batch %d at %dx%d" % (b, args.size, args.size))
+        h2d, d2h = int(sum(v.numel() * v.element_size() for v in data.values())), 48
     elif wl == "g_infer":
         from cycle_depth_estimation_b200 import networks as N
         b = args.batch if args.batch != 8 else 1
@@ -616,7 +673,7 @@ def secondary_arm(args):
     else:
         raise SystemExit("unknown workload " + wl)
     launches = lib.cdb_launch_count() - launches0
-    if wl == "model5" and not args.no_cuda_graph:
+    if wl in ("model5", "segcycle") and not args.no_cuda_graph:
         # replays bypass the library's host entry points: kernels of one captured step x timed steps
         launches = int(model._step_graph.launches) * (2 * args.steps + 1)
     clocks = sampler.stop()
@@ -636,7 +693,7 @@ def secondary_arm(args):
                 "kernel": "whole step (igemm_flat_kernel / igemm_kernel / wgrad_kernel dominate, "
                           "profiles/r01_step_kernels_*.txt)",
                 "peak_source": peaks["source"] + " (sustained)"}
-    cpu = None if args.no_cpu_baseline else secondary_cpu_baseline(wl, b if wl in ("pix2pix", "model5") else 1)
+    cpu = None if args.no_cpu_baseline else secondary_cpu_baseline(wl, b if wl in ("pix2pix", "model5", "segcycle") else 1)
     line = {
         "metric": metric, "value": per_step * 1e3 / ms, "unit": unit, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -665,7 +722,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="eager launches instead of replaying the captured step")
-    ap.add_argument("--workload", default="cyclegan", choices=["cyclegan", "pix2pix", "model5", "g_infer", "metrics"],
+    ap.add_argument("--workload", default="cyclegan", choices=["cyclegan", "pix2pix", "model5", "g_infer", "metrics", "segcycle"],
                     help="cyclegan (default, the headline metric) or one of the secondary BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
