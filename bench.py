@@ -28,8 +28,8 @@ G_FWD_GFLOP = 99.10         # per image
 DOMINANT = dict(n=8, c=256, hw=64, k=3)  # the 18 x 6 residual-block convolutions of a step
 
 
-def make_opt(device, cuda_graph=False):
-    return argparse.Namespace(cuda_graph=cuda_graph, input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
+def make_opt(device, cuda_graph=False, batch_passes=True):
+    return argparse.Namespace(cuda_graph=cuda_graph, batch_passes=batch_passes, input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
                               n_layers_D=3, norm='instance', no_dropout=True, init_type='normal', init_gain=0.02,
                               no_lsgan=False, pool_size=50, lr=2e-4, beta1=0.5, lambda_A=10.0, lambda_B=10.0,
                               lambda_identity=0.5, isTrain=True, device=device, direction='AtoB')
@@ -255,7 +255,7 @@ def b200_arm(args):
         random.seed(1234)
         m = CycleGANModel()
         with contextlib.redirect_stdout(io.StringIO()):
-            m.initialize(make_opt("cuda", use_graph))
+            m.initialize(make_opt("cuda", use_graph, not args.no_batch_passes))
         return m
 
     # The whole step is replayed as ONE CUDA graph (cycle_gan_model.py) — under data parallelism the NCCL
@@ -380,6 +380,7 @@ def b200_arm(args):
                         "cycle/identity, ImagePool 50, Adam, 4 D updates per G update; batch %d per GPU at %dx%d "
                         "(BASELINE configs[1])" % (batch, size, size),
             "per_gpu_batch": batch, "image": size, "parallelism": "dp%d" % world, "launch_mode": graph_note,
+            "batched_passes": not args.no_batch_passes,
             "l2": "working set per step (saved activations of 6 generator + 18 discriminator passes, > 5 GB) "
                   "exceeds the 126 MB L2; no explicit flush",
             "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * batch,
@@ -610,7 +611,7 @@ def secondary_arm(args):
         b = args.batch
         model = SegCycle()
         with contextlib.redirect_stdout(io.StringIO()):
-            model.initialize(make_opt("cuda", not args.no_cuda_graph))
+            model.initialize(make_opt("cuda", not args.no_cuda_graph, not args.no_batch_passes))
         extra["launch_mode"] = "eager launches" if args.no_cuda_graph else "cuda graph replay of the whole step"
         a, bb = synthetic_batch(b, args.size, 1234)
         data = {'img_source': a, 'img_target': bb, 'lab_source': _seg_labels(b, args.size, 22, 5),
@@ -722,6 +723,9 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="eager launches instead of replaying the captured step")
+    ap.add_argument("--no-batch-passes", action="store_true",
+                    help="run every generator / discriminator pass separately (6 + 2 per update) instead of batching "
+                         "the passes that share a network")
     ap.add_argument("--workload", default="cyclegan", choices=["cyclegan", "pix2pix", "model5", "g_infer", "metrics", "segcycle"],
                     help="cyclegan (default, the headline metric) or one of the secondary BASELINE configs")
     args = ap.parse_args()

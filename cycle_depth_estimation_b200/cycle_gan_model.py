@@ -192,7 +192,32 @@ class CycleGANModel:
                 for param in net.parameters():
                     param.requires_grad = requires_grad
 
+    def _batched(self):
+        """opt.batch_passes (default on): passes of one network over independent inputs run as ONE launch sequence on
+        the concatenated batch.  InstanceNorm normalises per sample and the losses are means over equal-sized halves,
+        so every per-sample result is the one the separate passes of models/cycle_gan_model.py:80-99,111-137 produce;
+        what changes is the launch count (6 generator passes -> 3, 2 discriminator passes per update -> 1) and the
+        tile occupancy of the small discriminator layers.  Networks with BatchNorm couple the samples: not batched."""
+        return bool(getattr(self.opt, 'batch_passes', True)) and self.opt.norm == 'instance'
+
     def forward(self):
+        b = self.real_A.shape[0]
+        self._idt_A = self._idt_B = None
+        if self._batched() and self.isTrain and self.real_A.shape == self.real_B.shape:
+            want_idt = self.opt.lambda_identity > 0
+            # G_A over [real_A | real_B]: fake_B and (if used) the identity output idt_A = G_A(real_B)
+            out = self.netG_A(torch.cat([self.real_A, self.real_B], 0) if want_idt else self.real_A)
+            self.fake_B = out[:b]
+            if want_idt:
+                self._idt_A = out[b:]
+            # G_B over [real_B | fake_B | real_A]: fake_A, rec_A and idt_B = G_B(real_A)
+            parts = [self.real_B, self.fake_B] + ([self.real_A] if want_idt else [])
+            out = self.netG_B(torch.cat(parts, 0))
+            self.fake_A, self.rec_A = out[:b], out[b:2 * b]
+            if want_idt:
+                self._idt_B = out[2 * b:]
+            self.rec_B = self.netG_A(self.fake_A)
+            return
         self.fake_B = self.netG_A(self.real_A)
         self.rec_A = self.netG_B(self.fake_B)
         self.fake_A = self.netG_B(self.real_B)
@@ -222,6 +247,10 @@ class CycleGANModel:
         return pool.query(fake)
 
     def backward_D_basic(self, netD, real, fake):
+        if self._batched() and real.shape == fake.shape:
+            pred = netD(torch.cat([real, fake], 0))
+            b = real.shape[0]
+            return (self.criterionGAN(pred[:b], True) + self.criterionGAN(pred[b:], False)) * 0.5
         loss_D_real = self.criterionGAN(netD(real), True)
         loss_D_fake = self.criterionGAN(netD(fake), False)
         return (loss_D_real + loss_D_fake) * 0.5
@@ -239,9 +268,9 @@ class CycleGANModel:
     def backward_G(self):
         lambda_idt, lambda_A, lambda_B = self.opt.lambda_identity, self.opt.lambda_A, self.opt.lambda_B
         if lambda_idt > 0:
-            self.idt_A = self.netG_A(self.real_B)
+            self.idt_A = self._idt_A if getattr(self, '_idt_A', None) is not None else self.netG_A(self.real_B)
             self.loss_idt_A = self.criterionIdt(self.idt_A, self.real_B) * lambda_B * lambda_idt
-            self.idt_B = self.netG_B(self.real_A)
+            self.idt_B = self._idt_B if getattr(self, '_idt_B', None) is not None else self.netG_B(self.real_A)
             self.loss_idt_B = self.criterionIdt(self.idt_B, self.real_A) * lambda_A * lambda_idt
         else:
             self.loss_idt_A = 0
