@@ -33,6 +33,7 @@ struct WgParams {
   int32_t mpad, npad;
   int32_t tf32;                       // fp32 operands multiplied as TF32: 32 channels per 128-byte chunk row
   int32_t cpc;                        // channels per chunk: 64 (bf16) or 32 (tf32)
+  int32_t tg, n_groups;               // taps per item (their shifted tiles sit side by side in N) and tap groups
   float* ws;                          // [splits][taps][mpad][npad]
   int* abort_flag;
   WgTap taps[kWgMaxTaps];
@@ -60,8 +61,8 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   const uint32_t a_chunks = 128u / cpc;
   const uint32_t a_bytes = a_chunks * kChunkBytes;
   const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / cpc;
-  const uint32_t stage_bytes = a_bytes + b_chunks * kChunkBytes;
-  const int total_items = p.n_taps * p.m_tiles * p.n_tiles * p.splits;
+  const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.tg) * b_chunks * kChunkBytes;
+  const int total_items = p.n_groups * p.m_tiles * p.n_tiles * p.splits;
   const int k_tiles_total = p.tiles_n * p.tiles_h * p.tiles_w;
 
   if (threadIdx.x == 0) {
@@ -86,7 +87,10 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   const uint32_t tmem_base = tmem_base_smem;
   volatile int* abort_flag = &abort_smem;
 
-  // item -> (split, tap, m_tile, n_tile); split fastest so that the CTAs of one wave share operands
+  // item -> (split, tap group, m_tile, n_tile); split fastest so that the CTAs of one wave share operands.
+  // A group holds p.tg consecutive taps (tg > 1 only when the shift is on the N side and there is one N tile):
+  // the M-side tile is fetched once per K block for all of them, which is what the few-channel 7x7 layers need
+  // (64-channel operands, 7 filter rows: the dy tile was re-read 7 times).
   auto decode = [&](int item, int& split, int& tap, int& mt, int& nt) {
     split = item % p.splits;
     item /= p.splits;
@@ -104,11 +108,12 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
       for (int item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
         int split, tap, mt, nt;
         decode(item, split, tap, mt, nt);
-        const WgTap tp = p.taps[tap];
+        const int tap0 = tap * p.tg;
+        const int ntap = min(p.tg, p.n_taps - tap0);
+        const WgTap tp = p.taps[tap0];
         const CUtensorMap* amap = p.shift_on_a ? &maps.shift[tp.map] : &maps.fixed;
-        const CUtensorMap* bmap = p.shift_on_a ? &maps.fixed : &maps.shift[tp.map];
         const int a_dh = p.shift_on_a ? tp.dh : 0, a_dw = p.shift_on_a ? tp.dw : 0;
-        const int b_dh = p.shift_on_a ? 0 : tp.dh, b_dw = p.shift_on_a ? 0 : tp.dw;
+        const uint32_t item_bytes = a_bytes + static_cast<uint32_t>(ntap) * b_chunks * kChunkBytes;
         const int kt0 = split * p.k_tiles_per_split;
         int kt1 = kt0 + p.k_tiles_per_split;
         if (kt1 > k_tiles_total) kt1 = k_tiles_total;
@@ -125,12 +130,17 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
           }
           const uint32_t full = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          mbar_arrive_expect_tx(full, stage_bytes);
+          mbar_arrive_expect_tx(full, item_bytes);
           for (uint32_t j = 0; j < a_chunks; ++j)
             tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * cpc, q0 + a_dw, p0 + a_dh, img0);
-          for (uint32_t j = 0; j < b_chunks; ++j)
-            tma_load_4d(bmap, full, sa + a_bytes + j * kChunkBytes, nt * p.bn + j * cpc, q0 + b_dw,
-                        p0 + b_dh, img0);
+          for (int tl = 0; tl < ntap; ++tl) {
+            const WgTap tq = p.taps[tap0 + tl];
+            const CUtensorMap* bmap = p.shift_on_a ? &maps.fixed : &maps.shift[tq.map];
+            const int b_dh = p.shift_on_a ? 0 : tq.dh, b_dw = p.shift_on_a ? 0 : tq.dw;
+            for (uint32_t j = 0; j < b_chunks; ++j)
+              tma_load_4d(bmap, full, sa + a_bytes + (tl * b_chunks + j) * kChunkBytes, nt * p.bn + j * cpc, q0 + b_dw,
+                          p0 + b_dh, img0);
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -141,7 +151,6 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   } else if (warp == 1) {
     if (lane == 0) {
       const bool tf32 = p.tf32 != 0;
-      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -157,6 +166,8 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
         if (!mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag)) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
+        const int ntap = min(p.tg, p.n_taps - tap * p.tg);
+        const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn * ntap));
         for (int kt = kt0; kt < kt1; ++kt) {
           if (!mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag)) {
             ok = false;
@@ -206,9 +217,11 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>(buf) * 256u;
-      float* dst = p.ws + ((static_cast<int64_t>(split) * p.n_taps + tap) * p.mpad + mt * 128 + row) * p.npad +
-                   nt * p.bn;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      const int ntap = min(p.tg, p.n_taps - tap * p.tg);
+      for (int c0 = 0; c0 < p.bn * ntap; c0 += 16) {
+        const int tl = c0 / p.bn, cn = c0 - tl * p.bn;   // bn is a multiple of 64: a 16-column slab never straddles taps
+        float* dst = p.ws + ((static_cast<int64_t>(split) * p.n_taps + tap * p.tg + tl) * p.mpad + mt * 128 + row) *
+                                p.npad + nt * p.bn + cn - c0;
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
@@ -364,6 +377,7 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const __grid_con
 
 struct WgPlan {
   int m_is_s;  // M side = S tensor
+  int tg, n_groups;
   int cM, cN, mpad, npad, bn, m_tiles, n_tiles;
   int tile_w, tile_h, tile_n, tiles_w, tiles_h, tiles_n, k_tiles, splits, k_per_split, n_taps;
 };
@@ -397,7 +411,16 @@ static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g
   pl->tiles_n = ceil_div(s_act->n, pl->tile_n);
   pl->k_tiles = pl->tiles_w * pl->tiles_h * pl->tiles_n;
   pl->n_taps = g->rowpack ? g->r : g->r * g->s;
-  const int items = pl->n_taps * pl->m_tiles * pl->n_tiles;
+  // tap grouping: the shifted operand is on the N side, one N tile, and several of its tiles fit in 256 columns
+  pl->tg = 1;
+  if (pl->m_is_s && pl->n_tiles == 1 && !tf32 && !getenv("CDB_WGRAD_NO_TAP_GROUPS")) {
+    int tg = 256 / pl->bn;
+    if (tg > 4) tg = 4;
+    if (tg > pl->n_taps) tg = pl->n_taps;
+    if (tg >= 1) pl->tg = tg;
+  }
+  pl->n_groups = ceil_div(pl->n_taps, pl->tg);
+  const int items = pl->n_groups * pl->m_tiles * pl->n_tiles;
   static const int waves = getenv("CDB_WGRAD_WAVES") ? atoi(getenv("CDB_WGRAD_WAVES")) : 1;
   int splits = (waves * sm_count()) / (items > 0 ? items : 1);
   if (splits < 1) splits = 1;
@@ -632,9 +655,11 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.npad = pl.npad;
   prm.tf32 = tf32 ? 1 : 0;
   prm.cpc = cpc;
+  prm.tg = pl.tg;
+  prm.n_groups = pl.n_groups;
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
-  const int stage_bytes = (128 / cpc) * kChunkBytes + (pl.bn / cpc) * kChunkBytes;
+  const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;
@@ -644,7 +669,7 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
     CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
-  const int items = pl.n_taps * pl.m_tiles * pl.n_tiles * pl.splits;
+  const int items = pl.n_groups * pl.m_tiles * pl.n_tiles * pl.splits;
   int grid = items < sm_count() ? items : sm_count();
   wgrad_kernel<<<grid, 256, smem, stream>>>(maps, prm);
   CDB_LAUNCH_OK();
