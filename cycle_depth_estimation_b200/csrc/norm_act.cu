@@ -362,7 +362,7 @@ __device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const 
 
 // Per-channel constants: xhat = y*a1 + b1 (a1 = rstd, b1 = -mean*rstd); z = xhat*gamma + beta (AFFINE) or xhat;
 // apply: dy = c1*(ga - m1 - xhat*m2) with c1 = rstd*gamma.  Row-strip mapping as in the forward kernel.
-template <bool kApply, int ACT, bool AFFINE>
+template <bool kApply, int ACT, bool AFFINE, int U>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
   __shared__ float red[kApply ? 1 : 256 * 16];
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
@@ -409,7 +409,6 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
     const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
     const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
     const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
-    constexpr int U = 2;
     const int pad = p.pad, H = p.H, W = p.W;
     const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
     const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
@@ -521,16 +520,25 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
 constexpr int kFusedCluster = 8;
 constexpr int kFusedVecs = 8;  // pixel vectors per thread
 
-template <int ACT>
-__global__ void __cluster_dims__(kFusedCluster, 1, 1) __launch_bounds__(256, 2)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+template <int ACT, bool ASYNC, int OCC>
+__global__ void __cluster_dims__(kFusedCluster, 1, 1) __launch_bounds__(256, OCC)
 norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ uint4 fused_smem[];       // y vectors [8][256] then g vectors [8][256] (thread-private slots)
   uint4* sy = fused_smem;
   uint4* sg = fused_smem + kFusedVecs * 256;
-  __shared__ float red[16 * 256];
-  __shared__ float part[64];    // this CTA's partial (s1, s2) for its 32 channels: [vector][channel][2]
+  __shared__ float red[8 * 64];  // per-warp partials [warp][vector][channel][2]
+  __shared__ float part[64];     // this CTA's partial (s1, s2) for its 32 channels: [vector][channel][2]
   __shared__ float tot[64];
   const int v = threadIdx.x & 3, lane = threadIdx.x >> 2;   // 4 channel vectors x 64 pixel lanes
   const int rank = static_cast<int>(cluster.block_rank());
@@ -539,15 +547,29 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   const int pixels = p.H * p.W;
   const int p0 = rank * ppc, p1 = min(pixels, p0 + ppc);
   const int W = p.W, H = p.H, pad = p.pad;
+  const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
+  const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
+  const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
+  if (ASYNC) {
+    // all 16 y / dout vectors of the thread go global -> shared memory (its private slots) without passing through
+    // registers: 16 copies of 16 bytes in flight per thread = 64 KB per CTA from the first instruction on (the
+    // per-channel coefficients are fetched behind them)
+#pragma unroll
+    for (int u = 0; u < kFusedVecs; ++u) {
+      const int px = p0 + lane + u * 64;
+      const int h = px / W, w = px - h * W;
+      if (px < p1) {
+        cp_async16(&sy[u * 256 + threadIdx.x], yb + h * p.y.sh + w * p.y.sw);
+        if (p.has_dout) cp_async16(&sg[u * 256 + threadIdx.x], db + h * p.dout.sh + w * p.dout.sw);
+      }
+    }
+  }
   float mean[8], rstd[8];
   {
     float scale[8], shift[8];
     norm_coeffs(p.norm, 0, p.stats, nullptr, nullptr, nullptr, nullptr, n, p.C, cvec * 8, p.inv_count, p.eps,
                 scale, shift, mean, rstd);
   }
-  const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
-  const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
-  const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -560,9 +582,19 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
       const int px = p0 + lane + (ub + k) * 64;
       const int h = px / W, w = px - h * W;
       if (px < p1) {
-        yr[k] = ld16(yb + h * p.y.sh + w * p.y.sw);
-        if (p.has_dout) gr[k] = ld16(db + h * p.dout.sh + w * p.dout.sw);
+        if (!ASYNC) {
+          yr[k] = ld16(yb + h * p.y.sh + w * p.y.sw);
+          if (p.has_dout) gr[k] = ld16(db + h * p.dout.sh + w * p.dout.sw);
+        }
         if (p.has_dskip) sr[k] = ld16(sb + h * p.dskip.sh + w * p.dskip.sw);
+      }
+    }
+    if (ASYNC) {
+      if (ub == 0) cp_async_wait_all();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        yr[k] = sy[(ub + k) * 256 + threadIdx.x];
+        if (p.has_dout) gr[k] = sg[(ub + k) * 256 + threadIdx.x];
       }
     }
 #pragma unroll
@@ -585,7 +617,7 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
       for (int j = 0; j < 8; ++j) g[j] += t[j];
     }
     sg[u * 256 + threadIdx.x] = pack8(g);   // the summed gradient (rounded to bf16 once) for the apply phase / gsum
-    sy[u * 256 + threadIdx.x] = yr[k];
+    if (!ASYNC) sy[u * 256 + threadIdx.x] = yr[k];
     unpack8(yr[k], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -598,18 +630,31 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     }
     }
   }
-  // ---- CTA reduction over the 64 pixel lanes (same layout as the two-pass kernel: vt = 4)
+  // ---- CTA reduction over the 64 pixel lanes: a warp holds 8 pixel lanes x 4 channel vectors (lane bits 2..4 are
+  // the pixel lane), so three shuffle steps leave the warp's sums in its first four lanes; 8 warps x 64 values then
+  // go through 2 KB of shared memory
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[(j * 2) * 256 + threadIdx.x] = s1[j];
-    red[(j * 2 + 1) * 256 + threadIdx.x] = s2[j];
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+    }
+  }
+  if ((threadIdx.x & 31) < 4) {
+    float* dst = red + (threadIdx.x >> 5) * 64 + v * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dst[j * 2] = s1[j];
+      dst[j * 2 + 1] = s2[j];
+    }
   }
   __syncthreads();
   if (threadIdx.x < 64) {
-    const int vv = threadIdx.x & 3, comp = threadIdx.x >> 2;   // comp = channel * 2 + {0: s1, 1: s2}
     float acc = 0.f;
-    for (int l = 0; l < 64; ++l) acc += red[comp * 256 + l * 4 + vv];
-    part[vv * 16 + comp] = acc;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) acc += red[wq * 64 + threadIdx.x];
+    part[threadIdx.x] = acc;
   }
   cluster.sync();
   // ---- cluster reduction through distributed shared memory
@@ -619,7 +664,7 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     for (int r = 0; r < kFusedCluster; ++r) acc += cluster.map_shared_rank(part, r)[threadIdx.x];
     tot[threadIdx.x] = acc * p.inv_count;
   }
-  cluster.sync();   // also keeps every CTA's `part` alive until all ranks have read it
+  __syncthreads();
   float m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -649,6 +694,7 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     }
     st16(ob + h * p.dy.sh + w * p.dy.sw, pack8(o));
   }
+  cluster.sync();   // keeps every CTA's `part` alive until all ranks have read it (off the critical path)
 }
 
 static bool fused_in_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32) {
@@ -663,27 +709,58 @@ static void launch_norm_bwd_fused(const NormBwdParams& p, int n, cudaStream_t st
   const int pixels = p.H * p.W;
   const int ppc = ceil_div(pixels, kFusedCluster);
   dim3 grid(kFusedCluster, p.C / 32, n);
-  const size_t smem = 2 * kFusedVecs * 256 * sizeof(uint4);   // 64 KB of thread-private y / g slots
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_LEAKY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(norm_bwd_fused_in_kernel<CDB_ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  switch (p.act) {
-    case CDB_ACT_RELU: norm_bwd_fused_in_kernel<CDB_ACT_RELU><<<grid, 256, smem, stream>>>(p, ppc); break;
-    case CDB_ACT_LEAKY: norm_bwd_fused_in_kernel<CDB_ACT_LEAKY><<<grid, 256, smem, stream>>>(p, ppc); break;
-    default: norm_bwd_fused_in_kernel<CDB_ACT_NONE><<<grid, 256, smem, stream>>>(p, ppc); break;
-  }
+  const size_t smem = 2 * kFusedVecs * 256 * sizeof(uint4);   // 64 KB of thread-private y / g slots (3 CTAs per SM)
+  // OCC = resident CTAs per SM the kernel is compiled for: 2 (<= 128 registers) or 3 (<= 85 registers: measured
+  // 2.3x SLOWER on B200, the kernel then spills 1 KB per thread — profiles/r01_norm_bwd_experiments.txt)
+  static const int occ = getenv("CDB_NORM_FUSED_OCC") ? atoi(getenv("CDB_NORM_FUSED_OCC")) : 2;
+  static const bool async = getenv("CDB_NORM_FUSED_ASYNC") ? atoi(getenv("CDB_NORM_FUSED_ASYNC")) != 0 : true;
+#define CDB_FUSED_LAUNCH(ACT_, ASYNC_, OCC_)                                                                       \
+  do {                                                                                                             \
+    static bool attr_done = false;                                                                                 \
+    if (!attr_done) {                                                                                              \
+      cudaFuncSetAttribute(norm_bwd_fused_in_kernel<ACT_, ASYNC_, OCC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                                             \
+      attr_done = true;                                                                                            \
+    }                                                                                                              \
+    norm_bwd_fused_in_kernel<ACT_, ASYNC_, OCC_><<<grid, 256, smem, stream>>>(p, ppc);                             \
+  } while (0)
+#define CDB_FUSED_ACT(ASYNC_, OCC_)                                          \
+  do {                                                                       \
+    switch (p.act) {                                                         \
+      case CDB_ACT_RELU: CDB_FUSED_LAUNCH(CDB_ACT_RELU, ASYNC_, OCC_); break; \
+      case CDB_ACT_LEAKY: CDB_FUSED_LAUNCH(CDB_ACT_LEAKY, ASYNC_, OCC_); break; \
+      default: CDB_FUSED_LAUNCH(CDB_ACT_NONE, ASYNC_, OCC_); break;          \
+    }                                                                        \
+  } while (0)
+  if (async && occ == 3) CDB_FUSED_ACT(true, 3);
+  else if (async) CDB_FUSED_ACT(true, 2);
+  else CDB_FUSED_ACT(false, 2);
+#undef CDB_FUSED_ACT
+#undef CDB_FUSED_LAUNCH
 }
 
+// Pixels per thread and iteration (all their loads are issued before the first use). 4 measured no faster than 2
+// on B200 (the kernels are bound by instruction latency at 2 blocks per SM, not by loads in flight:
+// profiles/r01_norm_bwd_experiments.txt), so 2 is the default and 4 stays selectable for experiments.
+static int bwd_unroll(const NormBwdParams& p) {
+  static const int forced = getenv("CDB_NORM_BWD_U") ? atoi(getenv("CDB_NORM_BWD_U")) : 0;
+  (void)p;
+  return forced == 4 ? 4 : 2;
+}
 template <bool kApply, bool AFFINE>
 static void launch_norm_bwd_act(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  if (bwd_unroll(p) == 4) {
+    switch (p.act) {
+      case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+      case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+      default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+    }
+    return;
+  }
   switch (p.act) {
-    case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE><<<grid, 256, 0, stream>>>(p); break;
-    case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE><<<grid, 256, 0, stream>>>(p); break;
-    default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
+    default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
   }
 }
 template <bool kApply>

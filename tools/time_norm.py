@@ -29,7 +29,9 @@ def run(n, h, w, c, pad, res, iters=30):
     print("n%d %dx%dx%d pad%d res=%d: fwd %.1f us (%.0f GB/s), bwd(reduce+apply) %.1f us (%.0f GB/s)" % (
         n, h, w, c, pad, res, tf, mb * (3 if res else 2) / tf * 1e-3 * 1e3, tb, mb * (5 if not res else 6) / tb * 1e-3 * 1e3), flush=True)
 
-run(8, 64, 64, 256, 1, False)
-run(8, 64, 64, 256, 1, True)
-run(8, 256, 256, 64, 3, False, iters=10)
-run(8, 128, 128, 128, 0, False, iters=10)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+print("batch", B, {k: v for k, v in os.environ.items() if k.startswith("CDB_")}, flush=True)
+run(B, 64, 64, 256, 1, False)
+run(B, 64, 64, 256, 1, True)
+run(B, 256, 256, 64, 3, False, iters=10)
+run(B, 128, 128, 128, 0, False, iters=10)
