@@ -330,6 +330,25 @@ int cdb_depth_pred_to_u8(const float* pred, int32_t n_img, int32_t h, int32_t w,
 int cdb_resize_linear_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, uint8_t* dst, int32_t dh,
                          int32_t dw, void* workspace, size_t ws_bytes, cdbStream_t stream);
 
+/* ---- device side of the loaders' per-sample arithmetic ------------------------------------
+ * cdb_depth_labels: new_multi/try_data.py:240-272 — from n_img raw depth maps depth[n][hw] (fp32, after the
+ *   loader's resize) the normalised depth dep_l[n][hw] (clamped at 8000) and the four range-limited depth labels
+ *   depth_l_s[n][4][hw] ([5000,8000], [3000,6000], [1000,4000], (-inf,2000] — the last one keeps the reference's quirk
+ *   of subtracting the minimum of the already normalised third range, :266); bit-identical to the numpy float32
+ *   statements (IEEE single ops in the same order; degenerate ranges give the same NaN / inf).
+ *   workspace: cdb_depth_labels_workspace(n_img) bytes, 4-byte aligned.
+ * cdb_label_lut_i64: dst[i] = lut[src[i]] as int64 class ids — the label-id remapping loops of
+ *   datasets/dataset_synthia.py:172-183 / new_multi/try_data.py:199-211 composed into one 256-entry table by the host
+ *   (input_pipeline.label_lut_*), followed by MaskToTensor (:26-28).
+ * cdb_image_normalize_u8: transforms.ToTensor() + transforms.Normalize(mean, std) (new_multi/try_data.py:425):
+ *   dst[n][c][hw] = (src[n][hw][c] / 255 - mean) / std in IEEE single arithmetic. */
+size_t cdb_depth_labels_workspace(int32_t n_img);
+int cdb_depth_labels(const float* depth, int32_t n_img, int64_t hw, float* dep_l, float* depth_l_s, void* workspace,
+                     size_t ws_bytes, cdbStream_t stream);
+int cdb_label_lut_i64(const uint8_t* src, int64_t numel, const uint8_t* lut_dev, int64_t* dst, cdbStream_t stream);
+int cdb_image_normalize_u8(const uint8_t* src, int32_t n_img, int64_t hw, int32_t channels, float mean, float stdv,
+                           float* dst, cdbStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

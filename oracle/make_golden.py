@@ -178,6 +178,61 @@ def make_encoder_decoder(ED):
                 g_dec_out1=dec.output1.model[1].weight.grad.clone())
 
 
+def _ref_lines(rel, first, last):
+    """Source lines [first, last] (1-based) of a reference file with comment-only lines dropped, dedented."""
+    import textwrap
+    with open(os.path.join(REF, rel)) as f:
+        lines = f.read().split("\n")[first - 1:last]
+    lines = [ln for ln in lines if ln.strip() and not ln.strip().startswith("#")]
+    return textwrap.dedent("\n".join(lines))
+
+
+def _ref_dict(rel, name):
+    """The literal of ``self.<name> = {...}`` in a reference file, evaluated (ignore_label as the file defines it)."""
+    import re
+    src = open(os.path.join(REF, rel)).read()
+    ign = int(re.search(r"^ignore_label\s*=\s*(\d+)", src, re.M).group(1))
+    start = src.index("self.%s = {" % name) + len("self.%s = " % name)
+    end = src.index("}", start) + 1
+    return eval(src[start:end], {"ignore_label": ign})
+
+
+def make_input_pipeline():
+    """Runs the reference's OWN loader statements (new_multi/try_data.py:199-211 and :240-272,
+    datasets/dataset_synthia.py:172-175) on seeded arrays by executing the source lines read from /root/reference."""
+    import torchvision.transforms as transforms
+    rng = np.random.default_rng(77)
+    fx = {'depth': [], 'labels': {}}
+    depth_block = _ref_lines("new_multi/try_data.py", 240, 272)
+    cases = [rng.uniform(0, 65535, (24, 40)), rng.uniform(0, 9000, (24, 40)), rng.uniform(1500, 3500, (16, 16)),
+             np.full((8, 8), 1234.0), rng.uniform(4100, 4900, (8, 12)), rng.uniform(0, 900, (8, 12))]
+    for c in cases:
+        d = c.astype(np.float32)
+        ns = {'np': np, 'depth_source': d.copy()}
+        with np.errstate(all='ignore'):
+            exec(depth_block, ns)
+        fx['depth'].append(dict(depth=d, dep_l=ns['depth_source'], depth_l_s=ns['depth_labels']))
+    real_map = _ref_dict("new_multi/try_data.py", "real_id_to_trainid")
+    syn_map = _ref_dict("datasets/dataset_synthia.py", "syn_id_to_trainid")
+    lab = rng.integers(0, 40, (32, 48), dtype=np.uint8)
+    lab[0, :8] = np.arange(248, 256, dtype=np.uint8)
+
+    class _Self:
+        real_id_to_trainid = real_map
+        syn_id_to_trainid = syn_map
+    ns = {'np': np, 'self': _Self, 'lab_source': lab.copy(), 'lab_target': lab.copy()}
+    exec(_ref_lines("new_multi/try_data.py", 199, 211), ns)
+    fx['labels']['sequential'] = dict(lab=lab, mapping=real_map, zero_to=7, out=ns['lab_source'].astype(np.uint8),
+                                      out_target=ns['lab_target'].astype(np.uint8))
+    ns = {'np': np, 'self': _Self, 'lab_source': lab.copy()}
+    exec(_ref_lines("datasets/dataset_synthia.py", 172, 175), ns)
+    fx['labels']['masked'] = dict(lab=lab, mapping=syn_map, out=ns['lab_source_copy'].astype(np.uint8))
+    img = rng.integers(0, 256, (20, 28, 3), dtype=np.uint8)
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+    fx['normalize'] = dict(img=img, out=tf(img))
+    return fx
+
+
 def main():
     if not available():
         raise SystemExit("reference not found at %s" % REF)
@@ -194,6 +249,7 @@ def main():
     torch.save(make_networks5(N5), os.path.join(OUT, "networks5.pt"))
     ED = load_ref("ref_encoder_decoder", "models/encoder_decoder.py")
     torch.save(make_encoder_decoder(ED), os.path.join(OUT, "encoder_decoder.pt"))
+    torch.save(make_input_pipeline(), os.path.join(OUT, "input_pipeline.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
