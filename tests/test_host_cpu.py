@@ -137,3 +137,27 @@ def test_unet_levels_and_networks5_module_trees():
     assert sum(p.numel() for p in N5.R_dep().parameters()) == 52765086
     with __import__('pytest').raises(RuntimeError):
         N5.G_1()(__import__('torch').zeros(1, 3, 32, 32))     # CPU tensors are refused: no fallback path
+
+
+def test_error_convention_of_the_entry_points_added_for_the_next_rows():
+    """Null arguments / bad sizes are refused on the host side before anything touches a device (SURVEY 8(b) error
+    convention) for the TF32, f3 and f4 entry points."""
+    import ctypes as C
+    from cycle_depth_estimation_b200 import _lib
+    L = _lib.lib()
+    assert L.cdb_pack_conv_weight_tf32(None, 8, 8, 3, 3, 1, None, None) == -1 and b"null" in L.cdb_last_error()
+    assert L.cdb_round_tf32(None, C.c_int64(16), None) == -1
+    assert L.cdb_round_tf32(None, C.c_int64(0), None) == 0
+    assert L.cdb_scale(None, C.c_float(0.5), None, None) == -1
+    assert L.cdb_nearest2x_fwd(None, None, None) == -1 and L.cdb_nearest2x_bwd(None, None, None) == -1
+    assert L.cdb_tanh_fwd(None, None, None) == -1 and L.cdb_tanh_bwd(None, None, None, None) == -1
+    assert L.cdb_depth_labels_workspace(3) == 24 and L.cdb_depth_labels_workspace(0) == 0
+    assert L.cdb_depth_labels(None, 1, C.c_int64(16), None, None, None, C.c_size_t(0), None) == -1
+    assert L.cdb_label_lut_i64(None, C.c_int64(4), None, None, None) == -1
+    assert L.cdb_image_normalize_u8(None, 1, C.c_int64(4), 3, C.c_float(0.5), C.c_float(0.5), None, None) == -1
+    x = _lib.CdbAct(16, 1, 4, 4, 8, 128, 32, 8, _lib.BF16, 0)
+    y = _lib.CdbAct(16, 1, 4, 4, 16, 256, 64, 16, _lib.BF16, 0)
+    assert L.cdb_scale(C.byref(x), C.c_float(0.5), C.byref(y), None) == -1 and b"shapes" in L.cdb_last_error()
+    assert L.cdb_nearest2x_fwd(C.byref(x), C.byref(x), None) == -1
+    f = _lib.CdbAct(16, 1, 4, 4, 8, 128, 32, 8, _lib.F32, 0)
+    assert L.cdb_tanh_fwd(C.byref(f), C.byref(f), None) == -2          # fp32 views: unsupported, not a fallback
