@@ -520,6 +520,52 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
 constexpr int kFusedCluster = 8;
 constexpr int kFusedVecs = 8;  // pixel vectors per thread
 
+// add_folded_extras with 32-bit element offsets and without the dynamically indexed coordinate arrays (which live in
+// local memory): same mirrored positions, same order of additions.
+__device__ __forceinline__ void fold_extras_i32(const __nv_bfloat16* db, int dsh, int dsw, int h, int w, int H, int W,
+                                                int pad, float* g) {
+  constexpr int kNone = -(1 << 30);
+  const int h1 = (h >= 1 && h <= pad) ? -h : kNone;
+  const int h2 = (h <= H - 2 && h >= H - 1 - pad) ? 2 * (H - 1) - h : kNone;
+  const int w1 = (w >= 1 && w <= pad) ? -w : kNone;
+  const int w2 = (w <= W - 2 && w >= W - 1 - pad) ? 2 * (W - 1) - w : kNone;
+  auto acc = [&](int hh, int ww) {
+    if (hh == kNone || ww == kNone) return;
+    float t[8];
+    unpack8(ld16(db + hh * dsh + ww * dsw), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += t[j];
+  };
+  acc(h, w1);
+  acc(h, w2);
+  acc(h1, w);
+  acc(h1, w1);
+  acc(h1, w2);
+  acc(h2, w);
+  acc(h2, w1);
+  acc(h2, w2);
+}
+
+// (h, w) of the pixels p, p + 64, p + 128, ... of a W-wide image with ONE division per thread
+struct Walk64 {
+  int h, w, W, qstep, rstep;
+  __device__ __forceinline__ void init(int px, int W_) {
+    W = W_;
+    h = px / W_;
+    w = px - h * W_;
+    qstep = 64 / W_;
+    rstep = 64 - qstep * W_;
+  }
+  __device__ __forceinline__ void next() {
+    w += rstep;
+    h += qstep;
+    if (w >= W) {
+      w -= W;
+      ++h;
+    }
+  }
+};
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
                "l"(gsrc)
@@ -547,6 +593,14 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   const int pixels = p.H * p.W;
   const int p0 = rank * ppc, p1 = min(pixels, p0 + ppc);
   const int W = p.W, H = p.H, pad = p.pad;
+  // 32-bit element offsets inside one image (fused_in_eligible bounds H * stride) and a division-free pixel walk
+  const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
+  const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
+  const int ssh = static_cast<int>(p.dskip.sh), ssw = static_cast<int>(p.dskip.sw);
+  const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
+  const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
+  Walk64 first;
+  first.init(p0 + lane, W);
   const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
   const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
   const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
@@ -554,39 +608,41 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     // all 16 y / dout vectors of the thread go global -> shared memory (its private slots) without passing through
     // registers: 16 copies of 16 bytes in flight per thread = 64 KB per CTA from the first instruction on (the
     // per-channel coefficients are fetched behind them)
+    Walk64 pw = first;
 #pragma unroll
-    for (int u = 0; u < kFusedVecs; ++u) {
+    for (int u = 0; u < kFusedVecs; ++u, pw.next()) {
       const int px = p0 + lane + u * 64;
-      const int h = px / W, w = px - h * W;
       if (px < p1) {
-        cp_async16(&sy[u * 256 + threadIdx.x], yb + h * p.y.sh + w * p.y.sw);
-        if (p.has_dout) cp_async16(&sg[u * 256 + threadIdx.x], db + h * p.dout.sh + w * p.dout.sw);
+        cp_async16(&sy[u * 256 + threadIdx.x], yb + pw.h * ysh + pw.w * ysw);
+        if (p.has_dout) cp_async16(&sg[u * 256 + threadIdx.x], db + pw.h * dsh + pw.w * dsw);
       }
     }
   }
-  float mean[8], rstd[8];
+  float rstd[8], b1[8];   // xhat = y * rstd + b1, b1 = -mean * rstd
   {
-    float scale[8], shift[8];
+    float scale[8], shift[8], mean[8];
     norm_coeffs(p.norm, 0, p.stats, nullptr, nullptr, nullptr, nullptr, n, p.C, cvec * 8, p.inv_count, p.eps,
                 scale, shift, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b1[j] = -mean[j] * rstd[j];
   }
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   // two batches of four pixels: 8-12 independent 16-byte loads in flight per thread
+  Walk64 pl = first, pc = first;   // load and compute positions
 #pragma unroll
   for (int ub = 0; ub < kFusedVecs; ub += 4) {
     uint4 yr[4], gr[4], sr[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k, pl.next()) {
       const int px = p0 + lane + (ub + k) * 64;
-      const int h = px / W, w = px - h * W;
       if (px < p1) {
         if (!ASYNC) {
-          yr[k] = ld16(yb + h * p.y.sh + w * p.y.sw);
-          if (p.has_dout) gr[k] = ld16(db + h * p.dout.sh + w * p.dout.sw);
+          yr[k] = ld16(yb + pl.h * ysh + pl.w * ysw);
+          if (p.has_dout) gr[k] = ld16(db + pl.h * dsh + pl.w * dsw);
         }
-        if (p.has_dskip) sr[k] = ld16(sb + h * p.dskip.sh + w * p.dskip.sw);
+        if (p.has_dskip) sr[k] = ld16(sb + pl.h * ssh + pl.w * ssw);
       }
     }
     if (ASYNC) {
@@ -598,17 +654,18 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k, pc.next()) {
     const int u = ub + k;
     const int px = p0 + lane + u * 64;
     if (px >= p1) continue;
-    const int h = px / W, w = px - h * W;
+    const int h = pc.h, w = pc.w;
     float g[8], f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.f;
     if (p.has_dout) {
       unpack8(gr[k], g);
-      if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad)) add_folded_extras(p, db, h, w, g);
+      if (pad > 0 && (h <= pad || h >= H - 1 - pad || w <= pad || w >= W - 1 - pad))
+        fold_extras_i32(db, dsh, dsw, h, w, H, W, pad, g);
     }
     if (p.has_dskip) {
       float t[8];
@@ -621,12 +678,12 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     unpack8(yr[k], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xhat = (f[j] - mean[j]) * rstd[j];
+      const float xhat = fmaf(f[j], rstd[j], b1[j]);
       float ga = g[j];
       if (ACT == CDB_ACT_RELU) ga = xhat > 0.f ? ga : 0.f;
       else if (ACT == CDB_ACT_LEAKY) ga = xhat > 0.f ? ga : ga * p.slope;
       s1[j] += ga;
-      s2[j] += ga * xhat;
+      s2[j] = fmaf(ga, xhat, s2[j]);
     }
     }
   }
@@ -674,25 +731,26 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   // ---- apply from registers
   __nv_bfloat16* ob = p.dy.ptr + n * p.dy.sn + cvec * 8;
   __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
+  Walk64 pa = first;
 #pragma unroll
-  for (int u = 0; u < kFusedVecs; ++u) {
+  for (int u = 0; u < kFusedVecs; ++u, pa.next()) {
     const int px = p0 + lane + u * 64;
     if (px >= p1) continue;
-    const int h = px / W, w = px - h * W;
+    const int h = pa.h, w = pa.w;
     float g[8], f[8], o[8];
     const uint4 gv = sg[u * 256 + threadIdx.x];
     unpack8(gv, g);
     unpack8(sy[u * 256 + threadIdx.x], f);
-    if (gb != nullptr) st16(gb + h * p.gsum.sh + w * p.gsum.sw, gv);
+    if (gb != nullptr) st16(gb + h * gsh + w * gsw, gv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xhat = (f[j] - mean[j]) * rstd[j];
+      const float xhat = fmaf(f[j], rstd[j], b1[j]);
       float ga = g[j];
       if (ACT == CDB_ACT_RELU) ga = xhat > 0.f ? ga : 0.f;
       else if (ACT == CDB_ACT_LEAKY) ga = xhat > 0.f ? ga : ga * p.slope;
       o[j] = rstd[j] * (ga - m1[j] - xhat * m2[j]);
     }
-    st16(ob + h * p.dy.sh + w * p.dy.sw, pack8(o));
+    st16(ob + h * osh + w * osw, pack8(o));
   }
   cluster.sync();   // keeps every CTA's `part` alive until all ranks have read it (off the critical path)
 }
@@ -702,7 +760,10 @@ static bool fused_in_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool
   const int pixels = p.H * p.W;
   return d->norm == CDB_NORM_INSTANCE && !d->use_running && d->gamma == nullptr && d->beta == nullptr && !accum_f32 &&
          p.pre_act == CDB_ACT_NONE && p.C % 32 == 0 && pixels <= kFusedCluster * kFusedVecs * 64 && pixels >= 64 &&
-         p.y.sh < (1 << 28);
+         // 32-bit element offsets inside one image (mirrored halo rows included)
+         (int64_t)(p.H + 2 * p.pad) * p.y.sh < (1 << 30) && (int64_t)(p.H + 2 * p.pad) * p.dout.sh < (1 << 30) &&
+         (int64_t)(p.H + 2 * p.pad) * p.dskip.sh < (1 << 30) && (int64_t)(p.H + 2 * p.pad) * p.dy.sh < (1 << 30) &&
+         (int64_t)(p.H + 2 * p.pad) * p.gsum.sh < (1 << 30) && p.W <= 4096;
 }
 
 static void launch_norm_bwd_fused(const NormBwdParams& p, int n, cudaStream_t stream) {
