@@ -548,7 +548,15 @@ def secondary_arm(args):
     torch.manual_seed(0)
     random.seed(1234)
     wl = args.workload
-    sampler = ClockSampler(0)
+    mp_world, mp_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    mp_dist = None
+    if mp_world > 1:
+        if wl != "metrics":
+            raise SystemExit("--workload %s runs on one GPU (BatchNorm couples the batch); only the default CycleGAN "
+                             "workload and --workload metrics shard over ranks" % wl)
+        import torch.distributed as mp_dist
+        mp_dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     launches0 = lib.cdb_launch_count()
     extra = {}
     if wl == "pix2pix":
@@ -660,16 +668,25 @@ def secondary_arm(args):
         gt[rng.random((n_img, h, w)) < 0.3] = 0
         pred = rng.integers(0, 256, (n_img, h, w), dtype=np.uint8)
         hg, hp = torch.from_numpy(gt).pin_memory(), torch.from_numpy(pred).pin_memory()
-        dg, dp = hg.cuda(), hp.cuda()
+        # one process per GPU: rank r owns the images r, r + world, ... (strong scaling over the
+        # fixed 697 pairs); the device-resident figure is max-over-ranks of the shard's kernel time, the end-to-end
+        # figure goes through my_eval.eval_metric_arrays, which shards, all-gathers the 697 x 7 float32 rows and
+        # reduces them in image order on every rank
+        dg, dp = hg[mp_rank::mp_world].cuda(), hp[mp_rank::mp_world].cuda()
         from cycle_depth_estimation_b200 import ops
         ms = _time_steps(lambda: ops.depth_metrics(dg, dp), args.steps, args.warmup)
         ms_e2e = _time_steps(lambda: my_eval.eval_metric_arrays(hg, hp), args.steps, 1)
+        if mp_world > 1:
+            t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+            mp_dist.all_reduce(t, op=mp_dist.ReduceOp.MAX)
+            ms, ms_e2e = float(t[0]), float(t[1])
+            extra["parallelism"] = "images sharded round-robin over %d ranks, no data-path collective" % mp_world
         tflop = 0.0
         metric, unit = "depth_metrics_img_per_s", "images/s (375x1242 uint8 pairs, 7 metrics each)"
         workload = "my_eval.py depth metrics over 697 synthetic 375x1242 KITTI Eigen-split pairs (BASELINE configs[4])"
         h2d, d2h = int(2 * n_img * h * w), 697 * 8 * 8
         extra["images_per_step"] = n_img
-        extra["algorithmic_gb_per_s"] = 2.0 * n_img * h * w / (ms * 1e-3) / 1e9
+        extra["algorithmic_gb_per_s"] = 2.0 * (n_img / mp_world) * h * w / (ms * 1e-3) / 1e9   # per GPU (one launch)
         extra["frac_of_hbm_peak"] = extra["algorithmic_gb_per_s"] / peaks["hbm"]
     else:
         raise SystemExit("unknown workload " + wl)
@@ -694,10 +711,18 @@ def secondary_arm(args):
                 "kernel": "whole step (igemm_flat_kernel / igemm_kernel / wgrad_kernel dominate, "
                           "profiles/r01_step_kernels_*.txt)",
                 "peak_source": peaks["source"] + " (sustained)"}
-    cpu = None if args.no_cpu_baseline else secondary_cpu_baseline(wl, b if wl in ("pix2pix", "model5", "segcycle") else 1)
+    if mp_world > 1:
+        torch.cuda.synchronize()
+        mp_dist.barrier()
+        if mp_rank != 0:
+            mp_dist.destroy_process_group()
+            return
+    cpu = None if (args.no_cpu_baseline or mp_world > 1) else secondary_cpu_baseline(
+        wl, b if wl in ("pix2pix", "model5", "segcycle") else 1)
     line = {
-        "metric": metric, "value": per_step * 1e3 / ms, "unit": unit, "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": metric, "value": per_step * 1e3 / ms, "unit": unit, "n_gpus": mp_world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if mp_world > 1 else "weak", "vs_baseline": None,
         "dtype": "u8/f64" if wl == "metrics" else "bf16", "data": "synthetic",
         "config": dict({"workload": workload, "l2": "inputs + saved activations exceed the 126 MB L2; no explicit flush",
                         "algorithmic_tflop_per_step": tflop,
@@ -711,6 +736,8 @@ def secondary_arm(args):
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    if mp_world > 1:
+        mp_dist.destroy_process_group()
 
 
 def main():

@@ -42,13 +42,46 @@ def compute_errors(ground_truth, predication):
     return tuple(float(v) for v in r[:7])
 
 
-def eval_metric_arrays(gts, preds):
+def _sharded_per_image(gts, preds, per_image_fn):
+    """One process per GPU: rank r evaluates the images r, r + world, r + 2 world, ...; the float32
+    per-image rows are all-gathered and put back in image order, so that every rank then performs the reference's own
+    ordered float32 reduction (:108) and obtains bit-identical means whatever the number of GPUs.  No other
+    collective is involved: the images are independent."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = len(gts)
+    mine = list(range(rank, n, world))
+    rows = max((n + world - 1) // world, 1)
+    local = np.zeros((rows, 7), np.float32)
+    if mine:
+        sel = lambda a: a[mine] if (torch.is_tensor(a) or isinstance(a, np.ndarray)) else np.stack([a[i] for i in mine])
+        local[:len(mine)] = np.asarray(per_image_fn(sel(gts), sel(preds)))[:, :7].astype(np.float32)
+    dev = torch.device('cuda') if dist.get_backend() == 'nccl' else torch.device('cpu')
+    mine_t = torch.from_numpy(local).to(dev)
+    gathered = torch.empty((world * rows, 7), dtype=torch.float32, device=dev)   # concatenation form (gloo and nccl)
+    dist.all_gather_into_tensor(gathered, mine_t)
+    g = gathered.view(world, rows, 7).cpu().numpy()
+    per = np.empty((n, 7), np.float32)
+    for i in range(n):
+        per[i] = g[i % world, i // world]
+    return per
+
+
+def eval_metric_arrays(gts, preds, per_image_fn=None):
     """eval_metric (:35-108) on in-memory stacks of equal-sized uint8 images. Per-image results are
-    stored as float32 and reduced as ``float32_array.sum() / count`` like the reference (:37-43,:108)."""
-    per = per_image_errors(gts, preds)[:, :7]
+    stored as float32 and reduced as ``float32_array.sum() / count`` like the reference (:37-43,:108).
+    With ``torch.distributed`` initialised (one process per GPU) the images are sharded round-robin over the ranks
+    (``_sharded_per_image``); every rank returns the same means.  ``per_image_fn`` replaces the device evaluation
+    (tests of the sharding logic on CPU / gloo)."""
+    import torch.distributed as dist
+    fn = per_image_fn or per_image_errors
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        per = _sharded_per_image(gts, preds, fn)
+    else:
+        per = np.asarray(fn(gts, preds))[:, :7].astype(np.float32)
     n = per.shape[0]
     acc = np.zeros((max(n, 1000), 7), np.float32)
-    acc[:n] = per.astype(np.float32)
+    acc[:n] = per
     return tuple(acc[:, k].sum() / n for k in range(7)), acc[:n]
 
 

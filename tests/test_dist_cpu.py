@@ -75,6 +75,58 @@ def test_grad_buckets_and_replicated_pool_world2():
     assert ref.trace == res[0][3]
 
 
+def _metrics_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        from cycle_depth_estimation_b200 import my_eval
+        from oracle import networks_oracle as O
+        gts, preds = _metric_pairs()
+        calls = []
+
+        def per_image(g, p):       # the device evaluation replaced by the oracle: the test is about the sharding
+            calls.append(len(g))
+            rows = O.eval_metric_arrays(list(g), list(p))[1]
+            return np.concatenate([np.asarray(rows, np.float64), np.ones((len(g), 1))], 1)
+        means, per = my_eval.eval_metric_arrays(gts, preds, per_image_fn=per_image)
+        q.put((rank, [float(m) for m in means], per.tolist(), calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def _metric_pairs(n=7):
+    import numpy as np
+    rng = np.random.default_rng(2019)
+    gts = rng.integers(0, 80, (n, 24, 40), dtype=np.uint8)
+    preds = rng.integers(0, 256, (n, 24, 40), dtype=np.uint8)
+    return gts, preds
+
+
+def test_depth_metrics_shard_round_robin_world2():
+    """images split round-robin, float32 rows all-gathered back into image order, the reference's
+    ordered float32 reduction on every rank -> means bit-identical to the single-process evaluation (7 images over
+    2 ranks: uneven shards)."""
+    import numpy as np
+    from oracle import networks_oracle as O
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    gts, preds = _metric_pairs()
+    ref_means, ref_rows = O.eval_metric_arrays(list(gts), list(preds))
+    assert res[0][3] == [4] and res[1][3] == [3]              # images 0,2,4,6 / 1,3,5
+    for r in res:
+        assert np.array_equal(np.asarray(r[2], np.float32), np.asarray(ref_rows, np.float32))
+        assert [np.float32(m) for m in r[1]] == [np.float32(m) for m in ref_means]
+
+
 def test_no_distributed_is_a_noop():
     from cycle_depth_estimation_b200.cycle_gan_model import GradBuckets
     p = torch.nn.Parameter(torch.zeros(4))
