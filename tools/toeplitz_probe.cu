@@ -1,5 +1,6 @@
-// Probe for round 2 (written in round 1, NOT yet run on hardware): can tcgen05 read the im2col ("Toeplitz") operand of
-// a few-channel convolution row straight from a CONTIGUOUS shared-memory copy of the input pixels?
+// Probe (round 1, verified on B200: relative L2 error 5.3e-8 with LBO = 16 B / SBO = 128 B, 1.4 with the two swapped —
+// profiles/r01_toeplitz_probe.txt): tcgen05 CAN read the im2col ("Toeplitz") operand of a few-channel convolution row
+// straight from a CONTIGUOUS shared-memory copy of the input pixels.
 //
 // Today the image layers (c7s1-64: 3 -> 64 channels, 7x7) use the row-packed operand: pixel q of the A tile is the
 // 128-byte window [16 q, 16 q + 128) of the input row (8 pixels x 8 bf16 channels), fetched by TMA as 128 overlapping
