@@ -8,6 +8,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/bin/toeplitz_conv_bench tools/toeplitz_conv_bench.cu
 //   tools/bin/toeplitz_conv_bench [batch]
+// -DSTAGED_STORE builds the variant with a coalesced (shared-memory staged) epilogue (written after the measured run).
 // Prints the error against a host evaluation on sampled outputs, the error of the statistics, and the time per launch.
 #include <cmath>
 #include <cstdio>
@@ -29,7 +30,8 @@ constexpr int kStageBytes = 15360;                                        // 7 x
 constexpr int kStages = 4;
 constexpr int kWBytes = kR * kCout * kTaps * kCh * 2;                     // 7 x 8 KB
 constexpr int kSlabBytes = 4 * 32 * 17 * 4;                               // epilogue transposes (4 warps)
-constexpr int kSmem = kWBytes + kStages * kStageBytes + kSlabBytes + 1024;
+constexpr int kStoreStageBytes = 4 * 4096;                                // -DSTAGED_STORE: 32 x 128 B per epilogue warp
+constexpr int kSmem = kWBytes + kStages * kStageBytes + kSlabBytes + kStoreStageBytes + 1024;
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -50,6 +52,8 @@ toeplitz_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w_base = base, st_base = base + kWBytes;
   float* slab_all = reinterpret_cast<float*>(gen + kWBytes + kStages * kStageBytes);
+  uint8_t* stage_all = gen + kWBytes + kStages * kStageBytes + kSlabBytes;   // 16-byte aligned (all sizes are)
+  (void)stage_all;
   const int total_tiles = n_img * kH * (kW / kBM);
 
   for (int i = threadIdx.x; i < kWBytes / 16; i += blockDim.x)
@@ -160,6 +164,32 @@ toeplitz_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[buf]));   // the accumulator is in registers: the next tile may overwrite it
+#ifdef STAGED_STORE
+      // (not yet run on hardware) the warp's 32 pixels x 128 B go through a swizzled staging tile so that every store
+      // instruction writes 512 contiguous bytes (4 pixels) instead of 32 separate 16-byte pieces
+      {
+        uint4* stg = reinterpret_cast<uint4*>(stage_all + ew * 4096);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[j * 8 + 0]), __uint_as_float(v[j * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[j * 8 + 2]), __uint_as_float(v[j * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[j * 8 + 4]), __uint_as_float(v[j * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
+          stg[lane * 8 + (j ^ (lane & 7))] = o;          // row `lane`, 16-byte chunk j at position j ^ (row & 7)
+        }
+        __syncwarp();
+        uint4* dst4 = reinterpret_cast<uint4*>(
+            y + ((static_cast<int64_t>(img) * kH + p) * kW + half * kBM + ew * 32) * kCout);
+        const int c = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = (lane >> 3) + 4 * i;
+          dst4[row * 8 + c] = stg[row * 8 + (c ^ (row & 7))];
+        }
+        __syncwarp();
+      }
+#else
       const int q = half * kBM + ew * 32 + lane;
       __nv_bfloat16* dst = y + ((static_cast<int64_t>(img) * kH + p) * kW + q) * kCout;
 #pragma unroll
@@ -171,6 +201,7 @@ toeplitz_conv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
         o.w = pack_bf16x2(__uint_as_float(v[j * 8 + 6]), __uint_as_float(v[j * 8 + 7]));
         reinterpret_cast<uint4*>(dst)[j] = o;
       }
+#endif
       if (img != cur_img) {
         flush();
         cur_img = img;
