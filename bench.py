@@ -4,8 +4,11 @@ cycle + identity losses, ImagePool 50, Adam, 4 D updates per G update) at batch 
 kernels of this repo.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload cyclegan|g_infer|pix2pix|model5|metrics|segcycle] [--no-cuda-graph] [--no-batch-passes]
 
-One JSON line on stdout (rank 0). See DESIGN.md "measurement" for the definition of every field.
+One JSON line on stdout (rank 0). See DESIGN.md "measurement" for the definition of every field.  The default
+workload (the headline metric) shards the batch over N ranks under torchrun; `--workload metrics` shards the 697
+image pairs; the other workloads run on one GPU.
 """
 import argparse
 import json
