@@ -228,6 +228,117 @@ def time_tf32_kernel(iters=20):
             "frac_of_nominal_tf32_peak": tf / 1100.0, "peak_source": "nominal dense TF32 1.1 PFLOP/s (fallback)"}
 
 
+def cudnn_same_box(batch, size, steps=3, warmup=2):
+    """The bar SURVEY 2.3 / BASELINE.md 3 name: the SAME training step through stock PyTorch on this GPU — the
+    oracle restatement of models/cycle_gan_model.py:80-160 around torch.nn.functional, i.e. cuDNN convolutions and
+    ATen norm / loss / Adam kernels — timed with CUDA events in this run, (a) fp32 with TF32 allowed (PyTorch's
+    default for convolutions on this hardware), (b) torch.autocast(bfloat16) with channels_last tensors.  The oracle is
+    used here as a timed baseline only; nothing of it is on the B200 path."""
+    import contextlib
+    import io
+    import random
+    from oracle import networks_oracle as O
+    from cycle_depth_estimation_b200 import networks as N
+    out = {}
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        nets = [N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+        nets += [N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cpu']) for _ in range(2)]
+    sds = [{k: v.cuda() for k, v in n.state_dict().items()} for n in nets]
+    a, b = synthetic_batch(batch, size, 1234)
+    a, b = a.cuda(), b.cuda()
+    old_bench, old_tf32 = torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name in ("ms_fp32_tf32", "ms_bf16_autocast"):
+            random.seed(1234)
+            oracle = O.CycleGANStepOracle(*sds)
+            xa, xb = a, b
+            if name == "ms_bf16_autocast":
+                xa = a.contiguous(memory_format=torch.channels_last)
+                xb = b.contiguous(memory_format=torch.channels_last)
+                for sd in (oracle.G_A, oracle.G_B, oracle.D_A, oracle.D_B):
+                    for v in sd.values():
+                        if v.dim() == 4:
+                            v.data = v.data.contiguous(memory_format=torch.channels_last)
+                ctx = torch.autocast("cuda", dtype=torch.bfloat16)
+            else:
+                torch.backends.cudnn.allow_tf32 = True
+                ctx = contextlib.nullcontext()
+            with ctx:
+                for _ in range(warmup):
+                    oracle.step(xa, xb)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    oracle.step(xa, xb)
+                e1.record()
+                torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / steps
+            del oracle
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = old_bench, old_tf32
+    out["how"] = ("oracle.CycleGANStepOracle (torch.nn.functional / cuDNN %s, torch %s) on cuda:0, same weights shape, "
+                  "inputs and step definition, %d warm-up + %d timed steps, CUDA events; cudnn.benchmark on; each "
+                  "oracle step also reads its losses back (8 floats)" % (torch.backends.cudnn.version(), torch.__version__,
+                                                                       warmup, steps))
+    return out
+
+
+def time_g_inference(batch, size=256, iters=30):
+    """BASELINE configs[0] through the TestModel mirror (models/test_model.py:33-46): eager launches and CUDA-graph
+    replay of the forward pass, device-resident input. Returns ms per forward for both."""
+    import contextlib
+    import io
+    from cycle_depth_estimation_b200.test_model import TestModel
+    res = {}
+    a, _ = synthetic_batch(batch, size, 1234)
+    dev = {'A': a.cuda(), 'A_paths': None}
+    for mode in ("eager", "graph"):
+        opt = make_opt("cuda", mode == "graph")
+        opt.isTrain = False
+        torch.manual_seed(0)
+        m = TestModel()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.initialize(opt)
+        m.eval()
+        for _ in range(4):
+            m.set_input(dev)
+            m.test()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            m.set_input(dev)
+            m.test()
+        e1.record()
+        torch.cuda.synchronize()
+        res[mode] = e0.elapsed_time(e1) / iters
+        del m
+    return res
+
+
+def run_secondary_lines(steps=5):
+    """The other BASELINE configs as sub-runs of this bench (one process each, this GPU), so that their numbers are
+    recorded with the headline line instead of being builder-only claims."""
+    out = []
+    for wl in ("g_infer", "pix2pix", "model5", "metrics"):
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", str(steps), "--warmup", "3",
+               "--no-cpu-baseline"]
+        try:
+            proc = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            line = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
+            out.append({"workload": wl, "metric": line["metric"], "value": line["value"], "unit": line["unit"],
+                        "ms_per_step": line["ms_per_step"], "e2e_value": line["e2e"]["value"],
+                        "roofline_frac": line["roofline"]["frac"], "roofline_bound": line["roofline"]["bound"],
+                        "gpu_launches": line["gpu_launches"]})
+        except Exception as exc:  # noqa: BLE001
+            out.append({"workload": wl, "error": "%s: %s" % (type(exc).__name__, exc)})
+    return out
+
+
 def b200_arm(args):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,6 +358,11 @@ def b200_arm(args):
     lib = _lib.lib()
     peaks = load_peaks()
     batch, size = args.batch, args.size
+    if args.scaling == "strong":
+        # north_star: "the batch sharded" — the GLOBAL batch stays at --batch, every rank takes batch / world samples
+        if batch % world:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of ranks")
+        batch //= world
     torch.manual_seed(0)            # identical initial weights on every rank
     random.seed(1234)               # identical ImagePool stream on every rank
     host_a, host_b = synthetic_batch(batch, size, 1234 + rank)
@@ -318,7 +434,7 @@ def b200_arm(args):
         launches = int(getattr(model, "_graph_launches", 0)) * args.steps
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
-    value = world * 1e3 / ms_step * (batch / 8.0)
+    value = world * 1e3 / ms_step * (batch / 8.0)   # batch-8 steps per second over all ranks
 
     # ---- end to end: pinned host inputs every step, losses read back every step
     host = {"img_source": host_a, "img_target": host_b}
@@ -356,17 +472,9 @@ def b200_arm(args):
         finish()
         return
     # ---- generator inference (BASELINE configs[0]) and the dominant kernel, rank 0 only
-    with torch.no_grad():
-        x1 = dev["img_source"][:1]
-        for _ in range(3):
-            model.netG_A(x1)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(20):
-            model.netG_A(x1)
-        e1.record()
-        torch.cuda.synchronize()
-        g_ms = e0.elapsed_time(e1) / 20
+    del model
+    torch.cuda.empty_cache()
+    g1, g8 = time_g_inference(1), time_g_inference(8)
     roof = time_dominant_kernel(peaks)
     tf32 = time_tf32_kernel()
     step_tflops = TFLOP_PER_SAMPLE * batch / (ms_step * 1e-3)
@@ -376,7 +484,7 @@ def b200_arm(args):
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": "CycleGAN training step: G_A/G_B resnet_9blocks + D_A/D_B 70x70 PatchGAN, LSGAN + L1 "
@@ -389,8 +497,12 @@ def b200_arm(args):
             "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * batch,
             "step_tflops_per_gpu": step_tflops,
             "step_frac_of_sustained_bf16_peak": step_tflops / peaks["bf16_sustained"],
-            "g_forward_img_per_s_batch1": 1e3 / g_ms,
-            "g_forward_tflops_batch1": G_FWD_GFLOP / g_ms,
+            "g_forward_img_per_s_batch1": 1e3 / g1["graph"],
+            "g_forward_tflops_batch1": G_FWD_GFLOP / g1["graph"],
+            "g_forward_ms": {"batch1_eager": g1["eager"], "batch1_graph_replay": g1["graph"],
+                             "batch8_eager": g8["eager"], "batch8_graph_replay": g8["graph"]},
+            "g_forward_img_per_s_batch8": 8e3 / g8["graph"],
+            "g_forward_tflops_batch8": 8 * G_FWD_GFLOP / g8["graph"],
             "tf32_variant_r256_conv": tf32,
             "device_abort_flag": abort,
         },
@@ -398,6 +510,17 @@ def b200_arm(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if world == 1 and not args.no_cudnn_baseline:
+        try:
+            cd = cudnn_same_box(batch, size)
+            cd["speedup_vs_fp32_tf32"] = cd["ms_fp32_tf32"] / ms_step
+            cd["speedup_vs_bf16_autocast"] = cd["ms_bf16_autocast"] / ms_step
+        except Exception as exc:  # noqa: BLE001
+            cd = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        line["config"]["cudnn_same_box"] = cd
+    if world == 1 and args.secondary:
+        torch.cuda.empty_cache()
+        line["secondary"] = run_secondary_lines()
     print(json.dumps(line), flush=True)
     finish()
 
@@ -752,6 +875,12 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cudnn-baseline", action="store_true",
+                    help="skip config.cudnn_same_box (the stock-PyTorch / cuDNN step timed on this GPU)")
+    ap.add_argument("--secondary", action="store_true",
+                    help="also run the other BASELINE configs as sub-runs and attach their lines as `secondary`")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch per GPU (default); strong: --batch is the global batch, sharded over the ranks")
     ap.add_argument("--no-cuda-graph", action="store_true", help="eager launches instead of replaying the captured step")
     ap.add_argument("--no-batch-passes", action="store_true",
                     help="run every generator / discriminator pass separately (6 + 2 per update) instead of batching "

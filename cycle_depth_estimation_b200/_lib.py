@@ -39,12 +39,18 @@ class CdbNormDesc(C.Structure):
                 ("channels", C.c_int32), ("pad", C.c_int32), ("use_running", C.c_int32),
                 ("update_running", C.c_int32), ("momentum", C.c_float), ("flags", C.c_int32),
                 ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-                ("running_mean", C.c_void_p), ("running_var", C.c_void_p)]
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("conv_bias", C.c_void_p)]
 
 
 class CdbAdamEntry(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("numel", C.c_int64)]
+
+
+class CdbAdamPackEntry(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("pack", C.c_void_p * 2), ("d0", C.c_int32), ("d1", C.c_int32), ("r", C.c_int32),
+                ("s", C.c_int32), ("rows_are_dim0", C.c_int32 * 2), ("rowpack", C.c_int32 * 2)]
 
 
 class CdbPackEntry(C.Structure):

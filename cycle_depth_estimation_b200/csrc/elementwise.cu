@@ -27,12 +27,13 @@ struct ToNhwcParams {
   const float* src;
   const float* act_out;
   int64_t s_n, s_c, s_h, s_w;
-  __nv_bfloat16* out;
+  void* out;               // bf16 or fp32 (fp32-storage network modes) NHWC interior
   int64_t o_n, o_h, o_w;
   int N, C, H, W, cs, pad, act;
   float slope;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(ToNhwcParams p) {
   const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(ToNhwcParams p) {
     const int h = (idx / p.W) % p.H;
     const int n = idx / (static_cast<int64_t>(p.W) * p.H);
     const int64_t sbase = n * p.s_n + h * p.s_h + w * p.s_w;
-    __nv_bfloat16* ob = p.out + n * p.o_n;
+    T* ob = static_cast<T*>(p.out) + n * p.o_n;
     for (int c0 = 0; c0 < p.cs; c0 += 8) {
       float f[8];
 #pragma unroll
@@ -75,8 +76,15 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(ToNhwcParams p) {
         if (w <= p.W - 2 && w >= p.W - 1 - p.pad) ww[nw++] = 2 * (p.W - 1) - w;
       }
       for (int a = 0; a < nh; ++a)
-        for (int b = 0; b < nw; ++b)
-          *reinterpret_cast<uint4*>(ob + hh[a] * p.o_h + ww[b] * p.o_w + c0) = pk;
+        for (int b = 0; b < nw; ++b) {
+          T* dst = ob + hh[a] * p.o_h + ww[b] * p.o_w + c0;
+          if constexpr (sizeof(T) == 2) {
+            *reinterpret_cast<uint4*>(dst) = pk;
+          } else {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
     }
   }
 }
@@ -236,13 +244,30 @@ __global__ void pool_apply_kernel(const float* __restrict__ fake, float* __restr
 // Multi-tensor Adam: up to kAdamMaxEntries parameter tensors per launch, their pointers passed in the (large,
 // __grid_constant__) kernel parameter block — no pointer table in device memory, so the launch is valid in a
 // CUDA graph as is. Block b finds its (tensor, chunk) by binary search over the cumulative chunk counts.
-constexpr int kAdamMaxEntries = 384;
+// an entry may name up to two packed bf16 GEMM operands of its filter (the forward and the
+// data-gradient layout the convolution kernels read); the kernel then writes the updated value into them as
+// well, so that no separate re-pack pass runs after the optimizer step.
+constexpr int kAdamMaxEntries = 256;
 constexpr int kAdamChunk = 16384;
+struct AdamPackDev {
+  __nv_bfloat16* out;
+  int32_t rows_are_dim0, rowpack, kpad, n_taps;
+};
+struct AdamEntryDev {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  AdamPackDev pack[2];
+  int32_t d1, R, S, pad_;
+};
 struct AdamMultiParams {
   int32_t n_entries, step;
   float lr, b1, b2, eps;
   const int32_t* step_dev;
-  CdbAdamEntry e[kAdamMaxEntries];
+  const float* lr_dev;
+  AdamEntryDev e[kAdamMaxEntries];
   int32_t cum[kAdamMaxEntries + 1];
 };
 
@@ -253,7 +278,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     if (q.cum[mid] <= static_cast<int>(blockIdx.x)) lo = mid;
     else hi = mid;
   }
-  const CdbAdamEntry& en = q.e[lo];
+  const AdamEntryDev& en = q.e[lo];
   const int64_t begin = static_cast<int64_t>(blockIdx.x - q.cum[lo]) * kAdamChunk;
   const int64_t end = begin + kAdamChunk < en.numel ? begin + kAdamChunk : en.numel;
   float bc1, bc2_sqrt;
@@ -265,18 +290,41 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
     bc1 = static_cast<float>(1.0 - pow(static_cast<double>(q.b1), static_cast<double>(q.step)));
     bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(q.b2), static_cast<double>(q.step))));
   }
-  const float step_size = q.lr / bc1;
+  const float lr = q.lr_dev != nullptr ? *q.lr_dev : q.lr;   // device-resident learning rate: schedulers act on replays
+  const float step_size = lr / bc1;
   float* __restrict__ p = en.param;
   const float* __restrict__ g = en.grad;
   float* __restrict__ m = en.exp_avg;
   float* __restrict__ v = en.exp_avg_sq;
+  const bool packs = en.pack[0].out != nullptr || en.pack[1].out != nullptr;
+  const int rs = en.R * en.S;
   for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
     const float gi = g[i];
     const float mi = m[i] + (1.f - q.b1) * (gi - m[i]);
     const float vi = q.b2 * v[i] + (1.f - q.b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + q.eps));
+    const float pn = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + q.eps));
+    p[i] = pn;
+    if (packs) {
+      // element (i0, i1, r, s) of the filter [d0][d1][R][S] -> packed[row][tap * kpad + k] (pack_weight_kernel's map)
+      const int ii = static_cast<int>(i);
+      const int tap_rs = ii % rs;
+      const int i01 = ii / rs;
+      const int i1 = i01 % en.d1, i0 = i01 / en.d1;
+      const int r = tap_rs / en.S, sc = tap_rs - r * en.S;
+      const __nv_bfloat16 b = __float2bfloat16(pn);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const AdamPackDev& pk = en.pack[t];
+        if (pk.out == nullptr) continue;
+        const int row = pk.rows_are_dim0 ? i0 : i1;
+        const int k = pk.rows_are_dim0 ? i1 : i0;
+        const int tap = pk.rowpack ? r : tap_rs;
+        const int kk = pk.rowpack ? sc * pk.rowpack + k : k;
+        pk.out[(static_cast<int64_t>(row) * pk.n_taps + tap) * pk.kpad + kk] = b;
+      }
+    }
   }
 }
 
@@ -297,7 +345,8 @@ extern "C" int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t 
                                 float slope, const CdbAct* out, int32_t pad, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(src && out && out->ptr, CDB_ERR_BAD_DESC, "nchw_to_nhwc: null argument");
-  CDB_REQUIRE(out->dtype == CDB_BF16 && out->c % 8 == 0 && out->c >= c, CDB_ERR_BAD_DESC, "nchw_to_nhwc: out channels");
+  CDB_REQUIRE((out->dtype == CDB_BF16 || out->dtype == CDB_F32) && out->c % 8 == 0 && out->c >= c, CDB_ERR_BAD_DESC,
+              "nchw_to_nhwc: out channels");
   CDB_REQUIRE(out->n == n && out->h == h && out->w == w, CDB_ERR_BAD_DESC, "nchw_to_nhwc: out must be the interior view");
   CDB_REQUIRE(out->sn % 8 == 0 && out->sh % 8 == 0 && out->sw % 8 == 0 && (reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0,
               CDB_ERR_ALIGNMENT, "nchw_to_nhwc: alignment");
@@ -309,7 +358,7 @@ extern "C" int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t 
   p.s_c = s_c;
   p.s_h = s_h;
   p.s_w = s_w;
-  p.out = static_cast<__nv_bfloat16*>(out->ptr);
+  p.out = out->ptr;
   p.o_n = out->sn;
   p.o_h = out->sh;
   p.o_w = out->sw;
@@ -321,7 +370,8 @@ extern "C" int cdb_nchw_to_nhwc(const float* src, int32_t n, int32_t c, int32_t 
   p.pad = pad;
   p.act = act;
   p.slope = slope;
-  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * h * w, 1), 256, 0, stream>>>(p);
+  if (out->dtype == CDB_F32) nchw_to_nhwc_kernel<float><<<grid_for((int64_t)n * h * w, 1), 256, 0, stream>>>(p);
+  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for((int64_t)n * h * w, 1), 256, 0, stream>>>(p);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
@@ -416,10 +466,10 @@ extern "C" int cdb_image_pool_apply(const float* fake, float* pool, const int32_
   return CDB_OK;
 }
 
-extern "C" int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entries, float lr, float beta1, float beta2,
-                              float eps, int32_t step, const int32_t* step_dev, cdbStream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CDB_REQUIRE(entries_host && n_entries > 0 && (step >= 1 || step_dev), CDB_ERR_BAD_DESC, "adam_multi: bad argument");
+static int adam_multi_launch(const CdbAdamEntry* plain, const CdbAdamPackEntry* packed, int32_t n_entries, float lr,
+                             const float* lr_dev, float beta1, float beta2, float eps, int32_t step,
+                             const int32_t* step_dev, cudaStream_t stream) {
+  CDB_REQUIRE((plain || packed) && n_entries > 0 && (step >= 1 || step_dev), CDB_ERR_BAD_DESC, "adam_multi: bad argument");
   static thread_local AdamMultiParams q;
   for (int base = 0; base < n_entries; base += kAdamMaxEntries) {
     const int n = n_entries - base < kAdamMaxEntries ? n_entries - base : kAdamMaxEntries;
@@ -430,18 +480,60 @@ extern "C" int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entrie
     q.b2 = beta2;
     q.eps = eps;
     q.step_dev = step_dev;
+    q.lr_dev = lr_dev;
     int blocks = 0;
     for (int i = 0; i < n; ++i) {
-      const CdbAdamEntry& en = entries_host[base + i];
-      CDB_REQUIRE(en.param && en.grad && en.exp_avg && en.exp_avg_sq && en.numel > 0, CDB_ERR_BAD_DESC,
+      AdamEntryDev& d = q.e[i];
+      memset(&d, 0, sizeof(d));
+      if (plain) {
+        const CdbAdamEntry& en = plain[base + i];
+        d.param = en.param, d.grad = en.grad, d.exp_avg = en.exp_avg, d.exp_avg_sq = en.exp_avg_sq, d.numel = en.numel;
+      } else {
+        const CdbAdamPackEntry& en = packed[base + i];
+        d.param = en.param, d.grad = en.grad, d.exp_avg = en.exp_avg, d.exp_avg_sq = en.exp_avg_sq, d.numel = en.numel;
+        d.d1 = en.d1, d.R = en.r, d.S = en.s;
+        for (int t = 0; t < 2; ++t) {
+          if (!en.pack[t]) continue;
+          CDB_REQUIRE(en.d0 >= 1 && en.d1 >= 1 && en.r >= 1 && en.s >= 1 &&
+                          (int64_t)en.d0 * en.d1 * en.r * en.s == en.numel && en.numel < (1ll << 31),
+                      CDB_ERR_BAD_DESC, "adam_pack_multi: filter geometry of entry %d", base + i);
+          const int kdim = en.rows_are_dim0[t] ? en.d1 : en.d0;
+          AdamPackDev& pk = d.pack[t];
+          pk.out = static_cast<__nv_bfloat16*>(en.pack[t]);
+          pk.rows_are_dim0 = en.rows_are_dim0[t];
+          pk.rowpack = en.rowpack[t];
+          if (pk.rowpack) {
+            CDB_REQUIRE(en.s * pk.rowpack <= 64 && kdim <= pk.rowpack, CDB_ERR_BAD_DESC,
+                        "adam_pack_multi: rowpack geometry of entry %d", base + i);
+            pk.kpad = 64;
+            pk.n_taps = en.r;
+          } else {
+            pk.kpad = round_up(kdim, 64);
+            pk.n_taps = en.r * en.s;
+          }
+        }
+      }
+      CDB_REQUIRE(d.param && d.grad && d.exp_avg && d.exp_avg_sq && d.numel > 0, CDB_ERR_BAD_DESC,
                   "adam_multi: bad entry %d", base + i);
-      q.e[i] = en;
       q.cum[i] = blocks;
-      blocks += (int)((en.numel + kAdamChunk - 1) / kAdamChunk);
+      blocks += (int)((d.numel + kAdamChunk - 1) / kAdamChunk);
     }
     q.cum[n] = blocks;
     adam_multi_kernel<<<blocks, 256, 0, stream>>>(q);
     CDB_LAUNCH_OK();
   }
   return CDB_OK;
+}
+
+extern "C" int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entries, float lr, float beta1, float beta2,
+                              float eps, int32_t step, const int32_t* step_dev, cdbStream_t stream_) {
+  return adam_multi_launch(entries_host, nullptr, n_entries, lr, nullptr, beta1, beta2, eps, step, step_dev,
+                           static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int cdb_adam_pack_multi(const CdbAdamPackEntry* entries_host, int32_t n_entries, float lr,
+                                   const float* lr_dev, float beta1, float beta2, float eps, int32_t step,
+                                   const int32_t* step_dev, cdbStream_t stream_) {
+  return adam_multi_launch(nullptr, entries_host, n_entries, lr, lr_dev, beta1, beta2, eps, step, step_dev,
+                           static_cast<cudaStream_t>(stream_));
 }

@@ -11,22 +11,35 @@
 
 namespace cdb {
 
-struct View {  // NHWC view, channel stride 1
-  __nv_bfloat16* ptr;
+// Storage type of the activations: bf16 (the default network mode) or fp32 (the TF32 / error-compensated TF32
+// network modes, whose convolutions read fp32 operands).  All kernels of this file are templates over it; the
+// arithmetic is fp32 in both cases, only the 8-channel vector load / store differs (16 B vs 2 x 16 B).
+struct View {  // NHWC view, channel stride 1; ptr is T* of the kernel's storage type
+  void* ptr;
   int64_t sn, sh, sw;
 };
 
 static inline View view_of(const CdbAct* a) {
   View v;
-  v.ptr = a ? static_cast<__nv_bfloat16*>(a->ptr) : nullptr;
+  v.ptr = a ? a->ptr : nullptr;
   v.sn = a ? a->sn : 0;
   v.sh = a ? a->sh : 0;
   v.sw = a ? a->sw : 0;
   return v;
 }
 
-struct Bf8 {
-  uint4 raw;
+struct F8 {  // eight fp32 channels
+  float4 a, b;
+};
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<__nv_bfloat16> {
+  typedef uint4 type;
+};
+template <>
+struct Vec8<float> {
+  typedef F8 type;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
@@ -38,15 +51,39 @@ __device__ __forceinline__ void unpack8(const uint4& r, float* f) {
     f[2 * i + 1] = t.y;
   }
 }
-__device__ __forceinline__ uint4 pack8(const float* f) {
+__device__ __forceinline__ void unpack8(const F8& r, float* f) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w;
+  f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+template <typename T>
+__device__ __forceinline__ typename Vec8<T>::type pack8(const float* f);
+template <>
+__device__ __forceinline__ uint4 pack8<__nv_bfloat16>(const float* f) {
   uint4 r;
   __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&r);
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return r;
 }
+template <>
+__device__ __forceinline__ F8 pack8<float>(const float* f) {
+  F8 r;
+  r.a = make_float4(f[0], f[1], f[2], f[3]);
+  r.b = make_float4(f[4], f[5], f[6], f[7]);
+  return r;
+}
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ F8 ld16(const float* p) {
+  F8 r;
+  r.a = reinterpret_cast<const float4*>(p)[0];
+  r.b = reinterpret_cast<const float4*>(p)[1];
+  return r;
+}
+__device__ __forceinline__ void st16(float* p, const F8& v) {
+  reinterpret_cast<float4*>(p)[0] = v.a;
+  reinterpret_cast<float4*>(p)[1] = v.b;
+}
 
 // Walks pixels p0+lane, p0+lane+lanes, ... of a W-wide image keeping (h, w) without divisions.
 struct PixelWalk {
@@ -93,6 +130,7 @@ static int chunks_for(int pixels, int lanes, int n, int cv_tiles, int per_sm_def
 // ------------------------------------------------------------------------------------------------
 // statistics: stats[g][c][2] += (sum, sum of squares), g = image (instance) or 0 (batch)
 // ------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256)
 channel_stats_kernel(View y, int H, int W, int C, int vt, int per_image, float* __restrict__ stats) {
   __shared__ float red[256 * 16];
@@ -108,7 +146,7 @@ channel_stats_kernel(View y, int H, int W, int C, int vt, int per_image, float* 
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   const bool active = cvec * 8 < C;
   if (active) {
-    const __nv_bfloat16* base = y.ptr + n * y.sn + cvec * 8;
+    const T* base = static_cast<const T*>(y.ptr) + n * y.sn + cvec * 8;
     PixelWalk pw;
     pw.init(p0 + lane, W);
     const int ysh = static_cast<int>(y.sh), ysw = static_cast<int>(y.sw);
@@ -210,8 +248,9 @@ __device__ __forceinline__ float act_fwd_t(float v, float slope) {
   return v;
 }
 
-__device__ __forceinline__ void write_halo(__nv_bfloat16* ob, int osh, int osw, int h, int w, int H, int W,
-                                           int pad, const uint4& o) {
+template <typename T>
+__device__ __forceinline__ void write_halo(T* ob, int osh, int osw, int h, int w, int H, int W,
+                                           int pad, const typename Vec8<T>::type& o) {
   // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
   int hh[2], ww[2];
   int nh = 0, nw = 0;
@@ -225,8 +264,9 @@ __device__ __forceinline__ void write_halo(__nv_bfloat16* ob, int osh, int osw, 
     for (int b = 0; b < nw; ++b) st16(ob + hh[a] * osh + ww[b] * osw, o);
 }
 
-template <int ACT, bool HAS_RES>
+template <typename T, int ACT, bool HAS_RES>
 __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(NormFwdParams p) {
+  typedef typename Vec8<T>::type V8;
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
   const int cvec = blockIdx.z * p.vt + v;
   if (cvec * 8 >= p.C) return;
@@ -236,21 +276,21 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(NormFwdParams p) {
   float scale[8], shift[8];
   norm_coeffs(p.norm, p.use_running, p.stats, p.gamma, p.beta, p.running_mean, p.running_var,
               p.per_image ? n : 0, p.C, cvec * 8, p.inv_count, p.eps, scale, shift, nullptr, nullptr);
-  const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
-  const __nv_bfloat16* rb = HAS_RES ? p.res.ptr + n * p.res.sn + cvec * 8 : nullptr;
-  __nv_bfloat16* ob = p.out.ptr + n * p.out.sn + cvec * 8;
+  const T* yb = static_cast<const T*>(p.y.ptr) + n * p.y.sn + cvec * 8;
+  const T* rb = HAS_RES ? static_cast<const T*>(p.res.ptr) + n * p.res.sn + cvec * 8 : nullptr;
+  T* ob = static_cast<T*>(p.out.ptr) + n * p.out.sn + cvec * 8;
   const int pad = p.pad, H = p.H, W = p.W;
   const float slope = p.slope;
-  constexpr int U = 4;
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;
   const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
   const int rsh = static_cast<int>(p.res.sh), rsw = static_cast<int>(p.res.sw);
   const int osh = static_cast<int>(p.out.sh), osw = static_cast<int>(p.out.sw);
   for (int h = r0; h < r1; ++h) {
-    const __nv_bfloat16* yr_ = yb + h * ysh;
-    const __nv_bfloat16* rr_ = HAS_RES ? rb + h * rsh : nullptr;
+    const T* yr_ = yb + h * ysh;
+    const T* rr_ = HAS_RES ? rb + h * rsh : nullptr;
     const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
     for (int w0 = lane; w0 < W; w0 += lanes * U) {
-      uint4 yr[U], rr[U];
+      V8 yr[U], rr[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int w = w0 + u * lanes;
@@ -273,22 +313,22 @@ __global__ void __launch_bounds__(256, 3) norm_act_fwd_kernel(NormFwdParams p) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += r[j];
         }
-        const uint4 o = pack8(f);
+        const V8 o = pack8<T>(f);
         st16(ob + h * osh + w * osw, o);
-        if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) write_halo(ob, osh, osw, h, w, H, W, pad, o);
+        if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) write_halo<T>(ob, osh, osw, h, w, H, W, pad, o);
       }
     }
   }
 }
 
-template <bool HAS_RES>
+template <typename T, bool HAS_RES>
 static void launch_norm_fwd(const NormFwdParams& p, dim3 grid, cudaStream_t stream) {
   switch (p.act) {
-    case CDB_ACT_NONE: norm_act_fwd_kernel<CDB_ACT_NONE, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
-    case CDB_ACT_RELU: norm_act_fwd_kernel<CDB_ACT_RELU, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
-    case CDB_ACT_LEAKY: norm_act_fwd_kernel<CDB_ACT_LEAKY, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
-    case CDB_ACT_TANH: norm_act_fwd_kernel<CDB_ACT_TANH, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
-    default: norm_act_fwd_kernel<CDB_ACT_SIGMOID, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_NONE: norm_act_fwd_kernel<T, CDB_ACT_NONE, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_RELU: norm_act_fwd_kernel<T, CDB_ACT_RELU, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_LEAKY: norm_act_fwd_kernel<T, CDB_ACT_LEAKY, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_TANH: norm_act_fwd_kernel<T, CDB_ACT_TANH, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
+    default: norm_act_fwd_kernel<T, CDB_ACT_SIGMOID, HAS_RES><<<grid, 256, 0, stream>>>(p); break;
   }
 }
 
@@ -304,12 +344,14 @@ static int rows_per_block_for(int H, int n, int cv_tiles, int per_sm) {
 
 // Batch-norm running statistics (training mode): r = (1-m) r + m * batch (unbiased variance).
 __global__ void bn_running_kernel(const float* __restrict__ stats, int C, float count, float momentum,
-                                  float* __restrict__ rmean, float* __restrict__ rvar) {
+                                  float* __restrict__ rmean, float* __restrict__ rvar,
+                                  const float* __restrict__ conv_bias) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
-  const float mean = stats[ch * 2] / count;
+  float mean = stats[ch * 2] / count;
   const float var = fmaxf(stats[ch * 2 + 1] / count - mean * mean, 0.f);
   const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+  if (conv_bias != nullptr) mean += conv_bias[ch];   // the statistics were taken on the bias-free convolution output
   rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * mean;
   rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * unbiased;
 }
@@ -339,7 +381,8 @@ struct NormBwdParams {
 };
 
 // Adds to g the reflect images of (h, w) other than (h, w) itself (border pixels only).
-__device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const __nv_bfloat16* db, int h, int w,
+template <typename T>
+__device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const T* db, int h, int w,
                                                   float* g) {
   const int pad = p.pad, H = p.H, W = p.W;
   int hh[3], ww[3];
@@ -362,8 +405,9 @@ __device__ __forceinline__ void add_folded_extras(const NormBwdParams& p, const 
 
 // Per-channel constants: xhat = y*a1 + b1 (a1 = rstd, b1 = -mean*rstd); z = xhat*gamma + beta (AFFINE) or xhat;
 // apply: dy = c1*(ga - m1 - xhat*m2) with c1 = rstd*gamma.  Row-strip mapping as in the forward kernel.
-template <bool kApply, int ACT, bool AFFINE, int U>
+template <typename T, bool kApply, int ACT, bool AFFINE, int U>
 __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
+  typedef typename Vec8<T>::type V8;
   __shared__ float red[kApply ? 1 : 256 * 16];
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
   const int cvec = blockIdx.z * p.vt + v;
@@ -406,17 +450,17 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
         }
       }
     }
-    const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
-    const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
-    const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
+    const T* yb = static_cast<const T*>(p.y.ptr) + n * p.y.sn + cvec * 8;
+    const T* db = p.has_dout ? static_cast<const T*>(p.dout.ptr) + n * p.dout.sn + cvec * 8 : nullptr;
+    const T* sb = p.has_dskip ? static_cast<const T*>(p.dskip.ptr) + n * p.dskip.sn + cvec * 8 : nullptr;
     const int pad = p.pad, H = p.H, W = p.W;
     const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
     const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
     const int ssh = static_cast<int>(p.dskip.sh), ssw = static_cast<int>(p.dskip.sw);
     const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
     const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
-    __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
-    __nv_bfloat16* ob = kApply ? p.dy.ptr + n * p.dy.sn + cvec * 8 : nullptr;
+    T* gb = p.write_gsum ? static_cast<T*>(p.gsum.ptr) + n * p.gsum.sn + cvec * 8 : nullptr;
+    T* ob = kApply ? static_cast<T*>(p.dy.ptr) + n * p.dy.sn + cvec * 8 : nullptr;
     const bool has_dout = p.has_dout, has_dskip = p.has_dskip;
     const int pre_act = p.pre_act;
     const float slope = p.slope;
@@ -424,7 +468,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
     for (int h = r0; h < r1; ++h) {
       const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
       for (int w0 = lane; w0 < W; w0 += lanes * U) {
-        uint4 yr[U], dr[U], sr[U];
+        V8 yr[U], dr[U], sr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int w = w0 + u * lanes;
@@ -443,7 +487,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
           for (int j = 0; j < 8; ++j) g[j] = 0.f;
           if (has_dout) {
             unpack8(dr[u], g);
-            if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) add_folded_extras(p, db, h, w, g);
+            if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) add_folded_extras<T>(p, db, h, w, g);
           }
           if (has_dskip) {
             float t[8];
@@ -452,7 +496,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
             for (int j = 0; j < 8; ++j) g[j] += t[j];
           }
           unpack8(yr[u], f);
-          if (kApply && gb != nullptr) st16(gb + h * gsh + w * gsw, pack8(g));
+          if (kApply && gb != nullptr) st16(gb + h * gsh + w * gsw, pack8<T>(g));
           float o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -483,7 +527,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(NormBwdParams p) {
               o4[0] = qa;
               o4[1] = qb;
             } else {
-              st16(ob + h * osh + w * osw, pack8(o));
+              st16(ob + h * osh + w * osw, pack8<T>(o));
             }
           }
         }
@@ -601,9 +645,9 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
   Walk64 first;
   first.init(p0 + lane, W);
-  const __nv_bfloat16* yb = p.y.ptr + n * p.y.sn + cvec * 8;
-  const __nv_bfloat16* db = p.has_dout ? p.dout.ptr + n * p.dout.sn + cvec * 8 : nullptr;
-  const __nv_bfloat16* sb = p.has_dskip ? p.dskip.ptr + n * p.dskip.sn + cvec * 8 : nullptr;
+  const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(p.y.ptr) + n * p.y.sn + cvec * 8;
+  const __nv_bfloat16* db = p.has_dout ? static_cast<const __nv_bfloat16*>(p.dout.ptr) + n * p.dout.sn + cvec * 8 : nullptr;
+  const __nv_bfloat16* sb = p.has_dskip ? static_cast<const __nv_bfloat16*>(p.dskip.ptr) + n * p.dskip.sn + cvec * 8 : nullptr;
   if (ASYNC) {
     // all 16 y / dout vectors of the thread go global -> shared memory (its private slots) without passing through
     // registers: 16 copies of 16 bytes in flight per thread = 64 KB per CTA from the first instruction on (the
@@ -673,7 +717,7 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] += t[j];
     }
-    sg[u * 256 + threadIdx.x] = pack8(g);   // the summed gradient (rounded to bf16 once) for the apply phase / gsum
+    sg[u * 256 + threadIdx.x] = pack8<__nv_bfloat16>(g);   // the summed gradient (rounded to bf16 once) for the apply phase / gsum
     if (!ASYNC) sy[u * 256 + threadIdx.x] = yr[k];
     unpack8(yr[k], f);
 #pragma unroll
@@ -729,8 +773,8 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
     m2[j] = tot[v * 16 + j * 2 + 1];
   }
   // ---- apply from registers
-  __nv_bfloat16* ob = p.dy.ptr + n * p.dy.sn + cvec * 8;
-  __nv_bfloat16* gb = p.write_gsum ? p.gsum.ptr + n * p.gsum.sn + cvec * 8 : nullptr;
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(p.dy.ptr) + n * p.dy.sn + cvec * 8;
+  __nv_bfloat16* gb = p.write_gsum ? static_cast<__nv_bfloat16*>(p.gsum.ptr) + n * p.gsum.sn + cvec * 8 : nullptr;
   Walk64 pa = first;
 #pragma unroll
   for (int u = 0; u < kFusedVecs; ++u, pa.next()) {
@@ -750,7 +794,7 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
       else if (ACT == CDB_ACT_LEAKY) ga = xhat > 0.f ? ga : ga * p.slope;
       o[j] = rstd[j] * (ga - m1[j] - xhat * m2[j]);
     }
-    st16(ob + h * osh + w * osw, pack8(o));
+    st16(ob + h * osh + w * osw, pack8<__nv_bfloat16>(o));
   }
   cluster.sync();   // keeps every CTA's `part` alive until all ranks have read it (off the critical path)
 }
@@ -808,50 +852,64 @@ static int bwd_unroll(const NormBwdParams& p) {
   (void)p;
   return forced == 4 ? 4 : 2;
 }
-template <bool kApply, bool AFFINE>
+template <typename T, bool kApply, bool AFFINE>
 static void launch_norm_bwd_act(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
-  if (bwd_unroll(p) == 4) {
+  if (sizeof(T) == 2 && bwd_unroll(p) == 4) {
     switch (p.act) {
-      case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
-      case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
-      default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+      case CDB_ACT_RELU: norm_act_bwd_kernel<T, kApply, CDB_ACT_RELU, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+      case CDB_ACT_LEAKY: norm_act_bwd_kernel<T, kApply, CDB_ACT_LEAKY, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
+      default: norm_act_bwd_kernel<T, kApply, CDB_ACT_NONE, AFFINE, 4><<<grid, 256, 0, stream>>>(p); break;
     }
     return;
   }
+  constexpr int U = sizeof(T) == 2 ? 2 : 1;
   switch (p.act) {
-    case CDB_ACT_RELU: norm_act_bwd_kernel<kApply, CDB_ACT_RELU, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
-    case CDB_ACT_LEAKY: norm_act_bwd_kernel<kApply, CDB_ACT_LEAKY, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
-    default: norm_act_bwd_kernel<kApply, CDB_ACT_NONE, AFFINE, 2><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_RELU: norm_act_bwd_kernel<T, kApply, CDB_ACT_RELU, AFFINE, U><<<grid, 256, 0, stream>>>(p); break;
+    case CDB_ACT_LEAKY: norm_act_bwd_kernel<T, kApply, CDB_ACT_LEAKY, AFFINE, U><<<grid, 256, 0, stream>>>(p); break;
+    default: norm_act_bwd_kernel<T, kApply, CDB_ACT_NONE, AFFINE, U><<<grid, 256, 0, stream>>>(p); break;
   }
 }
-template <bool kApply>
+template <typename T, bool kApply>
 static void launch_norm_bwd(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
-  if (p.gamma != nullptr || p.beta != nullptr) launch_norm_bwd_act<kApply, true>(p, grid, stream);
-  else launch_norm_bwd_act<kApply, false>(p, grid, stream);
+  if (p.gamma != nullptr || p.beta != nullptr) launch_norm_bwd_act<T, kApply, true>(p, grid, stream);
+  else launch_norm_bwd_act<T, kApply, false>(p, grid, stream);
 }
 
 }  // namespace cdb
 
 using namespace cdb;
 
-static int check_view(const CdbAct* a, const char* what) {
+// dtype: the storage type every view of the call must have (bf16, or fp32 for the TF32 network modes)
+static int check_view(const CdbAct* a, const char* what, int dtype = CDB_BF16) {
   CDB_REQUIRE(a && a->ptr, CDB_ERR_BAD_DESC, "%s: null tensor", what);
-  CDB_REQUIRE(a->dtype == CDB_BF16, CDB_ERR_UNSUPPORTED, "%s: bf16 only", what);
+  CDB_REQUIRE(a->dtype == dtype, CDB_ERR_UNSUPPORTED, "%s: all views of a call must share one storage type (%s)", what,
+              dtype == CDB_BF16 ? "bf16" : "fp32");
   CDB_REQUIRE(a->sn % 8 == 0 && a->sh % 8 == 0 && a->sw % 8 == 0 && (reinterpret_cast<uintptr_t>(a->ptr) & 15) == 0,
               CDB_ERR_ALIGNMENT, "%s: 16-byte alignment of pixels required", what);
+  return CDB_OK;
+}
+static int storage_type(const CdbAct* y, const char* what, int* dtype) {
+  CDB_REQUIRE(y && (y->dtype == CDB_BF16 || y->dtype == CDB_F32), CDB_ERR_UNSUPPORTED, "%s: bf16 or fp32 storage", what);
+  *dtype = y->dtype;
   return CDB_OK;
 }
 
 extern "C" int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_image, float* stats,
                                  cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = check_view(y, "channel_stats y");
+  int dt;
+  int rc = storage_type(y, "channel_stats y", &dt);
+  if (rc) return rc;
+  rc = check_view(y, "channel_stats y", dt);
   if (rc) return rc;
   CDB_REQUIRE(stats && c_real >= 1 && c_real <= y->c, CDB_ERR_BAD_DESC, "channel_stats: bad arguments");
   const Mapping m = mapping_for(round_up(c_real, 8));
   const int chunks = chunks_for(y->h * y->w, m.lanes, y->n, m.cv_tiles);
   dim3 grid(chunks, y->n, m.cv_tiles);
-  channel_stats_kernel<<<grid, 256, 0, stream>>>(view_of(y), y->h, y->w, c_real, m.vt, per_image, stats);
+  if (dt == CDB_F32)
+    channel_stats_kernel<float><<<grid, 256, 0, stream>>>(view_of(y), y->h, y->w, c_real, m.vt, per_image, stats);
+  else
+    channel_stats_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(view_of(y), y->h, y->w, c_real, m.vt, per_image, stats);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
@@ -874,13 +932,16 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
                                 const CdbAct* out, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(d, CDB_ERR_BAD_DESC, "norm_act_fwd: null desc");
-  int rc = check_view(y, "norm_act_fwd y");
+  int dt;
+  int rc = storage_type(y, "norm_act_fwd y", &dt);
   if (rc) return rc;
-  rc = check_view(out, "norm_act_fwd out");
+  rc = check_view(y, "norm_act_fwd y", dt);
+  if (rc) return rc;
+  rc = check_view(out, "norm_act_fwd out", dt);
   if (rc) return rc;
   const bool has_res = residual && residual->ptr;
   if (has_res) {
-    rc = check_view(residual, "norm_act_fwd residual");
+    rc = check_view(residual, "norm_act_fwd residual", dt);
     if (rc) return rc;
   }
   CDB_REQUIRE(out->n == y->n && out->h == y->h && out->w == y->w, CDB_ERR_BAD_DESC,
@@ -912,13 +973,18 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.running_var = d->running_var;
   p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 3);
   dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
-  if (has_res) launch_norm_fwd<true>(p, grid, stream);
-  else launch_norm_fwd<false>(p, grid, stream);
+  if (dt == CDB_F32) {
+    if (has_res) launch_norm_fwd<float, true>(p, grid, stream);
+    else launch_norm_fwd<float, false>(p, grid, stream);
+  } else {
+    if (has_res) launch_norm_fwd<__nv_bfloat16, true>(p, grid, stream);
+    else launch_norm_fwd<__nv_bfloat16, false>(p, grid, stream);
+  }
   CDB_LAUNCH_OK();
   if (d->norm == CDB_NORM_BATCH && !d->use_running && d->update_running && d->running_mean && d->running_var) {
     const float count = (float)((int64_t)y->n * y->h * y->w);
     bn_running_kernel<<<ceil_div(d->channels, 128), 128, 0, stream>>>(d->stats, d->channels, count, d->momentum,
-                                                                      d->running_mean, d->running_var);
+                                                                      d->running_mean, d->running_var, d->conv_bias);
     CDB_LAUNCH_OK();
   }
   return CDB_OK;
@@ -928,7 +994,10 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
                                 float* bstats, const CdbAct* dy, const CdbAct* gsum, cdbStream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(d, CDB_ERR_BAD_DESC, "norm_act_bwd: null desc");
-  int rc = check_view(y, "norm_act_bwd y");
+  int dt;
+  int rc = storage_type(y, "norm_act_bwd y", &dt);
+  if (rc) return rc;
+  rc = check_view(y, "norm_act_bwd y", dt);
   if (rc) return rc;
   const bool accum_f32 = (d->flags & CDB_NORM_FLAG_ACCUM_F32) != 0;
   if (accum_f32) {
@@ -936,14 +1005,14 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
                     (reinterpret_cast<uintptr_t>(dy->ptr) & 31) == 0,
                 CDB_ERR_ALIGNMENT, "norm_act_bwd: ACCUM_F32 needs an fp32 dy view with 32-byte aligned pixels");
   } else {
-    rc = check_view(dy, "norm_act_bwd dy");
+    rc = check_view(dy, "norm_act_bwd dy", dt);
     if (rc) return rc;
   }
   const bool has_dout = dout && dout->ptr, has_dskip = dskip && dskip->ptr, has_gsum = gsum && gsum->ptr;
   CDB_REQUIRE(has_dout || has_dskip, CDB_ERR_BAD_DESC, "norm_act_bwd: no incoming gradient");
-  if (has_dout && (rc = check_view(dout, "norm_act_bwd dout"))) return rc;
-  if (has_dskip && (rc = check_view(dskip, "norm_act_bwd dskip"))) return rc;
-  if (has_gsum && (rc = check_view(gsum, "norm_act_bwd gsum"))) return rc;
+  if (has_dout && (rc = check_view(dout, "norm_act_bwd dout", dt))) return rc;
+  if (has_dskip && (rc = check_view(dskip, "norm_act_bwd dskip", dt))) return rc;
+  if (has_gsum && (rc = check_view(gsum, "norm_act_bwd gsum", dt))) return rc;
   CDB_REQUIRE(d->act == CDB_ACT_NONE || d->act == CDB_ACT_RELU || d->act == CDB_ACT_LEAKY, CDB_ERR_UNSUPPORTED,
               "norm_act_bwd: activation %d", d->act);
   NormBwdParams p;
@@ -983,17 +1052,19 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.bstats = bstats;
   p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 2);
   dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
-  if (fused_in_eligible(d, p, accum_f32)) {
+  if (dt == CDB_BF16 && fused_in_eligible(d, p, accum_f32)) {
     launch_norm_bwd_fused(p, y->n, stream);
     CDB_LAUNCH_OK();
     return CDB_OK;
   }
   if (need_reduce || (bstats && d->norm == CDB_NORM_NONE)) {
     // norm none + bstats: the reduction yields the bias gradient (sum of ga) in component 0
-    launch_norm_bwd<false>(p, grid, stream);
+    if (dt == CDB_F32) launch_norm_bwd<float, false>(p, grid, stream);
+    else launch_norm_bwd<__nv_bfloat16, false>(p, grid, stream);
     CDB_LAUNCH_OK();
   }
-  launch_norm_bwd<true>(p, grid, stream);
+  if (dt == CDB_F32) launch_norm_bwd<float, true>(p, grid, stream);
+  else launch_norm_bwd<__nv_bfloat16, true>(p, grid, stream);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -4,8 +4,10 @@
 // out = base + sigmoid(mean_hw(t)) * s, bilinear x2 up-sampling (align_corners = True), PReLU with a
 // learnable slope, dropout, and the NHWC bf16 -> NCHW fp32 conversion at module outputs.
 // One thread handles 8 channels (16 bytes of bf16) of one pixel; consecutive threads take consecutive
-// channel vectors, so a warp touches whole 128-byte lines.
+// channel vectors, so a warp touches whole 128-byte lines.  Every view carries its own storage type (bf16, or
+// fp32 in the TF32 network modes); the arithmetic is fp32 either way.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace cdb {
 
@@ -13,6 +15,7 @@ struct PView {
   char* ptr;
   int64_t sn, sh, sw;  // elements
   int n, h, w, c;
+  int f32;             // storage type: 0 = bf16, 1 = fp32
 };
 
 static inline PView pview(const CdbAct* a) {
@@ -25,6 +28,7 @@ static inline PView pview(const CdbAct* a) {
   v.h = a->h;
   v.w = a->w;
   v.c = a->c;
+  v.f32 = a->dtype == CDB_F32 ? 1 : 0;
   return v;
 }
 
@@ -54,10 +58,23 @@ __device__ __forceinline__ float* f32w(const PView& v, int n, int h, int w, int 
   return reinterpret_cast<float*>(v.ptr) + n * v.sn + h * v.sh + w * v.sw + c;
 }
 __device__ __forceinline__ void ld8(const PView& v, int n, int h, int w, int c, float* f) {
-  pw_unpack8(*reinterpret_cast<const uint4*>(bf(v, n, h, w, c)), f);
+  if (v.f32) {
+    const float4* p = reinterpret_cast<const float4*>(f32w(v, n, h, w, c));
+    const float4 a = p[0], b = p[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    pw_unpack8(*reinterpret_cast<const uint4*>(bf(v, n, h, w, c)), f);
+  }
 }
 __device__ __forceinline__ void st8(const PView& v, int n, int h, int w, int c, const float* f) {
-  *reinterpret_cast<uint4*>(bfw(v, n, h, w, c)) = pw_pack8(f);
+  if (v.f32) {
+    float4* p = reinterpret_cast<float4*>(f32w(v, n, h, w, c));
+    p[0] = make_float4(f[0], f[1], f[2], f[3]);
+    p[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    *reinterpret_cast<uint4*>(bfw(v, n, h, w, c)) = pw_pack8(f);
+  }
 }
 
 // idx -> (cv, w, h, n) over a view of shape (n, h, w, cvn*8)
@@ -82,7 +99,7 @@ static int pw_grid(int64_t total) {
   return (int)b;
 }
 
-// ---- out = a + b ; mode 1: dst(bf16) = src(f32) ; mode 2: dst(f32) = src(bf16) ; mode 3: dst(f32) += src(bf16)
+// ---- out = a + b ; cast: dst = src or dst += src between any pair of storage types
 __global__ void __launch_bounds__(256) pw_add_kernel(PView a, PView b, PView o, int64_t total, int cvn) {
   PW_LOOP(total) {
     PW_DECODE(idx, cvn, o.w, o.h)
@@ -95,29 +112,18 @@ __global__ void __launch_bounds__(256) pw_add_kernel(PView a, PView b, PView o, 
   }
 }
 
-__global__ void __launch_bounds__(256) pw_cast_kernel(PView s, PView d, int64_t total, int cvn, int mode) {
+__global__ void __launch_bounds__(256) pw_cast_kernel(PView s, PView d, int64_t total, int cvn, int accumulate) {
   PW_LOOP(total) {
     PW_DECODE(idx, cvn, d.w, d.h)
     float x[8];
-    if (mode == 1) {
-      const float4* p = reinterpret_cast<const float4*>(f32w(s, n, h, w, c));
-      const float4 u = p[0], v = p[1];
-      x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
-      x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-      st8(d, n, h, w, c, x);
-    } else {
-      ld8(s, n, h, w, c, x);
-      float4* p = reinterpret_cast<float4*>(f32w(d, n, h, w, c));
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
-      if (mode == 3) {
-        u = p[0];
-        v = p[1];
-      }
-      u.x += x[0]; u.y += x[1]; u.z += x[2]; u.w += x[3];
-      v.x += x[4]; v.y += x[5]; v.z += x[6]; v.w += x[7];
-      p[0] = u;
-      p[1] = v;
+    ld8(s, n, h, w, c, x);
+    if (accumulate) {
+      float y[8];
+      ld8(d, n, h, w, c, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += y[j];
     }
+    st8(d, n, h, w, c, x);
   }
 }
 
@@ -174,7 +180,9 @@ __global__ void __launch_bounds__(256) pw_scale_kernel(PView x, PView o, float a
 __global__ void __launch_bounds__(256) pw_nearest_fwd_kernel(PView x, PView o, int64_t total, int cvn) {
   PW_LOOP(total) {
     PW_DECODE(idx, cvn, o.w, o.h)
-    *reinterpret_cast<uint4*>(bfw(o, n, h, w, c)) = *reinterpret_cast<const uint4*>(bf(x, n, h >> 1, w >> 1, c));
+    float t[8];
+    ld8(x, n, h >> 1, w >> 1, c, t);
+    st8(o, n, h, w, c, t);
   }
 }
 __global__ void __launch_bounds__(256) pw_nearest_bwd_kernel(PView g, PView dx, int64_t total, int cvn) {
@@ -438,7 +446,9 @@ __device__ __forceinline__ uint32_t pw_hash(uint64_t k) {
   return (uint32_t)k;
 }
 __global__ void __launch_bounds__(256)
-pw_dropout_kernel(PView x, PView o, uint64_t seed, float p_drop, int64_t total, int cvn) {
+pw_dropout_kernel(PView x, PView o, uint64_t seed, const uint64_t* __restrict__ seed_dev, float p_drop, int64_t total,
+                  int cvn) {
+  if (seed_dev != nullptr) seed += *seed_dev;   // device-resident seed: a replayed CUDA graph draws a new mask every step
   const float scale = 1.f / (1.f - p_drop);
   const uint32_t thr = (uint32_t)(p_drop * 4294967296.0);
   PW_LOOP(total) {
@@ -477,12 +487,44 @@ pw_to_nchw_kernel(PView x, float* __restrict__ dst, int C, int64_t d_n, int64_t 
   }
 }
 
-static int pw_check(const CdbAct* a, const char* what, int dtype = CDB_BF16) {
+// ---- error-compensated TF32 ("3xTF32"): x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi).  A convolution of
+// [hi | lo | hi] against weights [w_hi | w_hi | w_lo] concatenated along the contraction dimension accumulates
+// x_hi w_hi + x_lo w_hi + x_hi w_lo in the fp32 TMEM accumulator: fp32-level accuracy (~1e-6) from kind::tf32 MMAs.
+//   mode 0: out [n, h, w, 3c]  channels [hi | lo | hi]   (forward / data gradient: contraction over channels)
+//   mode 1: out [3n, h, w, c]  images   [hi ; lo ; hi]   (weight gradient: contraction over pixels)
+//   mode 2: out [3n, h, w, c]  images   [hi ; hi ; lo]   (the other weight-gradient operand)
+//   mode 3: out [n, h, w, c]   = hi                      (single-pass TF32: the operand rounded to nearest)
+__global__ void __launch_bounds__(256) pw_split_tf32_kernel(PView x, PView o, int mode, int64_t total, int cvn) {
+  PW_LOOP(total) {
+    PW_DECODE(idx, cvn, x.w, x.h)
+    float t[8], hi[8], lo[8];
+    ld8(x, n, h, w, c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = round_tf32(t[j]);
+      lo[j] = round_tf32(t[j] - hi[j]);
+    }
+    if (mode == 3) {
+      st8(o, n, h, w, c, hi);
+    } else if (mode == 0) {
+      st8(o, n, h, w, c, hi);
+      st8(o, n, h, w, x.c + c, lo);
+      st8(o, n, h, w, 2 * x.c + c, hi);
+    } else {
+      st8(o, n, h, w, c, hi);
+      st8(o, n + x.n, h, w, c, mode == 1 ? lo : hi);
+      st8(o, n + 2 * x.n, h, w, c, mode == 1 ? hi : lo);
+    }
+  }
+}
+
+// dtype: CDB_BF16 / CDB_F32 to require one storage type, -1 to accept either (each view carries its own)
+static int pw_check(const CdbAct* a, const char* what, int dtype = -1) {
   CDB_REQUIRE(a && a->ptr, CDB_ERR_BAD_DESC, "%s: null tensor", what);
-  CDB_REQUIRE(a->dtype == dtype, CDB_ERR_UNSUPPORTED, "%s: unexpected dtype %d", what, a->dtype);
-  const uintptr_t mask = dtype == CDB_BF16 ? 15 : 31;
+  CDB_REQUIRE((dtype == -1 && (a->dtype == CDB_BF16 || a->dtype == CDB_F32)) || a->dtype == dtype, CDB_ERR_UNSUPPORTED,
+              "%s: unexpected dtype %d", what, a->dtype);
   CDB_REQUIRE(a->c % 8 == 0 && a->sn % 8 == 0 && a->sh % 8 == 0 && a->sw % 8 == 0 &&
-                  (reinterpret_cast<uintptr_t>(a->ptr) & mask) == 0,
+                  (reinterpret_cast<uintptr_t>(a->ptr) & 15) == 0,
               CDB_ERR_ALIGNMENT, "%s: 8-channel alignment of pixels required", what);
   return CDB_OK;
 }
@@ -511,20 +553,11 @@ extern "C" int cdb_cast(const CdbAct* src, const CdbAct* dst, int32_t accumulate
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CDB_REQUIRE(src && dst, CDB_ERR_BAD_DESC, "cast: null argument");
   int rc;
-  int mode;
-  if (src->dtype == CDB_F32 && dst->dtype == CDB_BF16) {
-    CDB_REQUIRE(!accumulate, CDB_ERR_UNSUPPORTED, "cast: accumulate into bf16");
-    mode = 1;
-  } else if (src->dtype == CDB_BF16 && dst->dtype == CDB_F32) {
-    mode = accumulate ? 3 : 2;
-  } else {
-    return fail(CDB_ERR_UNSUPPORTED, "cast: dtype pair %d -> %d", src->dtype, dst->dtype);
-  }
   if ((rc = pw_check(src, "cast src", src->dtype)) || (rc = pw_check(dst, "cast dst", dst->dtype))) return rc;
   CDB_REQUIRE(same_shape(src, dst), CDB_ERR_BAD_DESC, "cast: shapes differ");
   const int64_t total = vec_total(dst);
   if (total == 0) return CDB_OK;
-  pw_cast_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(src), pview(dst), total, dst->c / 8, mode);
+  pw_cast_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(src), pview(dst), total, dst->c / 8, accumulate ? 1 : 0);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
@@ -735,7 +768,20 @@ extern "C" int cdb_dropout(const CdbAct* x, const CdbAct* out, uint64_t seed, fl
   CDB_REQUIRE(same_shape(x, out) && p_drop >= 0.f && p_drop < 1.f, CDB_ERR_BAD_DESC, "dropout: bad arguments");
   const int64_t total = vec_total(out);
   if (total == 0) return CDB_OK;
-  pw_dropout_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), seed, p_drop, total, out->c / 8);
+  pw_dropout_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), seed, nullptr, p_drop, total, out->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_dropout_dev(const CdbAct* x, const CdbAct* out, uint64_t seed, const uint64_t* seed_dev, float p_drop,
+                               cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(x, "dropout x")) || (rc = pw_check(out, "dropout out"))) return rc;
+  CDB_REQUIRE(same_shape(x, out) && p_drop >= 0.f && p_drop < 1.f && seed_dev, CDB_ERR_BAD_DESC, "dropout_dev: bad arguments");
+  const int64_t total = vec_total(out);
+  if (total == 0) return CDB_OK;
+  pw_dropout_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), seed, seed_dev, p_drop, total, out->c / 8);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }
@@ -803,7 +849,7 @@ __global__ void __launch_bounds__(256)
 zero_frame_kernel(PView full, int top, int left, int ih, int iw, int64_t frame_px, int64_t total, int cvn) {
   const int W = full.w, H = full.h;
   const int64_t top_band = (int64_t)top * W, mid_band = (int64_t)ih * (W - iw);
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % cvn);
     int64_t t = idx / cvn;
@@ -824,7 +870,7 @@ zero_frame_kernel(PView full, int top, int left, int ih, int iw, int64_t frame_p
       w = (int)(jj % W);
     }
     (void)H;
-    *reinterpret_cast<uint4*>(bfw(full, n, h, w, cv * 8)) = z;
+    st8(full, n, h, w, cv * 8, z);
   }
 }
 }  // namespace cdb
@@ -842,6 +888,26 @@ extern "C" int cdb_zero_frame(const CdbAct* full, int32_t top, int32_t left, int
   if (total == 0) return CDB_OK;
   zero_frame_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(full), top, left, inner_h, inner_w, frame_px, total,
                                                         full->c / 8);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" int cdb_split_tf32(const CdbAct* x, const CdbAct* out, int32_t mode, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = pw_check(x, "split_tf32 x", CDB_F32)) || (rc = pw_check(out, "split_tf32 out", CDB_F32))) return rc;
+  CDB_REQUIRE(mode >= 0 && mode <= 3, CDB_ERR_BAD_DESC, "split_tf32: mode %d", mode);
+  if (mode == 3)
+    CDB_REQUIRE(same_shape(x, out), CDB_ERR_BAD_DESC, "split_tf32: rounding mode needs out shaped like x");
+  else if (mode == 0)
+    CDB_REQUIRE(out->n == x->n && out->h == x->h && out->w == x->w && out->c == 3 * x->c, CDB_ERR_BAD_DESC,
+                "split_tf32: channel mode needs out [n, h, w, 3c]");
+  else
+    CDB_REQUIRE(out->n == 3 * x->n && out->h == x->h && out->w == x->w && out->c == x->c, CDB_ERR_BAD_DESC,
+                "split_tf32: batch mode needs out [3n, h, w, c]");
+  const int64_t total = vec_total(x);
+  if (total == 0) return CDB_OK;
+  pw_split_tf32_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(x), pview(out), mode, total, x->c / 8);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

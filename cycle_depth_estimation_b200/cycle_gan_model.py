@@ -22,64 +22,91 @@ from .graph_step import StepGraph
 from .image_pool import ImagePool
 
 
-class FusedAdam:
-    """torch.optim.Adam(lr, betas, eps=1e-8) semantics on the cdb_adam_step kernel (one launch per
-    parameter tensor). Keeps ``param_groups`` / ``zero_grad`` / ``step`` so schedulers and the step glue
-    work unchanged."""
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas, eps=1e-8) semantics on the multi-tensor cdb_adam_pack_multi kernel: ONE launch
+    per optimizer step, which also writes the updated filters into the packed bf16 GEMM operands the convolution
+    kernels read (SURVEY 8(f) f1 — no separate re-pack pass).
+
+    A real ``torch.optim.Optimizer``: ``param_groups`` / ``state`` / ``state_dict`` / ``load_state_dict`` /
+    ``zero_grad`` are the base class's, so ``networks.get_scheduler`` (models/networks.py:24-38) and
+    ``update_learning_rate`` (models/base_model.py:91-95) work on it unchanged; the per-parameter state uses
+    torch.optim.Adam's keys (``step``, ``exp_avg``, ``exp_avg_sq``).  With ``device_step`` (CUDA-graph replay of the
+    training step) the step count AND the learning rate live in device memory: ``sync_lr()`` — called outside the
+    graph before every replay — copies ``param_groups[i]['lr']`` to the device scalar the captured kernel reads, so
+    a scheduler's change takes effect on the next replay."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, device_step=False):
-        self.param_groups = [{'params': list(params), 'lr': lr, 'betas': betas, 'eps': eps, 'initial_lr': lr}]
-        self.state = {}
-        self.defaults = {'lr': lr, 'betas': betas, 'eps': eps}
-        # device_step: the step count lives in device memory (one counter per optimizer) so that a CUDA graph of
-        # the training step replays with the right bias corrections
+        super(FusedAdam, self).__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        # device_step: step count and learning rate are read from device memory by the kernel, so that a CUDA graph
+        # of the training step replays with the right bias corrections and the scheduler's current rate
         self.device_step = device_step
         self._step_dev = None
+        self._lr_dev = {}        # group index -> (fp32 device scalar, last value written)
 
-    def zero_grad(self, set_to_none=True):
-        for g in self.param_groups:
-            for p in g['params']:
-                if set_to_none:
-                    p.grad = None
-                elif p.grad is not None:
-                    p.grad.zero_()
+    def _device(self):
+        return self.param_groups[0]['params'][0].device
+
+    def sync_lr(self):
+        """Copies every group's current learning rate to its device scalar (no-op when unchanged). Must run
+        outside a CUDA-graph capture / before a replay."""
+        if not self.device_step:
+            return
+        for gi, g in enumerate(self.param_groups):
+            lr = float(g['lr'])
+            cur = self._lr_dev.get(gi)
+            if cur is None:
+                self._lr_dev[gi] = [torch.full((1,), lr, dtype=torch.float32, device=self._device()), lr]
+            elif cur[1] != lr:
+                cur[0].fill_(lr)
+                cur[1] = lr
 
     @torch.no_grad()
-    def step(self):
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        capturing = torch.cuda.is_current_stream_capturing() if torch.cuda.is_available() else False
         if self.device_step:
             if self._step_dev is None:
-                dev = self.param_groups[0]['params'][0].device
-                self._step_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+                self._step_dev = torch.zeros((1,), dtype=torch.int32, device=self._device())
             self._step_dev.add_(1)
-        for g in self.param_groups:
+            if not capturing:
+                self.sync_lr()
+        for gi, g in enumerate(self.param_groups):
             b1, b2 = g['betas']
             groups = {}
-            for p in g['params']:
-                if p.grad is None:
-                    continue
-                st = self.state.get(p)
-                if st is None:
-                    st = {'step': 0, 'exp_avg': torch.zeros_like(p), 'exp_avg_sq': torch.zeros_like(p)}
-                    self.state[p] = st
-                st['step'] += 1
-                if p.grad.dtype != torch.float32 or not p.data.is_contiguous():
-                    raise TypeError("FusedAdam: contiguous fp32 parameters and gradients expected")
-                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                groups.setdefault(st['step'], []).append((p.data, grad, st['exp_avg'], st['exp_avg_sq']))
-            # one multi-tensor launch per distinct step count (normally exactly one)
-            for step, items in groups.items():
-                ops.adam_multi(items, g['lr'], b1, b2, g['eps'], step, self._step_dev if self.device_step else None)
             updated = []
             for p in g['params']:
                 if p.grad is None:
                     continue
+                st = self.state[p]
+                if len(st) == 0:
+                    st['step'] = 0
+                    st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                step = int(st['step']) + 1      # a loaded torch.optim.Adam state holds a tensor here
+                st['step'] = step
+                if p.grad.dtype != torch.float32 or not p.data.is_contiguous():
+                    raise TypeError("FusedAdam: contiguous fp32 parameters and gradients expected")
+                grad = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                packs = engine_mod._pack_cache.adam_targets(p)
+                groups.setdefault(step, []).append((p.data, grad, st['exp_avg'], st['exp_avg_sq'], packs))
+                updated.append((p, packs))
+            # one multi-tensor launch per distinct step count (normally exactly one)
+            lr_dev = self._lr_dev[gi][0] if (self.device_step and gi in self._lr_dev) else None
+            for step, items in groups.items():
+                ops.adam_pack_multi(items, g['lr'], b1, b2, g['eps'], step,
+                                    self._step_dev if self.device_step else None, lr_dev)
+            for p, packs in updated:
                 # the kernel writes through raw pointers, which autograd's version counter cannot
                 # see; the packed-weight cache also keys on this explicit counter
                 p._cdb_version = getattr(p, '_cdb_version', 0) + 1
-                updated.append(p)
-            # bf16 GEMM operands of the updated filters: one multi-tensor re-pack instead of one launch per
-            # filter and layout at their next use
-            engine_mod._pack_cache.refresh(updated)
+                engine_mod._pack_cache.stamp(p, packs)
+            # cached layouts the kernel did not emit (a third layout of a filter, flipped / folded 7x7 forms):
+            # one multi-tensor re-pack for the plain ones, the rest re-pack lazily at their next use
+            engine_mod._pack_cache.refresh([p for p, _ in updated])
+        return loss
 
 
 class GradBuckets:
@@ -226,7 +253,7 @@ class CycleGANModel:
     def _pool_query(self, pool, fake):
         """Replicated pool under data parallelism: all ranks see the global batch in rank-major order
         and replay the identical random stream; each rank keeps its own slice of the result."""
-        if getattr(self, '_plan_dev', None) is not None:
+        if getattr(self, '_plan_dev', None) is not None and getattr(self, '_in_graphed_step', False):
             slot = self._plan_slot
             self._plan_slot += 1
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -324,7 +351,13 @@ class CycleGANModel:
         def step():
             self._plan_dev.copy_(self._plan_host, non_blocking=True)
             self._eager_step(True)
-        self._step_graph.run(step)
+        # the planned (device-table) pool path is taken only here: a validation step ('test') after the capture
+        # goes through the ordinary host-side pool.query (models/train.py:35-41 runs 'test' steps between epochs)
+        self._in_graphed_step = True
+        try:
+            self._step_graph.run(step, self.optimizers)
+        finally:
+            self._in_graphed_step = False
 
     def optimize_parameters(self, train_or_test='train'):
         if getattr(self, '_graph_mode', False) and train_or_test == 'train':

@@ -176,6 +176,58 @@ class _PackCache:
         return packed
 
 
+    def get_tf32(self, weight, rows_are_dim0, cs, x3, flipped=False):
+        """fp32 (TF32-rounded) GEMM operand of the fp32-storage network modes.  cs: stored channels of the
+        activation the convolution contracts over.  x3 (error-compensated mode): the contraction dimension holds
+        [w_hi | w_hi | w_lo], each block zero-padded to cs channels, matching the [x_hi | x_lo | x_hi] operand
+        ops.split_tf32(x, 0) produces."""
+        store = weight.__dict__.setdefault('_cdb_packed', {})
+        key = ('tf32', rows_are_dim0, cs, x3, flipped)
+        ver = (weight.data_ptr(), weight._version, getattr(weight, '_cdb_version', 0), _pack_epoch[0])
+        hit = store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        w = weight.detach().flip(2, 3) if flipped else weight.detach()
+        if x3:
+            kd = 1 if rows_are_dim0 else 0
+            hi = ops.round_tf32_(w.clone(memory_format=torch.contiguous_format))
+            lo = w - hi                       # exact in fp32; rounded to TF32 by the packing kernel
+            shape = list(w.shape)
+            shape[kd] = 3 * cs
+            w3 = torch.zeros(shape, dtype=torch.float32, device=w.device)
+            k = w.shape[kd]
+            for blk, part in enumerate((hi, hi, lo)):
+                w3.narrow(kd, blk * cs, k).copy_(part)
+            w = w3
+        packed = ops.pack_conv_weight_tf32(w.contiguous(), rows_are_dim0)
+        store[key] = (ver, packed)
+        return packed
+
+    def adam_targets(self, weight):
+        """Packed bf16 layouts of `weight` that the fused Adam kernel refreshes itself: at most two plain
+        (unflipped, unfolded) ones.  Returns [(packed tensor, rows_are_dim0, rowpack)]."""
+        store = weight.__dict__.get('_cdb_packed')
+        if not store or weight.dim() != 4 or not weight.is_contiguous():
+            return []
+        out = []
+        for key, (_, packed) in store.items():
+            if len(key) == 3 and key[0] in (True, False) and not key[2]:
+                out.append((packed[0], key[0], key[1]))
+                if len(out) == 2:
+                    break
+        return out
+
+    def stamp(self, weight, packs):
+        """Marks the layouts in `packs` (just rewritten by the Adam kernel) as current for the weight's new version."""
+        if not packs:
+            return
+        store = weight.__dict__['_cdb_packed']
+        ver = (weight.data_ptr(), weight._version, getattr(weight, '_cdb_version', 0), _pack_epoch[0])
+        bufs = {id(b) for b, _, _ in packs}
+        for key, (old_ver, packed) in list(store.items()):
+            if id(packed[0]) in bufs:
+                store[key] = (ver, packed)
+
     def refresh(self, params):
         """After an optimizer step: re-packs every cached plain layout of `params` with ONE multi-tensor launch
         and stamps the cache entries with the parameters' new versions (flipped / folded layouts of the two 7x7
@@ -418,7 +470,8 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
                              st.norm.running_var if nk == NORM_BATCH else None,
                              use_running=use_running,
                              update_running=(nk == NORM_BATCH and training and st.norm.track_running_stats),
-                             momentum=float(st.norm.momentum) if getattr(st.norm, "momentum", None) is not None else 0.1)
+                             momentum=float(st.norm.momentum) if getattr(st.norm, "momentum", None) is not None else 0.1,
+                             conv_bias=conv.bias if bias is None else None)
         if nk == NORM_BATCH and training and st.norm.track_running_stats and st.norm.num_batches_tracked is not None:
             st.norm.num_batches_tracked += 1
         res = run.inner[st.res] if st.res is not None else None

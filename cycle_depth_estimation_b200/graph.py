@@ -79,6 +79,31 @@ class Tape:
         self.param_grads = {}
         self.needs = {}            # param -> bool, filled in before the backward replay
         self.arena = ops.ZeroArena(device)
+        # storage / arithmetic mode of this network call (ops.set_precision): bf16 storage + kind::f16, or fp32
+        # storage + kind::tf32 (single pass, or error-compensated 'tf32x3')
+        self.prec = ops.get_precision()
+        self.dtype = BF16 if self.prec == 'bf16' else torch.float32
+
+    # ---------------------------------------------------------------- convolution calls (precision dispatch)
+    def _operand(self, x, mode_x3, mode_tf32=3):
+        return ops.split_tf32(x, mode_x3 if self.prec == 'tf32x3' else mode_tf32)
+
+    def _conv(self, g, xin, weight, rows_are_dim0, out, bias=None, act=ACT_NONE, slope=0.0, stats=None,
+              stats_batch=False, rowpack=0, flipped=False):
+        """One forward / data-gradient convolution launch in the precision of this call."""
+        if self.prec == 'bf16':
+            wp, rows_pad, kpad = _pack.get(weight, rows_are_dim0, rowpack, flipped)
+            ops.conv2d_fwd_ex(g, xin, wp, rows_pad, kpad, out, bias, act, slope, stats, stats_batch)
+            return
+        assert not rowpack
+        wp, rows_pad, kpad = _pack.get_tf32(weight, rows_are_dim0, xin.shape[3], self.prec == 'tf32x3', flipped)
+        ops.conv2d_fwd_ex(g, self._operand(xin, 0), wp, rows_pad, kpad, out, bias, act, slope, stats, stats_batch)
+
+    def _wgrad(self, g, x, dy, dw):
+        if self.prec == 'bf16':
+            ops.conv2d_wgrad(g, x, dy, dw, False)
+        else:
+            ops.conv2d_wgrad(g, self._operand(x, 1), self._operand(dy, 2), dw, False)
 
     # ---------------------------------------------------------------- bookkeeping
     def add_param_grad(self, p, g):
@@ -106,7 +131,7 @@ class Tape:
             for g, ch in v.parent.grads:
                 items.append((g[..., v.c0:v.c0 + v.t.shape[3]], False))
         if v.grad32 is not None:
-            g = torch.empty(tuple(v.t.shape), dtype=BF16, device=self.dev)
+            g = torch.empty(tuple(v.t.shape), dtype=self.dtype, device=self.dev)
             ops.cast(v.grad32, g)
             items.append((g, False))
         if not items:
@@ -119,14 +144,14 @@ class Tape:
             if v.halo_kind != 'reflect':
                 raise NotImplementedError("two halo-covering gradient contributions of a zero-padded value")
             g = halo_items.pop()
-            folded = torch.empty(tuple(v.t.shape), dtype=BF16, device=self.dev)
+            folded = torch.empty(tuple(v.t.shape), dtype=self.dtype, device=self.dev)
             desc = ops.norm_desc(NORM_NONE, ACT_NONE, 0.0, 0.0, v.c, v.halo)
             ops.norm_act_bwd(desc, v.t, folded, g, None, None, None)
             plain.append(folded)
         dout = halo_items[0] if halo_items else None
         while len(plain) > (1 if dout is not None else 2):
             a, b = plain.pop(), plain.pop()
-            s = torch.empty(tuple(a.shape), dtype=BF16, device=self.dev)
+            s = torch.empty(tuple(a.shape), dtype=self.dtype, device=self.dev)
             ops.add(a, b, s)
             plain.append(s)
         if dout is None:
@@ -141,7 +166,7 @@ class Tape:
             return None
         if dskip is None and not (v.halo and v.halo_kind == 'reflect' and any(ch for _, ch in v.grads)):
             return dout
-        out = torch.empty(tuple(v.t.shape), dtype=BF16, device=self.dev)
+        out = torch.empty(tuple(v.t.shape), dtype=self.dtype, device=self.dev)
         desc = ops.norm_desc(NORM_NONE, ACT_NONE, 0.0, 0.0, v.c, v.halo if v.halo_kind == 'reflect' else 0)
         ops.norm_act_bwd(desc, v.t, out, dout, dskip, None, None)
         return out
@@ -150,9 +175,9 @@ class Tape:
     def new_val(self, n, h, w, c, halo=0, halo_kind=None, slack_w=0):
         cs = ops.round_up(c, 8)
         if halo and halo_kind == 'zero':
-            buf = ops.empty_zero_halo(n, h, w, cs, halo, slack_w, self.dev)
+            buf = ops.empty_zero_halo(n, h, w, cs, halo, slack_w, self.dev, self.dtype)
         else:
-            buf = torch.empty((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=BF16, device=self.dev)
+            buf = torch.empty((n, h + 2 * halo, w + 2 * halo + slack_w, cs), dtype=self.dtype, device=self.dev)
         t = buf[:, halo:halo + h, halo:halo + w, :]
         full = buf if slack_w == 0 else buf[:, :, :w + 2 * halo, :]
         return Val(t, c, full, halo, halo_kind if halo else None)
@@ -176,7 +201,7 @@ class Tape:
             raise TypeError("fp32 NCHW input expected")
         n, c, h, w = x.shape
         rp = 0
-        if first_conv is not None and not isinstance(first_conv, nn.ConvTranspose2d):
+        if self.prec == 'bf16' and first_conv is not None and not isinstance(first_conv, nn.ConvTranspose2d):
             k = first_conv.kernel_size[0]
             if first_conv.dilation[0] == 1 and ((c <= 8 and k <= 8) or (c <= 16 and k <= 4)):
                 rp = 8 if c <= 8 else 16
@@ -187,7 +212,7 @@ class Tape:
             k, st = conv.kernel_size[0], conv.stride[0]
             wo = (w + 2 * p0 - (k - 1) - 1) // st + 1
             wneed = max(w + 2 * p0, st * (wo - 1) + 64 // rp)
-            buf = torch.zeros((n, h + 2 * p0, wneed, rp), dtype=BF16, device=self.dev)
+            buf = torch.zeros((n, h + 2 * p0, wneed, rp), dtype=self.dtype, device=self.dev)
             t = buf[:, p0:p0 + h, p0:p0 + w, :]
             ops.nchw_to_nhwc(x, t, pad=p0 if kind == 'reflect' else 0)
             v = Val(t, c, buf, p0, kind if p0 else None)
@@ -230,7 +255,7 @@ class Tape:
         gout = gout.contiguous()
         if slot['kind'] == 'val':
             v = slot['val']
-            g = torch.empty(tuple(v.t.shape), dtype=BF16, device=self.dev)
+            g = torch.empty(tuple(v.t.shape), dtype=self.dtype, device=self.dev)
             ops.nchw_to_nhwc(gout, g, pad=0)
             self.add_grad(v, g)
         else:
@@ -289,7 +314,6 @@ class Tape:
         xin, pad, materialised = self._conv_operand(x, conv, transposed, reflect)
         rowpack = x.rowpack
         g = ops.geom(k, k, stride, pad, pad, dil, transposed, rowpack)
-        wp, rows_pad, kpad = _pack.get(conv.weight, not transposed, rowpack)
         flat = (not transposed and stride == 1 and not rowpack and pad == 0 and _regular_pitch(xin))
         if norm is None:
             nk = NORM_NONE
@@ -305,7 +329,7 @@ class Tape:
         if out_nchw:
             assert nk == NORM_NONE and res is None
             o = torch.empty((n, co, ho, wo), dtype=torch.float32, device=self.dev)
-            ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nchw(o), conv.bias, act, slope)
+            self._conv(g, xin, conv.weight, not transposed, ops.out_view_nchw(o), conv.bias, act, slope, rowpack=rowpack)
             slot = {'kind': 'nchw', 'differentiable': differentiable_out, 'gout': None}
             outv = None
         else:
@@ -321,24 +345,25 @@ class Tape:
                 raise NotImplementedError("residual add without normalisation")
             if outv.halo and outv.halo_kind == 'reflect':
                 raise NotImplementedError("reflect halo after a stage without normalisation")
-            ops.conv2d_fwd_ex(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(outv.t, co), conv.bias, act, slope,
-                              outv.stats, stats_batch=True)
+            self._conv(g, xin, conv.weight, not transposed, ops.out_view_nhwc(outv.t, co), conv.bias, act, slope,
+                       outv.stats, stats_batch=True, rowpack=rowpack)
         else:
             if flat:
-                y = ops.alloc_flat_output(n, ho, wo, xin.shape[2], cs, self.dev)
+                y = ops.alloc_flat_output(n, ho, wo, xin.shape[2], cs, self.dev, dtype=self.dtype)
             else:
-                y = torch.empty((n, ho, wo, cs), dtype=BF16, device=self.dev)
+                y = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=self.dev)
             # a bias directly in front of a batch-statistics normalisation cancels; with an activation in
             # between (act_first) or running statistics it does not
             bias = conv.bias if (use_running or act_first) else None
             if not use_running:
                 groups = n if nk == NORM_INSTANCE else 1
                 stats = self.arena.take((groups, co, 2))
-            ops.conv2d_fwd_ex(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(y, co), bias,
-                              act if act_first else ACT_NONE, slope, stats, stats_batch=(nk == NORM_BATCH))
+            self._conv(g, xin, conv.weight, not transposed, ops.out_view_nhwc(y, co), bias,
+                       act if act_first else ACT_NONE, slope, stats, stats_batch=(nk == NORM_BATCH), rowpack=rowpack)
             affine = getattr(norm, "affine", False)
             desc = self._norm_desc(nk, norm, act, slope, co, outv.halo if outv.halo_kind == 'reflect' else 0, stats,
-                                   use_running, update=True, flags=NORM_FLAG_ACT_FIRST if act_first else 0)
+                                   use_running, update=True, flags=NORM_FLAG_ACT_FIRST if act_first else 0,
+                                   conv_bias=conv.bias if bias is None else None)
             ops.norm_act_fwd(desc, y, outv.t, res.t if res is not None else None)
             if outv.stats is not None:
                 ops.channel_stats(outv.t, co, False, outv.stats)
@@ -353,7 +378,7 @@ class Tape:
             return o, slot
         return outv
 
-    def _norm_desc(self, nk, norm, act, slope, co, pad, stats, use_running, update=False, flags=0):
+    def _norm_desc(self, nk, norm, act, slope, co, pad, stats, use_running, update=False, flags=0, conv_bias=None):
         affine = norm is not None and getattr(norm, "affine", False)
         bn = nk == NORM_BATCH
         upd = bool(update and bn and self.training and norm.track_running_stats)
@@ -365,7 +390,8 @@ class Tape:
         return ops.norm_desc(nk, act, slope, float(norm.eps) if norm is not None else 0.0, co, pad, stats,
                              norm.weight if affine else None, norm.bias if affine else None,
                              norm.running_mean if bn else None, norm.running_var if bn else None,
-                             use_running=use_running, update_running=upd, momentum=mom, flags=flags)
+                             use_running=use_running, update_running=upd, momentum=mom, flags=flags,
+                             conv_bias=conv_bias)
 
     def _stage_backward(self, x, conv, transposed, norm, nk, act, slope, act_first, res, reflect, outv, slot, o_nchw,
                         y, stats, xin, pad, materialised, rowpack, flat, use_running, dims):
@@ -381,7 +407,7 @@ class Tape:
         if flat_dgrad:
             hz = (k - 1) * dil
             slack = 64 // cs if cs <= 16 else 0
-            dyp = ops.empty_zero_halo(n, ho, wo, cs, hz, slack, dev)
+            dyp = ops.empty_zero_halo(n, ho, wo, cs, hz, slack, dev, self.dtype)
             dy = dyp[:, hz:hz + ho, hz:hz + wo, :]
         else:
             dyp = None
@@ -391,7 +417,7 @@ class Tape:
             if gout is None:
                 return
             if dy is None:
-                dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+                dy = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
             ops.nchw_to_nhwc(gout, dy, pad=0, act_out=o_nchw if act != ACT_NONE else None, act=act, slope=slope)
             if want_b:
                 db = torch.empty((co,), dtype=torch.float32, device=dev)
@@ -406,7 +432,7 @@ class Tape:
                 need_kernel = (act != ACT_NONE) or want_b or dskip is not None or halo_fold or flat_dgrad
                 if need_kernel:
                     if dy is None:
-                        dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+                        dy = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
                     bstats = self.arena.take((1, co, 2)) if want_b else None
                     desc = ops.norm_desc(NORM_NONE, act, slope, 0.0, co, halo_fold)
                     if act in (ACT_TANH, ACT_SIGMOID):
@@ -418,14 +444,14 @@ class Tape:
                     dy = dout
             else:
                 if dy is None:
-                    dy = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+                    dy = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
                 groups = n if nk == NORM_INSTANCE else 1
                 bstats = self.arena.take((groups, co, 2))
                 desc = self._norm_desc(nk, norm, act, slope, co, halo_fold, stats, use_running,
                                        flags=NORM_FLAG_ACT_FIRST if act_first else 0)
                 gsum = None
                 if res is not None and (dskip is not None or halo_fold):
-                    gsum = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
+                    gsum = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
                 ops.norm_act_bwd(desc, y, dy, dout, dskip, bstats, gsum)
                 if res is not None:
                     self.add_grad(res, gsum if gsum is not None else dout)
@@ -441,50 +467,48 @@ class Tape:
                     self.add_param_grad(norm.bias, bstats[0, :, 0].contiguous())
         # ---- weight gradient
         if want_w:
-            if flat_dgrad and cs <= 16 and k * cs <= 64 and dil == 1:
+            if self.prec == 'bf16' and flat_dgrad and cs <= 16 and k * cs <= 64 and dil == 1:
                 tmp = torch.empty((ci, co, k, k), dtype=torch.float32, device=dev)
                 ops.conv2d_wgrad(ops.geom(k, k, 1, 0, 0, 1, True, cs), xin, dyp, tmp, False)
                 dw = tmp.flip(2, 3).permute(1, 0, 2, 3).contiguous()
             else:
                 dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-                ops.conv2d_wgrad(ops.geom(k, k, stride, pad, pad, dil, transposed, rowpack), xin, dy, dw, False)
+                self._wgrad(ops.geom(k, k, stride, pad, pad, dil, transposed, rowpack), xin, dy, dw)
             self.add_param_grad(conv.weight, dw)
         # ---- data gradient
         if not want_dx:
             return
-        wd, rows_pad, kpad = _pack.get(conv.weight, transposed, 0)
         if rowpack:
             # the row-packed image buffer is zero padded by construction: gradient of the interior only
             p = conv.padding[0] if not reflect else 0
             gd = ops.geom(k, k, stride, p, p, dil, not transposed, 0)
             if reflect:
-                full = torch.empty((n, hi + 2 * reflect, wi + 2 * reflect, ops.round_up(ci, 8)), dtype=BF16, device=dev)
-                ops.conv2d_fwd(gd, dy, wd, rows_pad, kpad, ops.out_view_nhwc(full, ci))
+                full = torch.empty((n, hi + 2 * reflect, wi + 2 * reflect, ops.round_up(ci, 8)), dtype=self.dtype, device=dev)
+                self._conv(gd, dy, conv.weight, transposed, ops.out_view_nhwc(full, ci))
                 self.add_grad(x, full[:, reflect:reflect + hi, reflect:reflect + wi, :], covers_halo=True)
             else:
-                dx = torch.empty((n, hi, wi, ops.round_up(ci, 8)), dtype=BF16, device=dev)
-                ops.conv2d_fwd(gd, dy, wd, rows_pad, kpad, ops.out_view_nhwc(dx, ci))
+                dx = torch.empty((n, hi, wi, ops.round_up(ci, 8)), dtype=self.dtype, device=dev)
+                self._conv(gd, dy, conv.weight, transposed, ops.out_view_nhwc(dx, ci))
                 self.add_grad(x, dx)
             return
         if flat_dgrad:
             hp, wp_ = xin.shape[1], xin.shape[2]
-            dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], xin.shape[3], dev)
-            if cs <= 16 and k * cs <= 64 and dil == 1:
+            dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], xin.shape[3], dev, dtype=self.dtype)
+            if self.prec == 'bf16' and cs <= 16 and k * cs <= 64 and dil == 1:
                 # few output channels: row-packed dy operand (one K block per filter row), taps reversed at packing
-                wr, rows_r, kpad_r = _pack.get(conv.weight, transposed, cs, flipped=True)
-                ops.conv2d_fwd(ops.geom(k, k, 1, 0, 0, 1, False, cs), dyp, wr, rows_r, kpad_r,
-                               ops.out_view_nhwc(dfull, ci))
+                self._conv(ops.geom(k, k, 1, 0, 0, 1, False, cs), dyp, conv.weight, transposed,
+                           ops.out_view_nhwc(dfull, ci), rowpack=cs, flipped=True)
             else:
                 gflip = ops.geom(k, k, 1, 0, 0, dil, False, 0, True)
-                ops.conv2d_fwd(gflip, dyp, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+                self._conv(gflip, dyp, conv.weight, transposed, ops.out_view_nhwc(dfull, ci))
         elif k == 1 and stride == 1 and pad == 0 and not transposed and _regular_pitch(dy):
             # the data gradient of a 1x1 convolution is a 1x1 convolution: flat kernel (plain GEMM, BM = 256)
-            dfull = ops.alloc_flat_output(n, hi, wi, wi, ops.round_up(ci, 8), dev)
-            ops.conv2d_fwd(ops.geom(1, 1), dy, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+            dfull = ops.alloc_flat_output(n, hi, wi, wi, ops.round_up(ci, 8), dev, dtype=self.dtype)
+            self._conv(ops.geom(1, 1), dy, conv.weight, transposed, ops.out_view_nhwc(dfull, ci))
         else:
             gd = ops.geom(k, k, stride, pad, pad, dil, not transposed, 0)
-            dfull = torch.empty(tuple(xin.shape), dtype=BF16, device=dev)
-            ops.conv2d_fwd(gd, dy, wd, rows_pad, kpad, ops.out_view_nhwc(dfull, ci))
+            dfull = torch.empty(tuple(xin.shape), dtype=self.dtype, device=dev)
+            self._conv(gd, dy, conv.weight, transposed, ops.out_view_nhwc(dfull, ci))
         if materialised:
             h_ = x.halo
             self.add_grad(x, dfull[:, h_:h_ + hi, h_:h_ + wi, :], covers_halo=(x.halo_kind == 'reflect'))
@@ -536,7 +560,7 @@ class Tape:
                 if x.grad32 is not None:
                     ops.norm_act_bwd(desc_b, x.t, x.grad32, dout, dskip, bstats, None)
                 else:
-                    dy = torch.empty((n, h, w, ops.round_up(c, 8)), dtype=BF16, device=self.dev)
+                    dy = torch.empty((n, h, w, ops.round_up(c, 8)), dtype=self.dtype, device=self.dev)
                     ops.norm_act_bwd(desc_b, x.t, dy, dout, dskip, bstats, None)
                     x.grads.append((dy, False))
                 if affine:
@@ -558,7 +582,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 ops.avgpool2_bwd(g, dx)
                 self.add_grad(x, dx)
             self.back.append(backward)
@@ -573,7 +597,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 ops.bilinear2x_bwd(g, dx)
                 self.add_grad(x, dx)
             self.back.append(backward)
@@ -596,13 +620,13 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                ds = torch.empty(tuple(s.t.shape), dtype=BF16, device=self.dev)
+                ds = torch.empty(tuple(s.t.shape), dtype=self.dtype, device=self.dev)
                 dsum = self.arena.take((n, c))
                 ops.gate_bwd(g, s.t, sums, c, inv, ds, dsum)
                 self.add_grad(s, ds)
                 if base is not None:
                     self.add_grad(base, g)
-                dt = torch.empty(tuple(att.t.shape), dtype=BF16, device=self.dev)
+                dt = torch.empty(tuple(att.t.shape), dtype=self.dtype, device=self.dev)
                 ops.gate_bcast(dsum, sums, c, inv, dt)
                 self.add_grad(att, dt)
             self.back.append(backward)
@@ -621,7 +645,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 want = self.wants(prelu_module.weight)
                 ds = torch.zeros((1,), dtype=torch.float32, device=self.dev) if want else None
                 ops.prelu_bwd(x.t, g, prelu_module.weight, dx, ds)
@@ -641,7 +665,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 ops.scale(g, float(alpha), dx)
                 self.add_grad(x, dx)
             self.back.append(backward)
@@ -657,7 +681,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 ops.nearest2x_bwd(g, dx)
                 self.add_grad(x, dx)
             self.back.append(backward)
@@ -674,7 +698,7 @@ class Tape:
                 g = self.total_grad(outv)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
                 ops.tanh_bwd(outv.t, g, dx)
                 self.add_grad(x, dx)
             self.back.append(backward)
@@ -684,15 +708,16 @@ class Tape:
         """In-place dropout (training mode only); the mask is regenerated from the seed in the backward."""
         if not self.training or p <= 0.0:
             return x
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        ops.dropout(x.t, x.t, seed, p)
+        # the seed lives in device memory: a captured training step draws a new mask at every replay
+        seed = ops.dropout_seed(self.dev)
+        ops.dropout_dev(x.t, x.t, seed, p)
         if self.record:
             def backward():
                 g = self.total_grad(x)
                 if g is None:
                     return
-                dx = torch.empty(tuple(x.t.shape), dtype=BF16, device=self.dev)
-                ops.dropout(g, dx, seed, p)
+                dx = torch.empty(tuple(x.t.shape), dtype=self.dtype, device=self.dev)
+                ops.dropout_dev(g, dx, seed, p)
                 x.grads[:] = [(dx, False)]
                 x.folded_parent = True
             self.back.append(backward)

@@ -9,8 +9,9 @@ and from then on replays the captured graph.
 
 Requirements on ``step_fn`` (met by the step mirrors of this package): static input tensors (copy new data into
 them), no host synchronisation, no host-side decisions that change between steps (the ImagePool's random draws
-are made up-front and reach the device through a pinned table; Adam reads its step count from device memory;
-dropout reads its seed from device memory).
+are made up-front and reach the device through a pinned table; Adam reads its step count and learning rate from
+device memory (``FusedAdam.sync_lr``); dropout reads its seed from a device counter that a node of the graph bumps,
+``ops.dropout_seed``).
 """
 import torch
 
@@ -33,7 +34,12 @@ class StepGraph:
         if self._done is not None:
             self._done.synchronize()
 
-    def run(self, step_fn):
+    def run(self, step_fn, optimizers=()):
+        """optimizers: FusedAdam instances stepped inside step_fn; their learning rates are copied to the device
+        scalars the captured kernels read (FusedAdam.sync_lr) before every call, so scheduler updates reach replays."""
+        for o in optimizers:
+            if hasattr(o, 'sync_lr'):
+                o.sync_lr()
         if self.graph is not None:
             self.graph.replay()
             self._done.record()

@@ -4,20 +4,32 @@ Same decisions, in the same order, from the same Python ``random`` stream as the
 (util/image_pool.py:12-32): fill the pool first, then with probability 1/2 return a random stored image
 and store the new one.  The images live in ONE preallocated device tensor [pool_size, C, H, W] and the
 returned batch is written in place, so a query is index bookkeeping on the host plus slice copies on the
-device — no per-image unsqueeze / clone / cat.  ``trace`` records the decisions for the parity tests.
+device — no per-image unsqueeze / clone / cat.  ``trace`` records the most recent decisions for the parity
+tests (bounded: a long training run does not grow host memory).
 """
 import random
 
 import torch
 
 
+class _Trace(list):
+    """List of the most recent decisions: the older half is dropped whenever MAX entries are reached."""
+    MAX = 1 << 16
+
+    def append(self, item):
+        if len(self) >= self.MAX:
+            del self[:self.MAX // 2]
+        list.append(self, item)
+
+
 class ImagePool():
+
     def __init__(self, pool_size):
         self.pool_size = pool_size
+        self.trace = _Trace()
         if self.pool_size > 0:
             self.num_imgs = 0
             self.images = None      # [pool_size, C, H, W], allocated at the first query
-            self.trace = []
 
     def query(self, images):
         if self.pool_size == 0:
@@ -51,6 +63,8 @@ class ImagePool():
     def plan(self, batch):
         """Draws the decisions of ONE query of `batch` images from Python's ``random`` exactly as ``query`` would
         (same calls, same order) and returns [(return_from, store_to)] with -1 = the incoming image / no store."""
+        if self.pool_size == 0:          # query() returns the batch untouched and draws nothing
+            return [(-1, -1)] * batch
         out = []
         for _ in range(batch):
             if self.num_imgs < self.pool_size:

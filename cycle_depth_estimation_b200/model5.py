@@ -202,7 +202,9 @@ class Seg_Depth:
                 for o in (self.optimizer_G_1, self.optimizer_G_2, self.optimizer_R_D, self.optimizer_FD1,
                           self.optimizer_FD2, self.optimizer_FD3):
                     o.zero_grad()               # gradients must be (re)allocated inside the capture
-            return sg.run(lambda: self._eager_step('train'))
+            return sg.run(lambda: self._eager_step('train'),
+                          (self.optimizer_G_1, self.optimizer_G_2, self.optimizer_R_D, self.optimizer_FD1,
+                           self.optimizer_FD2, self.optimizer_FD3))
         return self._eager_step(train_or_test)
 
     def _eager_step(self, train_or_test='train'):

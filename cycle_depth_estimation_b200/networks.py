@@ -13,8 +13,9 @@ import torch.nn as nn
 from torch.nn import init
 from torch.optim import lr_scheduler
 
-from . import engine, graph, losses
+from . import engine, graph, losses, ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
+from .ops import get_precision, precision, set_precision  # noqa: F401  (re-exported: the network precision switch)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -156,7 +157,29 @@ class _FusedNet(nn.Module):
             self.__dict__['_cdb_plan'] = plan
         return plan
 
+    def _chain_body(self, tape, x):
+        """The compiled stage list executed on the general tape (graph.py) — the route of the fp32-storage
+        precisions ('tf32', 'tf32x3'), which the bf16-specialised chain engine does not implement."""
+        plan = self._plan()
+        st0 = plan.stages[0]
+        v0 = tape.input_nchw(x, pad=st0.reflect, pad_kind='reflect' if st0.reflect else None, first_conv=st0.conv,
+                             want_grad=tape.input_wants[0])
+        vals = {0: v0}
+        out = slot = None
+        for idx, st in enumerate(plan.stages):
+            src = vals[st.src]
+            if idx == len(plan.stages) - 1:
+                out, slot = tape.stage(src, st.conv, None, st.act, st.slope, reflect=st.reflect, out_nchw=True)
+                break
+            halo, zh = plan.halo[st.dst], plan.zero_halo[st.dst]
+            vals[st.dst] = tape.stage(src, st.conv, st.norm, st.act, st.slope,
+                                      res=vals[st.res] if st.res is not None else None, reflect=st.reflect,
+                                      halo=halo or zh, halo_kind='reflect' if halo else ('zero' if zh else None))
+        return [out], [slot], [v0]
+
     def forward(self, input):
+        if ops.get_precision() != 'bf16' or getattr(self, '_cdb_force_tape', False):
+            return graph.run(self, self._chain_body, [input])[0]
         return engine.run_network(self, self._plan(), input)
 
 
@@ -214,9 +237,23 @@ class ResnetBlock(nn.Module):
         block += padded_conv() + [norm_layer(dim)]
         return nn.Sequential(*block)
 
+    def _block_body(self, tape, x):
+        stages, _ = engine.compile_chain([self])
+        a, b = stages
+        v0 = tape.input_nchw(x, pad=a.reflect, pad_kind='reflect' if a.reflect else None,
+                             want_grad=tape.input_wants[0])
+        if not a.reflect and a.conv.padding[0]:
+            raise NotImplementedError("standalone ResnetBlock with padding_type='zero'")
+        mid = tape.stage(v0, a.conv, a.norm, a.act, a.slope, reflect=a.reflect, halo=b.reflect,
+                         halo_kind='reflect' if b.reflect else None)
+        y = tape.stage(mid, b.conv, b.norm, b.act, b.slope, res=v0, reflect=b.reflect)
+        out, slot = tape.output_nchw(y)
+        return [out], [slot], [v0]
+
     def forward(self, x):
-        # only reached when a block is used outside a fused network
-        raise RuntimeError("ResnetBlock runs as part of a fused cdb200 network (ResnetGenerator.forward)")
+        """models/networks.py:234-236: out = x + conv_block(x).  Inside a ResnetGenerator the block is a pair of fused
+        stages of the generator's plan; called on its own (fp32 NCHW in / out) it runs the same two stages."""
+        return graph.run(self, self._block_body, [x])[0]
 
 
 class NLayerDiscriminator(_FusedNet):

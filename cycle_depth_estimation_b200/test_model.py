@@ -1,0 +1,83 @@
+"""Generator inference of the reference's ``models/test_model.py`` (``test.py --model test``, BASELINE configs[0]):
+one generator, ``set_input`` / ``forward`` / ``test``, no losses.
+
+``TestModel`` mirrors the reference class (models/test_model.py:21-46: ``initialize(opt)`` builds ``netG`` with
+``networks.define_G`` and aliases it as ``netG<model_suffix>``; ``set_input`` reads ``input['A']``; ``forward`` sets
+``fake_B = netG(real_A)``).  With ``opt.cuda_graph`` the forward pass (~60 short kernels at batch 1) is captured once per
+input shape and replayed as ONE CUDA graph: at batch 1 the eager pass is launch-bound, the replay is not.
+"""
+import torch
+
+from . import networks
+
+
+class TestModel:
+    def name(self):
+        return 'TestModel'
+
+    def initialize(self, opt):
+        assert (not opt.isTrain), 'TestModel cannot be used in train mode'   # models/test_model.py:22
+        self.opt = opt
+        self.isTrain = False
+        self.device = torch.device(getattr(opt, 'device', 'cuda'))
+        self.loss_names = []
+        self.visual_names = ['real_A', 'fake_B']
+        suffix = getattr(opt, 'model_suffix', '')
+        self.model_names = ['G' + suffix]
+        self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.netG, opt.norm, not opt.no_dropout,
+                                      opt.init_type, opt.init_gain, [self.device])
+        setattr(self, 'netG' + suffix, self.netG)
+        self._graph_mode = bool(getattr(opt, 'cuda_graph', False))
+        self._graphs = {}           # input shape -> (graph, static input, static output)
+        self.image_paths = None
+
+    def set_input(self, input):
+        a = input['A']
+        if self._graph_mode:
+            entry = self._graphs.get(tuple(a.shape))
+            if entry is not None:
+                entry[1].copy_(a, non_blocking=True)      # static input buffer of the captured forward
+                self.real_A = entry[1]
+                self.image_paths = input.get('A_paths')
+                return
+        self.real_A = a.to(self.device, non_blocking=True)
+        self.image_paths = input.get('A_paths')
+
+    def eval(self):
+        self.netG.eval()
+        return self
+
+    def _capture(self):
+        x = self.real_A.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                            # warm-up: weight packing, lazy allocations
+                self.netG(x)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            out = self.netG(x)
+        self._graphs[tuple(x.shape)] = (graph, x, out)
+        return graph, x, out
+
+    def forward(self):
+        if self._graph_mode and not torch.is_grad_enabled():
+            entry = self._graphs.get(tuple(self.real_A.shape))
+            if entry is None:
+                entry = self._capture()
+                entry[1].copy_(self.real_A)
+            elif self.real_A is not entry[1]:
+                entry[1].copy_(self.real_A)
+            entry[0].replay()
+            self.fake_B = entry[2]
+            return
+        self.fake_B = self.netG(self.real_A)
+
+    def test(self):
+        """models/base_model.py:60-62: forward without gradients."""
+        with torch.no_grad():
+            self.forward()
+
+    def get_current_visuals(self):
+        return {'real_A': self.real_A, 'fake_B': self.fake_B}

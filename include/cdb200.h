@@ -170,6 +170,9 @@ typedef struct CdbNormDesc {
   const float* beta;      /* [channels] or NULL */
   float* running_mean;    /* [channels] or NULL */
   float* running_var;     /* [channels] or NULL */
+  const float* conv_bias; /* [channels] or NULL: bias of the convolution in front of a training-mode BatchNorm. The
+                           * convolution skips it (it cancels in the normalised output), but torch's running_mean
+                           * tracks mean(conv + bias): the running update adds it back. */
 } CdbNormDesc;
 /* ACT_FIRST: the layer is conv -> act -> norm (new_multi/networks5_ds.py:636-638,661-676): y is the
  *   ACTIVATED convolution output (the conv epilogue applied `act`), forward = norm only, backward
@@ -255,6 +258,18 @@ int cdb_prelu_bwd(const CdbAct* x, const CdbAct* g, const float* slope, const Cd
 /* nn.Dropout(p) (models/networks.py:305-306): out = x * keep / (1-p), keep = hash(seed, index) >= p.
  * Calling it again on the gradient with the same seed is the backward pass. */
 int cdb_dropout(const CdbAct* x, const CdbAct* out, uint64_t seed, float p_drop, cdbStream_t stream);
+/* Same with the effective seed = seed + *seed_dev read from device memory at run time: a training step replayed as a
+ * CUDA graph then draws a fresh mask every step (the host-side seed of cdb_dropout is frozen at capture time). */
+int cdb_dropout_dev(const CdbAct* x, const CdbAct* out, uint64_t seed, const uint64_t* seed_dev, float p_drop,
+                    cdbStream_t stream);
+/* Error-compensated TF32 ("3xTF32", the `tf32x3` network precision): x = hi + lo with hi = rna_tf32(x),
+ * lo = rna_tf32(x - hi).  mode 0: out [n,h,w,3c] = channels [hi | lo | hi] (operand of a forward / data-gradient
+ * convolution whose packed weights are [w_hi | w_hi | w_lo] along the contraction dimension); mode 1 / 2: out
+ * [3n,h,w,c] = images [hi ; lo ; hi] / [hi ; hi ; lo] (the two operands of a weight gradient); mode 3: out [n,h,w,c] =
+ * hi (the operand of the single-pass `tf32` precision, rounded to nearest instead of truncated).  The fp32 TMEM
+ * accumulator then holds x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. the fp32 result of the reference's ATen
+ * convolution (models/networks.py:162-185) to ~1e-6 instead of TF32's ~3e-4.  x, out: fp32 views. */
+int cdb_split_tf32(const CdbAct* x, const CdbAct* out, int32_t mode, cdbStream_t stream);
 /* NHWC bf16 view -> NCHW fp32 tensor (module outputs), dst strides in elements. */
 int cdb_nhwc_to_nchw(const CdbAct* x, int32_t c_real, float* dst, int64_t d_n, int64_t d_c, int64_t d_h,
                      int64_t d_w, cdbStream_t stream);
@@ -302,6 +317,25 @@ typedef struct CdbAdamEntry {
 } CdbAdamEntry;
 int cdb_adam_multi(const CdbAdamEntry* entries_host, int32_t n_entries, float lr, float beta1, float beta2, float eps,
                    int32_t step, const int32_t* step_dev, cdbStream_t stream);
+
+/* SURVEY 8(f) row f1, second half: the same multi-tensor step also EMITS the packed bf16 GEMM operands the
+ * convolution kernels read (cdb_pack_conv_weight layouts), so no re-pack pass follows the optimizer
+ * (models/cycle_gan_model.py:66-69,149,160 are the optimizer call sites).  Per entry up to two packed copies of the
+ * filter [d0][d1][r][s] are refreshed (pack[t] == NULL: none); lr_dev != NULL reads the learning rate from device
+ * memory, which lets a learning-rate scheduler (models/networks.py:24-38) act on a replayed CUDA graph. */
+typedef struct CdbAdamPackEntry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  void* pack[2];
+  int32_t d0, d1, r, s;
+  int32_t rows_are_dim0[2];
+  int32_t rowpack[2];
+} CdbAdamPackEntry;
+int cdb_adam_pack_multi(const CdbAdamPackEntry* entries_host, int32_t n_entries, float lr, const float* lr_dev,
+                        float beta1, float beta2, float eps, int32_t step, const int32_t* step_dev, cdbStream_t stream);
 
 /* ImagePool.query (util/image_pool.py:12-32) with the host's random decisions supplied as a device table
  * plan_dev[batch][2] = {return_from, store_to} (-1: the incoming image / nothing stored); fake, out:

