@@ -98,19 +98,29 @@ def test_fused_adam_emits_the_packed_operands():
     opt.step()
     launches = ops._lib.lib().cdb_launch_count() - n0
     assert launches <= 2, launches                # one Adam launch (+ at most one re-pack of a third layout)
-    w = net.model[2].weight
-    store = w.__dict__['_cdb_packed']
-    assert len([k for k in store if len(k) == 3]) >= 2
-    for key, (ver, packed) in store.items():
-        if len(key) != 3 or key[2]:
+    checked = 0
+    for mod in net.model:
+        w = getattr(mod, 'weight', None)
+        if w is None or w.dim() != 4:
             continue
-        fresh, _, _ = ops.pack_conv_weight(w.detach().contiguous(), key[0], key[1])
-        assert torch.equal(packed[0], fresh), key
+        store = w.__dict__['_cdb_packed']
+        for key, (ver, packed) in store.items():
+            if len(key) != 3 or key[2]:
+                continue
+            fresh, _, _ = ops.pack_conv_weight(w.detach().contiguous(), key[0], key[1])
+            assert torch.equal(packed[0], fresh), (mod, key)      # bit-identical to a fresh packing of the new values
+            assert ver[2] == 1                                    # stamped with the post-step version: no lazy re-pack
+            checked += 1
+    assert checked >= 9, checked          # 5 forward layouts + 4 data-gradient layouts (the first layer needs no dgrad)
+    n0 = ops._lib.lib().cdb_launch_count()
     with torch.no_grad():
-        a = net(x)
-        engine.invalidate_packed_weights()
-        b = net(x)
-    assert torch.equal(a, b)
+        net(x)
+    fwd_launches = ops._lib.lib().cdb_launch_count() - n0
+    engine.invalidate_packed_weights()
+    n0 = ops._lib.lib().cdb_launch_count()
+    with torch.no_grad():
+        net(x)
+    assert ops._lib.lib().cdb_launch_count() - n0 == fwd_launches + 5   # only the invalidated run re-packs (5 filters)
 
 
 def test_dropout_draws_a_new_mask_at_every_replay():
