@@ -76,6 +76,7 @@ def lib():
     L.cdb_device_abort_flag.restype = C.c_int
     L.cdb_launch_count.restype = C.c_longlong
     L.cdb_conv2d_wgrad_workspace.restype = C.c_size_t
+    L.cdb_conv2d_toeplitz_wgrad_workspace.restype = C.c_size_t
     L.cdb_depth_metrics_workspace.restype = C.c_size_t
     L.cdb_validation_workspace.restype = C.c_size_t
     L.cdb_depth_labels_workspace.restype = C.c_size_t

@@ -43,16 +43,33 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 
+// Non-blocking probe of the phase (mbarrier.test_wait never suspends the thread; try_wait may park it for a
+// system-dependent time before it re-checks).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+
 // Bounded wait: a wrong descriptor or a lost arrive must not hang the GPU box. On timeout the
 // caller's abort flag (shared memory) is raised and every role drains out of its loop.
 #ifndef CDB_WAIT_TIMEOUT_CYCLES
 #define CDB_WAIT_TIMEOUT_CYCLES (2000000000ll)  // ~1 s at 1.9 GHz
 #endif
+#ifndef CDB_WAIT_SPIN
+#define CDB_WAIT_SPIN 0
+#endif
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (true) {
-    if (mbar_try_wait(bar, parity)) return true;
+    if (CDB_WAIT_SPIN ? mbar_test_wait(bar, parity) : mbar_try_wait(bar, parity)) return true;
     if (*abort_flag) return false;
     if (clock64() - t0 > CDB_WAIT_TIMEOUT_CYCLES) {
       *abort_flag = 1;
@@ -205,6 +222,7 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");

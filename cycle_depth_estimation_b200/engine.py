@@ -11,6 +11,8 @@ mask + norm backward (one fused kernel pair), tcgen05 wgrad and tcgen05 dgrad pe
 Reference structure being executed: models/networks.py:145-191 (ResnetGenerator), :195-236
 (ResnetBlock), :320-364 (NLayerDiscriminator), :367-389 (PixelDiscriminator).
 """
+import os as _os
+
 import torch
 import torch.nn as nn
 
@@ -176,6 +178,19 @@ class _PackCache:
         return packed
 
 
+    def get_toeplitz(self, weight, rows_are_dim0, flip):
+        """Toeplitz operand of an image layer (ops.pack_toeplitz_weight): (packed, rows_pad)."""
+        store = weight.__dict__.setdefault('_cdb_packed', {})
+        key = ('tz', rows_are_dim0, flip)
+        ver = (weight.data_ptr(), weight._version, getattr(weight, '_cdb_version', 0), _pack_epoch[0])
+        hit = store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        packed = ops.pack_toeplitz_weight(weight.detach().contiguous(), rows_are_dim0, flip,
+                                          out=hit[1][0] if hit is not None else None)
+        store[key] = (ver, packed)
+        return packed
+
     def get_tf32(self, weight, rows_are_dim0, cs, x3, flipped=False):
         """fp32 (TF32-rounded) GEMM operand of the fp32-storage network modes.  cs: stored channels of the
         activation the convolution contracts over.  x3 (error-compensated mode): the contraction dimension holds
@@ -211,7 +226,7 @@ class _PackCache:
             return []
         out = []
         for key, (_, packed) in store.items():
-            if len(key) == 3 and key[0] in (True, False) and not key[2]:
+            if len(key) == 3 and isinstance(key[0], bool) and not key[2]:
                 out.append((packed[0], key[0], key[1]))
                 if len(out) == 2:
                     break
@@ -239,7 +254,7 @@ class _PackCache:
                 continue
             ver = (w.data_ptr(), w._version, getattr(w, '_cdb_version', 0), _pack_epoch[0])
             for key, (old_ver, packed) in store.items():
-                if len(key) == 3 and key[0] != 'fold' and not key[2] and old_ver != ver and w.is_contiguous():
+                if len(key) == 3 and isinstance(key[0], bool) and not key[2] and old_ver != ver and w.is_contiguous():
                     items.append((w.detach(), key[0], key[1], packed[0]))
                     stamps.append((store, key, ver, packed))
         ops.pack_conv_weights_multi(items)
@@ -316,6 +331,20 @@ def _rowpack_for(st, cin):
     return 0
 
 
+def _toeplitz_first(st, cin):
+    """The first stage is an image layer the Toeplitz kernels take (csrc/conv_toeplitz.cu): stride 1, no dilation,
+    <= 8 input channels, filter <= 8 x 8, <= 128 output channels — c7s1-64 of the generators."""
+    c = st.conv
+    return (not st.transposed and c.stride[0] == 1 and c.dilation[0] == 1 and cin <= 8 and c.kernel_size[0] <= 8
+            and c.out_channels <= 128 and not _os.environ.get("CDB_NO_TOEPLITZ"))
+
+
+def _toeplitz_last(conv, transposed, cs):
+    """The data / weight gradient of a stride-1 layer with <= 8 output channels (c7s1-3): its 'image' is dy."""
+    return (not transposed and cs == 8 and conv.dilation[0] == 1 and conv.kernel_size[0] <= 8 and conv.in_channels <= 128
+            and not _os.environ.get("CDB_NO_TOEPLITZ"))
+
+
 def _norm_kind(st):
     if st.norm is None:
         return NORM_NONE
@@ -371,6 +400,7 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
     st0 = plan.stages[0]
     rp = _rowpack_for(st0, cin)
     run.rowpack = rp
+    run.toeplitz0 = bool(rp) and rp == 8 and _toeplitz_first(st0, cin)
     conv0 = st0.conv
     pad0 = st0.reflect if st0.reflect else conv0.padding[0]
     if rp:
@@ -437,15 +467,22 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         run.vals[st.dst] = dbuf
         run.inner[st.dst] = dinner
         run.dims[st.dst] = (ho, wo, co)
+        tz = is_first and run.toeplitz0
+        if tz:
+            twp, trows = _pack_cache.get_toeplitz(conv.weight, True, False)
         if nk == NORM_NONE:
             if halo:
                 raise NotImplementedError("reflect padding after a stage without normalisation")
             if st.res is not None:
                 raise NotImplementedError("residual add without normalisation")
-            ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(dinner, co), conv.bias, st.act, st.slope)
+            if tz:
+                ops.conv2d_toeplitz_fwd(xin, twp, trows, conv.kernel_size[0], conv.kernel_size[1],
+                                        ops.out_view_nhwc(dinner, co), conv.bias, st.act, st.slope)
+            else:
+                ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(dinner, co), conv.bias, st.act, st.slope)
             continue
         # conv -> raw y (+ fused per-channel sums) -> norm/act/residual/halo
-        if flat:
+        if flat or tz:
             y = ops.alloc_flat_output(n, ho, wo, xin.shape[2], cs, dev)  # pitched: TMA-store epilogue
         else:
             y = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
@@ -457,7 +494,12 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
         if not use_running:
             groups = n if nk == NORM_INSTANCE else 1
             stats = arena.take((groups, co, 2))
-        if nk == NORM_INSTANCE:
+        if tz:
+            ops.conv2d_toeplitz_fwd(xin, twp, trows, conv.kernel_size[0], conv.kernel_size[1], ops.out_view_nhwc(y, co),
+                                    bias, ACT_NONE, 0.0, stats if nk == NORM_INSTANCE else None)
+            if nk != NORM_INSTANCE and not use_running:
+                ops.channel_stats(y, co, False, stats)
+        elif nk == NORM_INSTANCE:
             ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(y, co), bias, ACT_NONE, 0.0, stats)
         else:
             ops.conv2d_fwd(g, xin, wp, rows_pad, kpad, ops.out_view_nhwc(y, co), bias, ACT_NONE, 0.0, None)
@@ -577,7 +619,15 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
         xin = run.vals[st.src] if materialised else run.inner[st.src]
         if want_w:
             k = conv.kernel_size[0]
-            if flat_dgrad and cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
+            if flat_dgrad and _toeplitz_last(conv, st.transposed, cs) and xin.is_contiguous():
+                # few output channels (the 7x7 c7s1-3 layer): the padded 64-channel input is iterated, the zero-haloed
+                # 3-channel dy is the shifted Toeplitz operand (taps reversed)
+                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                ops.conv2d_toeplitz_wgrad(xin, dyp, k, k, dw, False, flip=True)
+            elif is_first and run.toeplitz0:
+                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                ops.conv2d_toeplitz_wgrad(dy, xin, k, k, dw, True)
+            elif flat_dgrad and cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
                 # few output channels (the 7x7 c7s1-3 layer): correlate the padded input with the zero-haloed
                 # dy, whose 8 channels x 8 pixels form one K block per filter row; the result comes out as
                 # [cin, cout, R-1-r, S-1-s]
@@ -618,7 +668,12 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                 hp, wp_ = src_full.shape[1], src_full.shape[2]
                 dfull = ops.alloc_flat_output(n, hp, wp_, dyp.shape[2], src_full.shape[3], dev)
                 k = conv.kernel_size[0]
-                if cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
+                if _toeplitz_last(conv, st.transposed, cs):
+                    # few output channels (c7s1-3): dy is the 8-channel "image" of a Toeplitz convolution with the
+                    # flipped filter producing the 64-channel gradient of the padded input
+                    wr, rows_r = _pack_cache.get_toeplitz(conv.weight, False, True)
+                    ops.conv2d_toeplitz_fwd(dyp, wr, rows_r, k, k, ops.out_view_nhwc(dfull, ci))
+                elif cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
                     # few output channels (c7s1-3): the zero-haloed dy carries 8 channels per pixel, so one K
                     # block covers a whole filter row (row-packed operand, taps reversed at packing time)
                     wr, rows_r, kpad_r = _pack_cache.get(conv.weight, st.transposed, cs, flipped=True)

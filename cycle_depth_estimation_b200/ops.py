@@ -176,6 +176,30 @@ def conv2d_fwd(g, x, wpacked, rows_pad, kpad, out, bias=None, act=ACT_NONE, slop
                                     C.byref(out), C.byref(ep), _stream()))
 
 
+def pack_toeplitz_weight(w4, rows_are_dim0, flip=False, out=None):
+    """fp32 [d0,d1,R,S] -> bf16 Toeplitz operand [R, rows_pad * 64] (cdb_pack_toeplitz_weight); returns (packed, rows_pad)."""
+    _require_cuda(w4)
+    w4 = w4.detach()
+    assert w4.dtype == torch.float32 and w4.is_contiguous()
+    d0, d1, r, s = w4.shape
+    rows_pad = round_up(d0 if rows_are_dim0 else d1, 16)
+    if out is None:
+        out = torch.empty((r, rows_pad * 64), dtype=torch.bfloat16, device=w4.device)
+    check(_lib.lib().cdb_pack_toeplitz_weight(C.c_void_p(w4.data_ptr()), d0, d1, r, s, 1 if rows_are_dim0 else 0,
+                                              1 if flip else 0, C.c_void_p(out.data_ptr()), _stream()))
+    return out, rows_pad
+
+
+def conv2d_toeplitz_fwd(x, wpacked, rows_pad, r, s, out, bias=None, act=ACT_NONE, slope=0.0, stats=None, flags=0):
+    """Image-layer convolution (<= 8 input channels, stride 1) over the contiguous padded buffer x [n,h,w,8] bf16."""
+    _require_cuda(x, wpacked)
+    xv = act_view(x)
+    ep = CdbEpilogue(bias.data_ptr() if bias is not None else None, act, slope,
+                     stats.data_ptr() if stats is not None else None, flags)
+    check(_lib.lib().cdb_conv2d_toeplitz_fwd(C.byref(xv), C.c_void_p(wpacked.data_ptr()), rows_pad, r, s, C.byref(out),
+                                             C.byref(ep), _stream()))
+
+
 _ws_cache = {}
 
 
@@ -186,6 +210,20 @@ def _workspace(nbytes, device):
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def conv2d_toeplitz_wgrad(s_t, p_t, r, s, dw4, m_is_d0, flip=False, accumulate=False):
+    """Filter gradient of an image layer (cdb_conv2d_toeplitz_wgrad): s_t = the many-channel NHWC bf16 view whose
+    pixels are iterated, p_t = the contiguous [n,h,w,8] bf16 buffer that is shifted; dw4 fp32 [d0,d1,R,S]."""
+    _require_cuda(s_t, p_t, dw4)
+    assert dw4.dtype == torch.float32 and dw4.is_contiguous()
+    sv, pv = act_view(s_t), act_view(p_t)
+    L = _lib.lib()
+    need = L.cdb_conv2d_toeplitz_wgrad_workspace(C.byref(sv), r)
+    ws = _workspace(need, s_t.device)
+    check(L.cdb_conv2d_toeplitz_wgrad(C.byref(sv), C.byref(pv), r, s, C.c_void_p(dw4.data_ptr()), dw4.shape[0],
+                                      dw4.shape[1], 1 if m_is_d0 else 0, 1 if flip else 0, 1 if accumulate else 0,
+                                      C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel()), _stream()))
 
 
 def conv2d_wgrad(g, x, dy, dw4, accumulate=False):

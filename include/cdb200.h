@@ -116,6 +116,37 @@ int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void* wpacked, i
  * ignores the low 13 mantissa bits of its operands; cdb_pack_conv_weight_tf32 / cdb_round_tf32 / CDB_EP_ROUND_TF32
  * round to nearest beforehand.  rowpack is not available in this precision. */
 
+/* ---- K1c: image layers (<= 8 input channels, stride 1): Toeplitz operand -----------------------------
+ * The 7x7 c7s1-64 input layer of the generators (models/networks.py:158) and the data gradient of the 7x7 c7s1-3
+ * output layer (:185, whose contracted tensor is the 3-channel dy).  x: contiguous bf16 buffer [n][h][w][8] with the
+ * padding materialised (channels beyond the real ones zero); y: y->h x y->w valid outputs per image,
+ *   y[n,p,q,o] = sum_{r,s,c} x[n, p + r, q + s, c] * W[o,c,r,s]        (R, S <= 8, <= 128 output channels)
+ * wpacked from cdb_pack_toeplitz_weight.  A filter row is ONE K block (8 taps x 8 channels) whose A operand the tensor
+ * core reads from a plain copy of the pixel row through an overlapping no-swizzle descriptor: every input byte is
+ * fetched once per filter row instead of 8 times (conv_toeplitz.cu).  Epilogue as cdb_conv2d_fwd (bias, activation,
+ * InstanceNorm / BatchNorm sums).  Fast output (TMA stores): y laid out by the input pitch, i.e. y->sw == cstore,
+ * y->sh == x->w * cstore, y->sn a multiple of 128 rows, cstore a multiple of 64. */
+int cdb_conv2d_toeplitz_fwd(const CdbAct* x, const void* wpacked, int32_t w_rows_pad, int32_t r, int32_t s,
+                            const CdbOut* y, const CdbEpilogue* ep, cdbStream_t stream);
+/* fp32 W4[d0][d1][R][S] -> bf16 [R][rows_pad x 64] K-major blocks in the no-swizzle core-matrix order, k = s * 8 + c;
+ * rows = d0 (rows_are_dim0) or d1 (data gradient), the other dimension (<= 8) is contracted; flip packs
+ * W[..][R-1-r][S-1-s].  out holds R * round_up(rows, 16) * 64 bf16. */
+int cdb_pack_toeplitz_weight(const float* w4, int32_t d0, int32_t d1, int32_t r, int32_t s, int32_t rows_are_dim0,
+                             int32_t flip, void* out, cdbStream_t stream);
+
+/* Weight gradient of the image layers (the filter-gradient half of aten.convolution_backward for
+ * models/networks.py:158,185):
+ *   dw[..][r][s] (+)= sum_{n,h,w} S[n,h,w,m] * P[n, h + r', w + s', c],   (r', s') = (r, s) or (R-1-r, S-1-s) with flip
+ * S = s_act: the bf16 NHWC tensor with up to 128 channels whose pixels are iterated (dy of c7s1-64; the padded
+ * 64-channel input of c7s1-3); P = p_act: the contiguous buffer of 8-channel pixels that is shifted (the padded image;
+ * the zero-haloed 3-channel dy, with flip); dw4[d0][d1][R][S] has (d0, d1) = (m, c) when m_is_d0, else (c, m).
+ * Both operands are MN-major; the shifted one is read from one plain copy of each 71-pixel row segment through an
+ * overlapping no-swizzle descriptor (conv_toeplitz.cu).  workspace: cdb_conv2d_toeplitz_wgrad_workspace bytes. */
+size_t cdb_conv2d_toeplitz_wgrad_workspace(const CdbAct* s_act, int32_t r);
+int cdb_conv2d_toeplitz_wgrad(const CdbAct* s_act, const CdbAct* p_act, int32_t r, int32_t s, float* dw4, int32_t d0,
+                              int32_t d1, int32_t m_is_d0, int32_t flip, int32_t accumulate, void* workspace,
+                              size_t ws_bytes, cdbStream_t stream);
+
 /* Packs an fp32 4-D filter W4[d0][d1][R][S] (Conv2d: OIHW, ConvTranspose2d: IOHW) into the bf16
  * GEMM B operand [rows_pad][taps*kpad]:  packed[row][tap*kpad + k] = W4[row][k][r][s] when
  * rows_are_dim0, else W4[k][row][r][s]; tap = r*S+s (rowpack: tap = r, k = s*rowpack + ch, kpad 64).

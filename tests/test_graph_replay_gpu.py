@@ -105,7 +105,7 @@ def test_fused_adam_emits_the_packed_operands():
             continue
         store = w.__dict__['_cdb_packed']
         for key, (ver, packed) in store.items():
-            if len(key) != 3 or key[2]:
+            if len(key) != 3 or not isinstance(key[0], bool) or key[2]:
                 continue
             fresh, _, _ = ops.pack_conv_weight(w.detach().contiguous(), key[0], key[1])
             assert torch.equal(packed[0], fresh), (mod, key)      # bit-identical to a fresh packing of the new values
