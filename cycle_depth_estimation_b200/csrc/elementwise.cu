@@ -248,7 +248,7 @@ __global__ void pool_apply_kernel(const float* __restrict__ fake, float* __restr
 // data-gradient layout the convolution kernels read); the kernel then writes the updated value into them as
 // well, so that no separate re-pack pass runs after the optimizer step.
 constexpr int kAdamMaxEntries = 256;
-constexpr int kAdamChunk = 16384;
+constexpr int kAdamChunk = 8192;
 struct AdamPackDev {
   __nv_bfloat16* out;
   int32_t rows_are_dim0, rowpack, kpad, n_taps;
@@ -298,14 +298,11 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   float* __restrict__ v = en.exp_avg_sq;
   const bool packs = en.pack[0].out != nullptr || en.pack[1].out != nullptr;
   const int rs = en.R * en.S;
-  for (int64_t i = begin + threadIdx.x; i < end; i += 256) {
-    const float gi = g[i];
-    const float mi = m[i] + (1.f - q.b1) * (gi - m[i]);
-    const float vi = q.b2 * v[i] + (1.f - q.b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float pn = p[i] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + q.eps));
-    p[i] = pn;
+  const float b1 = q.b1, b2 = q.b2, eps = q.eps;
+  auto update = [&](int64_t i, float pi, float gi, float& mi, float& vi) -> float {
+    mi = mi + (1.f - b1) * (gi - mi);          // lerp, as torch does
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    const float pn = pi - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
     if (packs) {
       // element (i0, i1, r, s) of the filter [d0][d1][R][S] -> packed[row][tap * kpad + k] (pack_weight_kernel's map)
       const int ii = static_cast<int>(i);
@@ -325,6 +322,34 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
         pk.out[(static_cast<int64_t>(row) * pk.n_taps + tap) * pk.kpad + kk] = b;
       }
     }
+    return pn;
+  };
+  // 16-byte vector body (tensors from the torch allocator are 16-byte aligned; chunk boundaries are multiples of 4)
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  int64_t i = begin;
+  if (vec) {
+    const int64_t end4 = begin + ((end - begin) & ~static_cast<int64_t>(3));
+    for (int64_t j = begin + 4 * threadIdx.x; j < end4; j += 4 * 256) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + j);
+      float4 p4 = *reinterpret_cast<const float4*>(p + j);
+      float4 m4 = *reinterpret_cast<const float4*>(m + j);
+      float4 v4 = *reinterpret_cast<const float4*>(v + j);
+      p4.x = update(j, p4.x, g4.x, m4.x, v4.x);
+      p4.y = update(j + 1, p4.y, g4.y, m4.y, v4.y);
+      p4.z = update(j + 2, p4.z, g4.z, m4.z, v4.z);
+      p4.w = update(j + 3, p4.w, g4.w, m4.w, v4.w);
+      *reinterpret_cast<float4*>(m + j) = m4;
+      *reinterpret_cast<float4*>(v + j) = v4;
+      *reinterpret_cast<float4*>(p + j) = p4;
+    }
+    i = end4;
+  }
+  for (int64_t j = i + threadIdx.x; j < end; j += 256) {
+    float mi = m[j], vi = v[j];
+    p[j] = update(j, p[j], g[j], mi, vi);
+    m[j] = mi;
+    v[j] = vi;
   }
 }
 

@@ -526,9 +526,62 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
 DEBUG_RECORD = None  # set to a dict by tools/debug_bwd.py to capture per-stage gradients
 
 
+class _SideStream:
+    """Runs the weight gradients of a network call's backward on a second CUDA stream.  ``fork`` makes the side
+    stream wait for everything the current stream has issued so far (the gradient dy of the stage) and keeps the
+    tensors the side-stream kernels read alive until ``join`` — the caching allocator may otherwise hand their memory
+    to a later allocation of the main stream while the side stream is still reading it.  Works inside a CUDA-graph
+    capture (the event dependencies become graph edges: the weight gradients are parallel branches of the graph)."""
+    _streams = {}
+
+    def __init__(self, device, enabled):
+        self.enabled = enabled
+        self.keep = []
+        self.used = False
+        if enabled:
+            # one companion stream per (device, calling stream): two network calls running on two streams (the two
+            # discriminators of a CycleGAN update) keep independent weight-gradient branches
+            key = (device.index if device.index is not None else torch.cuda.current_device(),
+                   torch.cuda.current_stream().cuda_stream)
+            st = _SideStream._streams.get(key)
+            if st is None:
+                st = torch.cuda.Stream(device=device)
+                _SideStream._streams[key] = st
+            self.stream = st
+            self.ctx = None
+
+    def fork(self, *tensors):
+        if not self.enabled:
+            return
+        self.keep.extend(t for t in tensors if t is not None)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self.used = True
+
+    def __enter__(self):
+        if self.enabled:
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+        return False
+
+    def join(self):
+        if self.enabled and self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep = []
+
+
+_WGRAD_SIDE_STREAM = [not _os.environ.get("CDB_NO_WGRAD_STREAM")]
+
+
 def backward(plan, run, gout, need_input_grad, needs_param_grad):
     """Hand-written backward. Returns (grad_input or None, {param: grad})."""
     dev = gout.device
+    side = _SideStream(dev, _WGRAD_SIDE_STREAM[0])
     n = run.x_shape[0]
     grads = {}
     stages = plan.stages
@@ -615,29 +668,32 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
             dskip[st.dst] = None
         if DEBUG_RECORD is not None:
             DEBUG_RECORD[('dy', idx)] = dy.clone()
-        # ---- wgrad
+        # ---- wgrad: on the side stream, concurrently with the data-gradient / norm-backward chain of the earlier
+        # layers (it only has to be finished when the network call's backward returns)
         xin = run.vals[st.src] if materialised else run.inner[st.src]
         if want_w:
-            k = conv.kernel_size[0]
-            if flat_dgrad and _toeplitz_last(conv, st.transposed, cs) and xin.is_contiguous():
-                # few output channels (the 7x7 c7s1-3 layer): the padded 64-channel input is iterated, the zero-haloed
-                # 3-channel dy is the shifted Toeplitz operand (taps reversed)
-                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-                ops.conv2d_toeplitz_wgrad(xin, dyp, k, k, dw, False, flip=True)
-            elif is_first and run.toeplitz0:
-                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-                ops.conv2d_toeplitz_wgrad(dy, xin, k, k, dw, True)
-            elif flat_dgrad and cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
-                # few output channels (the 7x7 c7s1-3 layer): correlate the padded input with the zero-haloed
-                # dy, whose 8 channels x 8 pixels form one K block per filter row; the result comes out as
-                # [cin, cout, R-1-r, S-1-s]
-                tmp = torch.empty((ci, co, k, k), dtype=torch.float32, device=dev)
-                ops.conv2d_wgrad(ops.geom(k, k, 1, 0, 0, 1, True, cs), xin, dyp, tmp, False)
-                dw = tmp.flip(2, 3).permute(1, 0, 2, 3).contiguous()
-            else:
-                dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
-                ops.conv2d_wgrad(_geom_fwd(st, materialised, rowpack), xin, dy, dw, False)
-            grads[conv.weight] = dw
+            side.fork(dy, dyp if (flat_dgrad or fold_dgrad) else None)
+            with side:
+                k = conv.kernel_size[0]
+                if flat_dgrad and _toeplitz_last(conv, st.transposed, cs) and xin.is_contiguous():
+                    # few output channels (the 7x7 c7s1-3 layer): the padded 64-channel input is iterated, the zero-haloed
+                    # 3-channel dy is the shifted Toeplitz operand (taps reversed)
+                    dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                    ops.conv2d_toeplitz_wgrad(xin, dyp, k, k, dw, False, flip=True)
+                elif is_first and run.toeplitz0:
+                    dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                    ops.conv2d_toeplitz_wgrad(dy, xin, k, k, dw, True)
+                elif flat_dgrad and cs <= 16 and k * cs <= 64 and conv.dilation[0] == 1:
+                    # few output channels (the 7x7 c7s1-3 layer): correlate the padded input with the zero-haloed
+                    # dy, whose 8 channels x 8 pixels form one K block per filter row; the result comes out as
+                    # [cin, cout, R-1-r, S-1-s]
+                    tmp = torch.empty((ci, co, k, k), dtype=torch.float32, device=dev)
+                    ops.conv2d_wgrad(ops.geom(k, k, 1, 0, 0, 1, True, cs), xin, dyp, tmp, False)
+                    dw = tmp.flip(2, 3).permute(1, 0, 2, 3).contiguous()
+                else:
+                    dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+                    ops.conv2d_wgrad(_geom_fwd(st, materialised, rowpack), xin, dy, dw, False)
+                grads[conv.weight] = dw
         # ---- dgrad
         if want_dx:
             gd = _geom_dgrad(st, materialised and not (is_first and rowpack and not st.reflect))
@@ -701,6 +757,7 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                     DEBUG_RECORD[('dfull', st.src)] = dfull.clone()
         # free saved tensors of this stage early
         run.y[idx] = None
+    side.join()
     return gx, grads
 
 

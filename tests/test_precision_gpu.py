@@ -220,13 +220,15 @@ def _pixel_oracle(sd, x, norm='instance'):
 
 @pytest.mark.parametrize("norm", ['instance', 'batch'])
 def test_pixel_discriminator_tf32x3(norm):
-    """PixelDiscriminator, activations and every gradient <= 1e-3."""
+    """PixelDiscriminator: activations <= 1e-3 (measured 1.5e-6); gradients 2e-6 when no LeakyReLU branch
+    flips, 2e-3 when a single one of the 524288 pre-activations does (the run-to-run order of the statistics' atomics
+    decides) — asserted at GRAD_TOL like every other network."""
     from cycle_depth_estimation_b200 import networks as N
     torch.manual_seed(2)
     with quiet():
         net = N.define_D(3, 64, 'pixel', 3, norm, False, 'normal', 0.02, ['cuda'])
     _net_case(net, lambda sd, x: _pixel_oracle(sd, x, norm), seeded_image(2, 3, 64, 64),
-              seeded_image(2, 1, 64, 64, seed=5), "tf32x3", TOL)
+              seeded_image(2, 1, 64, 64, seed=5), "tf32x3", TOL, GRAD_TOL)
 
 
 @pytest.mark.parametrize("norm", ['instance', 'batch'])
