@@ -330,8 +330,20 @@ class CycleGANModel:
         else:
             self.loss_idt_A = 0
             self.loss_idt_B = 0
-        self.loss_G_A = self.criterionGAN(self.netD_A(self.fake_B), True)
-        self.loss_G_B = self.criterionGAN(self.netD_B(self.fake_A), True)
+        if bool(getattr(self.opt, 'concurrent_D', True)) and self.fake_B.is_cuda:
+            # the two (frozen) discriminator passes of the generator objective on the two discriminator streams: their
+            # small layers, and later their data gradients, overlap each other and the generators' backward
+            cur = torch.cuda.current_stream()
+            sa, sb = self._d_streams()
+            for side, net, fake, name in ((sa, self.netD_A, self.fake_B, 'loss_G_A'), (sb, self.netD_B, self.fake_A, 'loss_G_B')):
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    setattr(self, name, self.criterionGAN(net(fake), True))
+            cur.wait_stream(sa)
+            cur.wait_stream(sb)
+        else:
+            self.loss_G_A = self.criterionGAN(self.netD_A(self.fake_B), True)
+            self.loss_G_B = self.criterionGAN(self.netD_B(self.fake_A), True)
         self.loss_cycle_A = self.criterionCycle(self.rec_A, self.real_A) * lambda_A
         self.loss_cycle_B = self.criterionCycle(self.rec_B, self.real_B) * lambda_B
         self.loss_G = (self.loss_G_A + self.loss_G_B + self.loss_cycle_A + self.loss_cycle_B + self.loss_idt_A
