@@ -772,18 +772,32 @@ def secondary_arm(args):
                     "update; batch %d at %dx%d" % (b, args.size, args.size))
         h2d, d2h = int(sum(v.numel() * v.element_size() for v in data.values())), 48
     elif wl == "g_infer":
-        from cycle_depth_estimation_b200 import networks as N
+        from cycle_depth_estimation_b200.test_model import TestModel
         b = args.batch if args.batch != 8 else 1
+        opt = make_opt("cuda", not args.no_cuda_graph)
+        opt.isTrain = False
+        model = TestModel()
         with contextlib.redirect_stdout(io.StringIO()):
-            net = N.define_G(3, 3, 64, 'resnet_9blocks', 'instance', False, 'normal', 0.02, ['cuda']).eval()
+            model.initialize(opt)
+        model.eval()
+        extra["launch_mode"] = "eager launches" if args.no_cuda_graph else "cuda graph replay of the forward pass"
         a, _ = synthetic_batch(b, 256, 1234)
-        host, dev = a.pin_memory(), a.cuda()
-        with torch.no_grad():
-            ms = _time_steps(lambda: net(dev), args.steps, args.warmup)
-            ms_e2e = _time_steps(lambda: net(host.cuda(non_blocking=True)).cpu(), args.steps, 1)
+        host, dev = {'A': a.pin_memory(), 'A_paths': None}, {'A': a.cuda(), 'A_paths': None}
+
+        def step():
+            model.set_input(dev)
+            model.test()
+
+        def step_e2e():
+            model.set_input(host)        # pinned host image -> device (static input buffer of the captured forward)
+            model.test()
+            return model.fake_B.cpu()    # generated image back to the host
+        ms = _time_steps(step, args.steps, max(args.warmup, 4))
+        ms_e2e = _time_steps(step_e2e, args.steps, 2)
         tflop = 0.0991 * b
         metric, unit = "resnet9_generator_img_per_s", "img/s (256x256 forward, batch %d)" % b
-        workload = "ResnetGenerator resnet_9blocks ngf=64 InstanceNorm forward, batch %d, 256x256 (BASELINE configs[0])" % b
+        workload = ("TestModel (models/test_model.py): ResnetGenerator resnet_9blocks ngf=64 InstanceNorm forward, batch %d, "
+                    "256x256 (BASELINE configs[0])" % b)
         h2d, d2h = int(a.numel() * 4), int(a.numel() * 4)
         extra["images_per_step"] = b
     elif wl == "metrics":
@@ -820,6 +834,8 @@ def secondary_arm(args):
     if wl in ("model5", "segcycle") and not args.no_cuda_graph:
         # replays bypass the library's host entry points: kernels of one captured step x timed steps
         launches = int(model._step_graph.launches) * (2 * args.steps + 1)
+    if wl == "g_infer" and not args.no_cuda_graph:
+        launches = launches + int(getattr(model, "_graph_launches", 0)) * (2 * args.steps)
     clocks = sampler.stop()
     per_step = extra.get("images_per_step", 1)
     if wl == "metrics":

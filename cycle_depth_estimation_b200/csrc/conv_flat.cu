@@ -488,7 +488,13 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   prm.tiles_per_img = ceil_div(y->h * x->w, kFlatBM);
   {
     const char* e = getenv("CDB_FLAT_BN");
-    const int cap = e ? atoi(e) : 256;
+    int cap = e ? atoi(e) : 256;
+    if (!e) {
+      // small problems (generator inference at batch 1: 17 position tiles per image): narrower channel tiles until
+      // the tile count covers at least half of the SMs
+      const int m_tiles = y->n * prm.tiles_per_img;
+      while (cap > 64 && w_rows_pad > cap / 2 && m_tiles * ceil_div(w_rows_pad, cap) * 2 < sm_count()) cap /= 2;
+    }
     prm.bn = w_rows_pad < cap ? w_rows_pad : cap;
     e = getenv("CDB_FLAT_ROTATE");
     prm.rotate = e ? atoi(e) : 1;

@@ -538,6 +538,12 @@ extern "C" int cdb_conv2d_fwd(const CdbConvGeom* g, const CdbAct* x, const void*
   prm.cout = y->c;
   prm.cstore = y->cstore;
   prm.bn = w_rows_pad < 256 ? w_rows_pad : 256;
+  {
+    // small problems (inference at batch 1): narrower channel tiles until the tile count covers half of the SMs
+    const int px = y->n * (g->transposed ? ceil_div(y->h, g->stride) * ceil_div(y->w, g->stride) : y->h * y->w);
+    const int m_tiles = ceil_div(px, 128);
+    while (prm.bn > 64 && prm.bn % 32 == 0 && m_tiles * ceil_div(w_rows_pad, prm.bn) * 2 < sm_count()) prm.bn /= 2;
+  }
   prm.n_tiles_n = ceil_div(w_rows_pad, prm.bn);
   prm.out_dtype = y->dtype;
   prm.act = ep ? ep->act : CDB_ACT_NONE;

@@ -55,9 +55,12 @@ class TestModel:
             for _ in range(2):                            # warm-up: weight packing, lazy allocations
                 self.netG(x)
         torch.cuda.current_stream().wait_stream(side)
+        from . import _lib
         graph = torch.cuda.CUDAGraph()
+        n0 = _lib.lib().cdb_launch_count()
         with torch.no_grad(), torch.cuda.graph(graph):
             out = self.netG(x)
+        self._graph_launches = _lib.lib().cdb_launch_count() - n0      # library kernels inside one replay
         self._graphs[tuple(x.shape)] = (graph, x, out)
         return graph, x, out
 
