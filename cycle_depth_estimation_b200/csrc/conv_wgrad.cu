@@ -660,7 +660,12 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
   const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes;
-  int stages = (200 * 1024) / stage_bytes;
+  // shared-memory budget of the operand ring.  The weight gradients run on a companion stream next to the norm /
+  // activation backward kernels of the main stream (engine._SideStream): a ring that leaves room for one of their CTAs
+  // (64 KB for the cluster-fused InstanceNorm backward) lets the two kinds of kernels share an SM.
+  static const int budget_kb = getenv("CDB_WGRAD_SMEM_KB") ? atoi(getenv("CDB_WGRAD_SMEM_KB")) : 200;
+  int stages = (budget_kb * 1024) / stage_bytes;
+  if (stages < 2) stages = 2;
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;

@@ -799,6 +799,227 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
   cluster.sync();   // keeps every CTA's `part` alive until all ranks have read it (off the critical path)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming two-pass backward for the common case (bf16, batch statistics, no affine parameters, activation NONE /
+// ReLU / LeakyReLU after the norm): the instruction-lean form of norm_act_bwd_kernel.
+//   * the reduce pass accumulates  sum ga  and  sum ga * y  (not ga * xhat): no xhat evaluation per element; the
+//     finishing threads convert  sum ga * xhat = rstd * (sum ga * y - mean * sum ga)  once per block (linear);
+//   * the activation mask is  y > mean  (rstd > 0), so the reduce pass needs ONE coefficient per channel;
+//   * the apply pass is  dy = ga * A + y * B + D  with A = rstd, B = -rstd^2 m2, D = rstd^2 m2 mean - rstd m1;
+//   * fp32 arithmetic in register PAIRS (fma.rn.f32x2 / add.rn.f32x2 of sm_100: two lanes per instruction).
+// ~45 instead of ~70 instructions per 16-byte vector and <= 80 registers, i.e. 3 resident blocks per SM: the old
+// kernels (and the cluster-fused one) are bound by instruction latency at 16 warps per SM
+// (profiles/r01_norm_bwd_experiments.txt).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8_pairs(const uint4& r, float2* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = __bfloat1622float2(p[i]);
+}
+__device__ __forceinline__ uint4 pack8_pairs(const float2* f) {
+  uint4 r;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __float22bfloat162_rn(f[i]);
+  return r;
+}
+
+template <int ACT>
+__device__ __forceinline__ float2 mask_pair(float2 g, float2 y, float2 mean, float slope) {
+  if (ACT == CDB_ACT_RELU) return make_float2(y.x > mean.x ? g.x : 0.f, y.y > mean.y ? g.y : 0.f);
+  if (ACT == CDB_ACT_LEAKY) return make_float2(y.x > mean.x ? g.x : g.x * slope, y.y > mean.y ? g.y : g.y * slope);
+  return g;
+}
+
+// g (pairs) += the reflect images of (h, w) other than (h, w) itself
+__device__ __forceinline__ void fold_extras_pairs(const __nv_bfloat16* db, int dsh, int dsw, int h, int w, int H, int W,
+                                                  int pad, float2* g) {
+  float t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = 0.f;
+  fold_extras_i32(db, dsh, dsw, h, w, H, W, pad, t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = __fadd2_rn(g[i], make_float2(t[2 * i], t[2 * i + 1]));
+}
+
+template <bool kApply, int ACT, bool HAS_SKIP, bool WRITE_GSUM, int OCC>
+__global__ void __launch_bounds__(256, OCC) norm_bwd_stream_kernel(NormBwdParams p) {
+  __shared__ float red[kApply ? 1 : 256 * 16];
+  const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
+  const int cvec = blockIdx.z * p.vt + v;
+  const bool active = cvec * 8 < p.C;
+  const int n = blockIdx.y;
+  const int r0 = blockIdx.x * p.rows_per_block;
+  const int r1 = min(p.H, r0 + p.rows_per_block);
+  const int grp = p.per_image ? n : 0;
+  float2 mean2[4], A2[kApply ? 4 : 1], B2[kApply ? 4 : 1], D2[kApply ? 4 : 1];
+  float2 sg[kApply ? 1 : 4], sgy[kApply ? 1 : 4];
+  if (!kApply) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sg[kApply ? 0 : i] = sgy[kApply ? 0 : i] = make_float2(0.f, 0.f);
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mean[2], a[2], b[2], dd[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = cvec * 8 + 2 * i + e;
+        mean[e] = 0.f;
+        a[e] = 1.f;
+        b[e] = dd[e] = 0.f;
+        if (ch < p.C) {
+          const float s1 = p.stats[(static_cast<int64_t>(grp) * p.C + ch) * 2];
+          const float s2 = p.stats[(static_cast<int64_t>(grp) * p.C + ch) * 2 + 1];
+          mean[e] = s1 * p.inv_count;
+          const float var = fmaxf(s2 * p.inv_count - mean[e] * mean[e], 0.f);
+          const float rstd = rsqrtf(var + p.eps);
+          if (kApply) {
+            const float m1 = p.bstats[(static_cast<int64_t>(grp) * p.C + ch) * 2] * p.inv_count;
+            const float m2 = p.bstats[(static_cast<int64_t>(grp) * p.C + ch) * 2 + 1] * p.inv_count;
+            a[e] = rstd;
+            b[e] = -rstd * rstd * m2;
+            dd[e] = rstd * rstd * m2 * mean[e] - rstd * m1;
+          }
+        }
+      }
+      mean2[i] = make_float2(mean[0], mean[1]);
+      if (kApply) {
+        A2[kApply ? i : 0] = make_float2(a[0], a[1]);
+        B2[kApply ? i : 0] = make_float2(b[0], b[1]);
+        D2[kApply ? i : 0] = make_float2(dd[0], dd[1]);
+      }
+    }
+    const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(p.y.ptr) + n * p.y.sn + cvec * 8;
+    const __nv_bfloat16* db = static_cast<const __nv_bfloat16*>(p.dout.ptr) + n * p.dout.sn + cvec * 8;
+    const __nv_bfloat16* sb = HAS_SKIP ? static_cast<const __nv_bfloat16*>(p.dskip.ptr) + n * p.dskip.sn + cvec * 8 : nullptr;
+    __nv_bfloat16* ob = kApply ? static_cast<__nv_bfloat16*>(p.dy.ptr) + n * p.dy.sn + cvec * 8 : nullptr;
+    __nv_bfloat16* gb = (kApply && WRITE_GSUM) ? static_cast<__nv_bfloat16*>(p.gsum.ptr) + n * p.gsum.sn + cvec * 8 : nullptr;
+    const int pad = p.pad, H = p.H, W = p.W;
+    const int ysh = static_cast<int>(p.y.sh), ysw = static_cast<int>(p.y.sw);
+    const int dsh = static_cast<int>(p.dout.sh), dsw = static_cast<int>(p.dout.sw);
+    const int ssh = static_cast<int>(p.dskip.sh), ssw = static_cast<int>(p.dskip.sw);
+    const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
+    const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
+    const float slope = p.slope;
+    constexpr int U = OCC >= 3 ? 2 : 4;   // pixels in flight per thread: 3 blocks x 2 or 2 blocks x 4
+    for (int h = r0; h < r1; ++h) {
+      const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
+      for (int w0 = lane; w0 < W; w0 += lanes * U) {
+        uint4 yr[U], dr[U], sr[HAS_SKIP ? U : 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * lanes;
+          if (w < W) {
+            yr[u] = ld16(yb + h * ysh + w * ysw);
+            dr[u] = ld16(db + h * dsh + w * dsw);
+            if (HAS_SKIP) sr[HAS_SKIP ? u : 0] = ld16(sb + h * ssh + w * ssw);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * lanes;
+          if (w >= W) break;
+          float2 y2[4], g2[4];
+          unpack8_pairs(yr[u], y2);
+          unpack8_pairs(dr[u], g2);
+          if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) fold_extras_pairs(db, dsh, dsw, h, w, H, W, pad, g2);
+          if (HAS_SKIP) {
+            float2 t2[4];
+            unpack8_pairs(sr[HAS_SKIP ? u : 0], t2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) g2[i] = __fadd2_rn(g2[i], t2[i]);
+          }
+          if (kApply) {
+            if (WRITE_GSUM) st16(gb + h * gsh + w * gsw, pack8_pairs(g2));
+            float2 o2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 ga = mask_pair<ACT>(g2[i], y2[i], mean2[i], slope);
+              o2[i] = __ffma2_rn(ga, A2[kApply ? i : 0], __ffma2_rn(y2[i], B2[kApply ? i : 0], D2[kApply ? i : 0]));
+            }
+            st16(ob + h * osh + w * osw, pack8_pairs(o2));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 ga = mask_pair<ACT>(g2[i], y2[i], mean2[i], slope);
+              sg[kApply ? 0 : i] = __fadd2_rn(sg[kApply ? 0 : i], ga);
+              sgy[kApply ? 0 : i] = __ffma2_rn(ga, y2[i], sgy[kApply ? 0 : i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!kApply) {
+    // block reduction over the pixel lanes, then  (sum ga, rstd * (sum ga y - mean sum ga))  per channel
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      red[((2 * i) * 2) * 256 + threadIdx.x] = sg[kApply ? 0 : i].x;
+      red[((2 * i) * 2 + 1) * 256 + threadIdx.x] = sgy[kApply ? 0 : i].x;
+      red[((2 * i + 1) * 2) * 256 + threadIdx.x] = sg[kApply ? 0 : i].y;
+      red[((2 * i + 1) * 2 + 1) * 256 + threadIdx.x] = sgy[kApply ? 0 : i].y;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.vt * 8; t += 256) {
+      const int vv = t % p.vt, j = t / p.vt;     // channel j of vector vv
+      float a_g = 0.f, a_gy = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        a_g += red[(j * 2) * 256 + l * p.vt + vv];
+        a_gy += red[(j * 2 + 1) * 256 + l * p.vt + vv];
+      }
+      const int ch = (blockIdx.z * p.vt + vv) * 8 + j;
+      if (ch < p.C) {
+        const float s1 = p.stats[(static_cast<int64_t>(grp) * p.C + ch) * 2];
+        const float s2 = p.stats[(static_cast<int64_t>(grp) * p.C + ch) * 2 + 1];
+        const float mean = s1 * p.inv_count;
+        const float rstd = rsqrtf(fmaxf(s2 * p.inv_count - mean * mean, 0.f) + p.eps);
+        atomicAdd(p.bstats + (static_cast<int64_t>(grp) * p.C + ch) * 2, a_g);
+        atomicAdd(p.bstats + (static_cast<int64_t>(grp) * p.C + ch) * 2 + 1, rstd * (a_gy - mean * a_g));
+      }
+    }
+  }
+}
+
+static bool stream_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32, int dt) {
+  static const int mode = getenv("CDB_NORM_BWD_IMPL") ? atoi(getenv("CDB_NORM_BWD_IMPL")) : 1;   // 0: old kernels
+  if (mode == 0) return false;
+  return dt == CDB_BF16 && d->norm != CDB_NORM_NONE && !d->use_running && d->gamma == nullptr && d->beta == nullptr &&
+         !accum_f32 && p.pre_act == CDB_ACT_NONE && p.has_dout &&
+         (p.act == CDB_ACT_NONE || p.act == CDB_ACT_RELU || p.act == CDB_ACT_LEAKY) &&
+         (int64_t)(p.H + 2 * p.pad) * p.y.sh < (1 << 30) && (int64_t)(p.H + 2 * p.pad) * p.dout.sh < (1 << 30) &&
+         (int64_t)(p.H + 2 * p.pad) * p.dskip.sh < (1 << 30) && (int64_t)(p.H + 2 * p.pad) * p.dy.sh < (1 << 30) &&
+         (int64_t)(p.H + 2 * p.pad) * p.gsum.sh < (1 << 30);
+}
+
+template <bool kApply, int ACT, int OCC>
+static void launch_stream_occ(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  if (p.has_dskip) {
+    if (p.write_gsum) norm_bwd_stream_kernel<kApply, ACT, true, true, OCC><<<grid, 256, 0, stream>>>(p);
+    else norm_bwd_stream_kernel<kApply, ACT, true, false, OCC><<<grid, 256, 0, stream>>>(p);
+  } else {
+    if (p.write_gsum) norm_bwd_stream_kernel<kApply, ACT, false, true, OCC><<<grid, 256, 0, stream>>>(p);
+    else norm_bwd_stream_kernel<kApply, ACT, false, false, OCC><<<grid, 256, 0, stream>>>(p);
+  }
+}
+static int stream_occ() {
+  static const int occ = getenv("CDB_NORM_STREAM_OCC") ? atoi(getenv("CDB_NORM_STREAM_OCC")) : 2;
+  return occ;
+}
+template <bool kApply, int ACT>
+static void launch_stream_act(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  if (stream_occ() >= 3) launch_stream_occ<kApply, ACT, 3>(p, grid, stream);
+  else launch_stream_occ<kApply, ACT, 2>(p, grid, stream);
+}
+template <bool kApply>
+static void launch_stream(const NormBwdParams& p, dim3 grid, cudaStream_t stream) {
+  switch (p.act) {
+    case CDB_ACT_RELU: launch_stream_act<kApply, CDB_ACT_RELU>(p, grid, stream); break;
+    case CDB_ACT_LEAKY: launch_stream_act<kApply, CDB_ACT_LEAKY>(p, grid, stream); break;
+    default: launch_stream_act<kApply, CDB_ACT_NONE>(p, grid, stream); break;
+  }
+}
+
 static bool fused_in_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32) {
   if (getenv("CDB_NORM_NO_FUSED")) return false;
   const int pixels = p.H * p.W;
@@ -1052,6 +1273,16 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.bstats = bstats;
   p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 2);
   dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
+  if (stream_eligible(d, p, accum_f32, dt)) {
+    // three resident blocks per SM (the kernels are compiled for <= 85 registers)
+    p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, stream_occ() >= 3 ? 3 : 2);
+    dim3 sgrid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
+    launch_stream<false>(p, sgrid, stream);
+    CDB_LAUNCH_OK();
+    launch_stream<true>(p, sgrid, stream);
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
   if (dt == CDB_BF16 && fused_in_eligible(d, p, accum_f32)) {
     launch_norm_bwd_fused(p, y->n, stream);
     CDB_LAUNCH_OK();
