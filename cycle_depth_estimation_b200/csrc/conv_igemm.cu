@@ -70,6 +70,11 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
+// kPair: a CTA pair (cluster of 2, cta_group::2) works on two neighbouring pixel tiles with the same channel tile:
+// each CTA stages ITS 128-pixel window and HALF of the weight tile per (tap, chunk), the even CTA issues M = 256
+// instructions for both, each CTA drains its own 128 x bn accumulator (this kernel is bound by L2 -> SM operand
+// traffic: one stage of a 256-channel layer is 16 + 32 KB for 4.2 MFLOP; the pair needs 16 + 16 KB per SM).
+template <bool kPair>
 __global__ void __launch_bounds__(256, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -83,9 +88,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
-  const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+  // work units: (pixel tile, channel tile); pair: (two neighbouring pixel tiles, channel tile)
+  const int total_tiles = (kPair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles_n;
+  const int tile_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int k_blocks = p.n_taps * p.k_chunks;
 
   if (threadIdx.x == 0) {
@@ -96,7 +106,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
-      mbar_init(smem_u32(&bar_tempty[b]), 128);
+      mbar_init(smem_u32(&bar_tempty[b]), kPair ? 256 : 128);  // pair: the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
@@ -105,11 +115,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     prefetch_tmap(&maps.a[0]);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&tmem_base_smem), 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(&tmem_base_smem), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers exist before any TMA / commit / arrive reaches them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   volatile int* abort_flag = &abort_smem;
@@ -120,15 +136,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles && ok; tile += tile_step) {
         const int n_tile = tile % p.n_tiles_n;
-        int m_tile = tile / p.n_tiles_n;
+        // an odd tile count leaves the last pair's second CTA with a tile beyond the batch: TMA zero-fills it
+        int m_tile = kPair ? 2 * (tile / p.n_tiles_n) + static_cast<int>(rank) : tile / p.n_tiles_n;
         const int tw = m_tile % p.tiles_w;
         m_tile /= p.tiles_w;
         const int th = m_tile % p.tiles_h;
         const int tn = m_tile / p.tiles_h;
         const int q0 = tw * p.tile_w, p0 = th * p.tile_h, img0 = tn * p.tile_n;
-        const int n0 = n_tile * p.bn;
+        const int n0 = n_tile * p.bn + (kPair ? static_cast<int>(rank) * (p.bn / 2) : 0);
         for (int t = 0; t < p.n_taps && ok; ++t) {
           const IgemmTap tap = p.taps[t];
           const CUtensorMap* amap = &maps.a[tap.map];
@@ -139,9 +156,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             }
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t sa = smem_base + stage * stage_bytes;
-            mbar_arrive_expect_tx(full, stage_bytes);
-            tma_load_4d(amap, full, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
-            tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * p.kelems, n0);
+            if (kPair) {
+              // both CTAs' loads complete on the issuing (even) CTA's barrier, armed by it with the bytes of both
+              const uint32_t full0 = mapa_shared(full, 0);
+              if (rank == 0) mbar_arrive_expect_tx(full, 2u * stage_bytes);
+              tma_load_4d_pair(amap, full0, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
+              tma_load_2d_pair(&maps.b, full0, sa + kABytes, tap.wk + c * p.kelems, n0);
+            } else {
+              mbar_arrive_expect_tx(full, stage_bytes);
+              tma_load_4d(amap, full, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
+              tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * p.kelems, n0);
+            }
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -152,45 +177,67 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // pair: the whole warp of the even CTA walks the loop and an elected lane issues (a cta_group::2 instruction
+    // issued from a lone thread of a diverged warp takes 185-283 cycles, tools/mma_rate2.cu)
+    if (kPair ? (rank == 0) : (lane == 0)) {
       const bool tf32 = p.tf32 != 0;
-      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 0u, 0u, 128u, static_cast<uint32_t>(p.bn));
+      const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 0u, 0u, kPair ? 256u : 128u, static_cast<uint32_t>(p.bn));
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x, ++local) {
+      for (int tile = tile_first; tile < total_tiles && ok; tile += tile_step, ++local) {
         const int buf = local & 1;
         const uint32_t tphase = (local >> 1) & 1u;
-        if (!mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag)) break;
+        ok = mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag);
+        if (kPair) ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          if (!mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag)) {
-            ok = false;
-            break;
-          }
+          ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
+          if (kPair) ok = __all_sync(0xffffffffu, ok);
+          if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
           const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024, kLayoutSW128);
           // one instruction consumes 32 bytes of K per row in both precisions: 16 bf16 or 8 tf32
-          if (tf32) {
+          if (kPair) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                if (tf32) umma2_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma2_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma2_commit(smem_u32(&bar_empty[stage]));
+            }
+            __syncwarp();
           } else {
+            if (tf32) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&bar_empty[stage]));
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (ok) umma_commit(smem_u32(&bar_tfull[buf]));
+        if (ok) {
+          if (kPair) {
+            if (elect_one()) umma2_commit(smem_u32(&bar_tfull[buf]));
+            __syncwarp();
+          } else {
+            umma_commit(smem_u32(&bar_tfull[buf]));
+          }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -211,14 +258,15 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const float slope = p.slope;
     const int cout = p.cout, cstore = p.cstore;
     const bool stats_on = p.stats_on != 0;
+    const uint32_t tempty_remote = kPair ? mapa_shared(smem_u32(&bar_tempty[0]), 0) : 0u;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
       const int buf = local & 1;
       const uint32_t tphase = (local >> 1) & 1u;
       if (!mbar_wait(smem_u32(&bar_tfull[buf]), tphase, abort_flag)) break;
       tc_fence_after();
       const int n_tile = tile % p.n_tiles_n;
-      int m_tile = tile / p.n_tiles_n;
+      int m_tile = kPair ? 2 * (tile / p.n_tiles_n) + static_cast<int>(rank) : tile / p.n_tiles_n;
       const int tw = m_tile % p.tiles_w;
       m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
@@ -397,14 +445,19 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&bar_tempty[buf]));
+      if (kPair) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(buf) * 8u);
+      else mbar_arrive(smem_u32(&bar_tempty[buf]));
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // neither CTA leaves while the other may still read its shared memory / signal it
   if (threadIdx.x == 0 && abort_smem && p.abort_flag) atomicExch(p.abort_flag, 1);
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -432,6 +485,14 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
                         int w_ktotal, IgemmParams& prm, cudaStream_t stream) {
   IgemmMaps maps;
   memset(&maps, 0, sizeof(maps));
+  const int m_tiles = prm.tiles_n * prm.tiles_h * prm.tiles_w;
+  // CTA pairs (cta_group::2): OFF by default.  Measured on B200 (tools/time_igemm.py, batch 24): with 256-channel weight
+  // tiles the pair is 1-6 % faster in isolation (dgrad of u128 60.0 -> 56.4 us) and neutral in the step; with bn <= 128 it
+  // is SLOWER (d128 114 -> 138 us: an M = 256 instruction costs ~128+ cycles whatever N is, and these layers are bound by
+  // the A-operand traffic, which the pair does not reduce).  CDB_IGEMM_PAIR=1: bn == 256 layers; =2: every eligible layer.
+  static const int pair_env = getenv("CDB_IGEMM_PAIR") ? atoi(getenv("CDB_IGEMM_PAIR")) : 0;
+  const bool pair = pair_env != 0 && (pair_env > 1 ? (prm.bn % 16 == 0 && prm.bn >= 64)
+                                                   : (prm.bn == 256 && (int64_t)m_tiles * prm.n_tiles_n > sm_count()));
   const uint64_t esz = prm.tf32 ? 4 : 2;
   const CUtensorMapDataType dt = prm.tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   prm.kelems = prm.tf32 ? 32 : 64;
@@ -448,7 +509,7 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
   {
     uint64_t dims[2] = {(uint64_t)w_ktotal, (uint64_t)w_rows_pad};
     uint64_t str[1] = {(uint64_t)w_ktotal * esz};
-    uint32_t box[2] = {(uint32_t)prm.kelems, (uint32_t)prm.bn};
+    uint32_t box[2] = {(uint32_t)prm.kelems, (uint32_t)(pair ? prm.bn / 2 : prm.bn)};
     int rc = make_tmap(&maps.b, dt, 2, const_cast<void*>(wpacked), dims, str, box);
     if (rc != CDB_OK) return rc;
   }
@@ -467,22 +528,43 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
     int rc = make_tmap(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, prm.out, dims, str, box);
     if (rc != CDB_OK) return rc;
   }
-  const int stage_bytes = kABytes + prm.bn * 128;
+  const int stage_bytes = kABytes + (pair ? prm.bn / 2 : prm.bn) * 128;
   int stages = (200 * 1024 - 16384) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   prm.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 16384 + 1024;
-  static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
+  static size_t smem_attr[2] = {0, 0};
+  if (smem > smem_attr[pair ? 1 : 0]) {
+    if (pair) CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr[pair ? 1 : 0] = smem;
   }
-  const int total = prm.tiles_n * prm.tiles_h * prm.tiles_w * prm.n_tiles_n;
-  int grid = total < sm_count() ? total : sm_count();
-  if (grid < 1) return CDB_OK;
   prm.abort_flag = device_abort_flag_ptr();
-  igemm_kernel<<<grid, 256, smem, stream>>>(maps, prm);
+  if (pair) {
+    const int total = ((m_tiles + 1) / 2) * prm.n_tiles_n;
+    if (total < 1) return CDB_OK;
+    const int clusters = total < sm_count() / 2 ? total : sm_count() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CDB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, maps, prm));
+  } else {
+    const int total = m_tiles * prm.n_tiles_n;
+    int grid = total < sm_count() ? total : sm_count();
+    if (grid < 1) return CDB_OK;
+    igemm_kernel<false><<<grid, 256, smem, stream>>>(maps, prm);
+  }
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -44,6 +44,12 @@ struct WgMaps {
   CUtensorMap shift[4];  // G parity views
 };
 
+// kPair: a CTA pair (cluster of 2, cta_group::2) computes a 256-row accumulator: each CTA stages the 128 M-side
+// channels of ITS row tile and HALF of the N-side channels of every K block; the even CTA issues M = 256
+// instructions for both; each CTA drains its own 128 x N accumulator.  Per SM a K block of a 256 x 256-channel
+// layer is 16 + 16 KB instead of 16 + 32 KB for the same 4.2 MFLOP (the single-CTA kernel is bound by L2 -> SM
+// operand traffic at 94 B/clk: tensor pipe 47 % active).
+template <bool kPair>
 __global__ void __launch_bounds__(256, 1)
 wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -60,9 +66,13 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   const uint32_t cpc = static_cast<uint32_t>(p.cpc);
   const uint32_t a_chunks = 128u / cpc;
   const uint32_t a_bytes = a_chunks * kChunkBytes;
-  const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / cpc;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const uint32_t b_chunks = static_cast<uint32_t>(p.bn) / cpc / (kPair ? 2u : 1u);  // N-side chunks THIS CTA stages
   const uint32_t stage_bytes = a_bytes + static_cast<uint32_t>(p.tg) * b_chunks * kChunkBytes;
-  const int total_items = p.n_groups * p.m_tiles * p.n_tiles * p.splits;
+  const int m_units = kPair ? p.m_tiles / 2 : p.m_tiles;  // pair: two row tiles per work item
+  const int total_items = p.n_groups * m_units * p.n_tiles * p.splits;
+  const int item_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int k_tiles_total = p.tiles_n * p.tiles_h * p.tiles_w;
 
   if (threadIdx.x == 0) {
@@ -73,16 +83,22 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&bar_tfull[b]), 1);
-      mbar_init(smem_u32(&bar_tempty[b]), 128);
+      mbar_init(smem_u32(&bar_tempty[b]), kPair ? 256 : 128);  // pair: the epilogue threads of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&tmem_base_smem), 512);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(&tmem_base_smem), 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // the peer's barriers exist before any TMA / commit / arrive reaches them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   volatile int* abort_flag = &abort_smem;
@@ -96,8 +112,9 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
     item /= p.splits;
     nt = item % p.n_tiles;
     item /= p.n_tiles;
-    mt = item % p.m_tiles;
-    tap = item / p.m_tiles;
+    mt = item % m_units;
+    tap = item / m_units;
+    if (kPair) mt = 2 * mt + static_cast<int>(rank);
   };
 
   if (warp == 0) {
@@ -105,7 +122,7 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+      for (int item = item_first; item < total_items && ok; item += item_step) {
         int split, tap, mt, nt;
         decode(item, split, tap, mt, nt);
         const int tap0 = tap * p.tg;
@@ -128,18 +145,33 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
             ok = false;
             break;
           }
-          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t full_local = smem_u32(&bar_full[stage]);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          mbar_arrive_expect_tx(full, item_bytes);
-          for (uint32_t j = 0; j < a_chunks; ++j)
-            tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * cpc, q0 + a_dw, p0 + a_dh, img0);
-          for (int tl = 0; tl < ntap; ++tl) {
-            const WgTap tq = p.taps[tap0 + tl];
+          if (kPair) {
+            // both CTAs' loads complete on the issuing (even) CTA's barrier, armed by it with the bytes of both
+            const uint32_t full = mapa_shared(full_local, 0);
+            if (rank == 0) mbar_arrive_expect_tx(full_local, 2u * item_bytes);
+            for (uint32_t j = 0; j < a_chunks; ++j)
+              tma_load_4d_pair(amap, full, sa + j * kChunkBytes, mt * 128 + j * cpc, q0 + a_dw, p0 + a_dh, img0);
+            const WgTap tq = p.taps[tap0];
             const CUtensorMap* bmap = p.shift_on_a ? &maps.fixed : &maps.shift[tq.map];
             const int b_dh = p.shift_on_a ? 0 : tq.dh, b_dw = p.shift_on_a ? 0 : tq.dw;
             for (uint32_t j = 0; j < b_chunks; ++j)
-              tma_load_4d(bmap, full, sa + a_bytes + (tl * b_chunks + j) * kChunkBytes, nt * p.bn + j * cpc, q0 + b_dw,
-                          p0 + b_dh, img0);
+              tma_load_4d_pair(bmap, full, sa + a_bytes + j * kChunkBytes, nt * p.bn + (rank * b_chunks + j) * cpc,
+                               q0 + b_dw, p0 + b_dh, img0);
+          } else {
+            const uint32_t full = full_local;
+            mbar_arrive_expect_tx(full, item_bytes);
+            for (uint32_t j = 0; j < a_chunks; ++j)
+              tma_load_4d(amap, full, sa + j * kChunkBytes, mt * 128 + j * cpc, q0 + a_dw, p0 + a_dh, img0);
+            for (int tl = 0; tl < ntap; ++tl) {
+              const WgTap tq = p.taps[tap0 + tl];
+              const CUtensorMap* bmap = p.shift_on_a ? &maps.fixed : &maps.shift[tq.map];
+              const int b_dh = p.shift_on_a ? 0 : tq.dh, b_dw = p.shift_on_a ? 0 : tq.dw;
+              for (uint32_t j = 0; j < b_chunks; ++j)
+                tma_load_4d(bmap, full, sa + a_bytes + (tl * b_chunks + j) * kChunkBytes, nt * p.bn + j * cpc, q0 + b_dw,
+                            p0 + b_dh, img0);
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -149,13 +181,15 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // pair: the whole warp of the even CTA walks the loop and an elected lane issues (a cta_group::2 instruction
+    // issued from a lone thread of a diverged warp takes 185-283 cycles, tools/mma_rate2.cu)
+    if (kPair ? (rank == 0) : (lane == 0)) {
       const bool tf32 = p.tf32 != 0;
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       bool ok = true;
-      for (int item = blockIdx.x; item < total_items && ok; item += gridDim.x, ++local) {
+      for (int item = item_first; item < total_items && ok; item += item_step, ++local) {
         int split, tap, mt, nt;
         decode(item, split, tap, mt, nt);
         const int kt0 = split * p.k_tiles_per_split;
@@ -163,50 +197,67 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
         if (kt1 > k_tiles_total) kt1 = k_tiles_total;
         const int buf = local & 1;
         const uint32_t tphase = (local >> 1) & 1u;
-        if (!mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag)) break;
+        ok = mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag);
+        if (kPair) ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
         const int ntap = min(p.tg, p.n_taps - tap * p.tg);
-        const uint32_t idesc = make_idesc(tf32 ? 2u : 1u, 1u, 1u, 128u, static_cast<uint32_t>(p.bn * ntap));
+        const uint32_t idesc =
+            make_idesc(tf32 ? 2u : 1u, 1u, 1u, kPair ? 256u : 128u, static_cast<uint32_t>(p.bn * ntap));
         for (int kt = kt0; kt < kt1; ++kt) {
-          if (!mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag)) {
-            ok = false;
-            break;
-          }
+          ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
+          if (kPair) ok = __all_sync(0xffffffffu, ok);
+          if (!ok) break;
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
-          // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 k-rows.
-          // (descriptors built in the branch below)
-          if (tf32) {
-            // MN-major TF32: 128B swizzle with 32-byte atoms (4 k-rows x 128 B per atom): LBO = distance between
-            // 32-channel chunks, SBO = 512 B between the two 4-row groups of one K = 8 instruction.
-            // (pinned on B200 with tools/probe_tf32_wgrad.py: any other LBO/SBO assignment gives O(1) errors)
-            const uint64_t ta = make_smem_desc(sa, kChunkBytes, 512, kLayoutSW128Base32);
-            const uint64_t tb = make_smem_desc(sa + a_bytes, kChunkBytes, 512, kLayoutSW128Base32);
+          if (!kPair || elect_one()) {
+            if (tf32) {
+              // MN-major TF32: 128B swizzle with 32-byte atoms (4 k-rows x 128 B per atom): LBO = distance between
+              // 32-channel chunks, SBO = 512 B between the two 4-row groups of one K = 8 instruction.
+              // (pinned on B200 with tools/probe_tf32_wgrad.py: any other LBO/SBO assignment gives O(1) errors)
+              const uint64_t ta = make_smem_desc(sa, kChunkBytes, 512, kLayoutSW128Base32);
+              const uint64_t tb = make_smem_desc(sa + a_bytes, kChunkBytes, 512, kLayoutSW128Base32);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // 8 pixels (= 8 rows x 128 B) per instruction
-              umma_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-          } else {
-            const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
-            const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
+              for (int k = 0; k < 8; ++k) {  // 8 pixels (= 8 rows x 128 B) per instruction
+                if (kPair) umma2_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+                else umma_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+              // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 k-rows.
+              const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+              const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
-              umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
+                if (kPair) umma2_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+                else umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (kPair) umma2_commit(smem_u32(&bar_empty[stage]));
+            else umma_commit(smem_u32(&bar_empty[stage]));
           }
-          umma_commit(smem_u32(&bar_empty[stage]));
+          if (kPair) __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        if (ok) umma_commit(smem_u32(&bar_tfull[buf]));
+        if (ok) {
+          if (kPair) {
+            if (elect_one()) umma2_commit(smem_u32(&bar_tfull[buf]));
+            __syncwarp();
+          } else {
+            umma_commit(smem_u32(&bar_tfull[buf]));
+          }
+        }
       }
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
     const int row = ew * 32 + lane;
+    const uint32_t tempty_remote = kPair ? mapa_shared(smem_u32(&bar_tempty[0]), 0) : 0u;
     int local = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++local) {
+    for (int item = item_first; item < total_items; item += item_step, ++local) {
       int split, tap, mt, nt;
       decode(item, split, tap, mt, nt);
       const int kt0 = split * p.k_tiles_per_split;
@@ -236,14 +287,19 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&bar_tempty[buf]));
+      if (kPair) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(buf) * 8u);
+      else mbar_arrive(smem_u32(&bar_tempty[buf]));
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();  // neither CTA leaves while the other may still read its shared memory / signal it
   if (threadIdx.x == 0 && abort_smem && p.abort_flag) atomicExch(p.abort_flag, 1);
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // Sums the split-K partials and scatters them into the fp32 filter gradient W4[d0][d1][R][S].
@@ -380,6 +436,7 @@ struct WgPlan {
   int tg, n_groups;
   int cM, cN, mpad, npad, bn, m_tiles, n_tiles;
   int tile_w, tile_h, tile_n, tiles_w, tiles_h, tiles_n, k_tiles, splits, k_per_split, n_taps;
+  int pair;  // CTA pairs (cta_group::2): two row tiles per work item, the N-side operand split between the CTAs
 };
 
 static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g_act, WgPlan* pl) {
@@ -420,9 +477,11 @@ static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g
     if (tg >= 1) pl->tg = tg;
   }
   pl->n_groups = ceil_div(pl->n_taps, pl->tg);
-  const int items = pl->n_groups * pl->m_tiles * pl->n_tiles;
+  static const int pair_env = getenv("CDB_WGRAD_PAIR") ? atoi(getenv("CDB_WGRAD_PAIR")) : 1;
+  pl->pair = (pair_env && pl->tg == 1 && pl->m_tiles % 2 == 0 && pl->bn % 128 == 0 && !g->rowpack) ? 1 : 0;
+  const int items = pl->n_groups * (pl->pair ? pl->m_tiles / 2 : pl->m_tiles) * pl->n_tiles;
   static const int waves = getenv("CDB_WGRAD_WAVES") ? atoi(getenv("CDB_WGRAD_WAVES")) : 1;
-  int splits = (waves * sm_count()) / (items > 0 ? items : 1);
+  int splits = (waves * (pl->pair ? sm_count() / 2 : sm_count())) / (items > 0 ? items : 1);
   if (splits < 1) splits = 1;
   int max_splits = pl->k_tiles / 8;
   if (max_splits < 1) max_splits = 1;
@@ -659,7 +718,7 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.n_groups = pl.n_groups;
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
-  const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes;
+  const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes / (pl.pair ? 2 : 1);
   // shared-memory budget of the operand ring.  The weight gradients run on a companion stream next to the norm /
   // activation backward kernels of the main stream (engine._SideStream): a ring that leaves room for one of their CTAs
   // (64 KB for the cluster-fused InstanceNorm backward) lets the two kinds of kernels share an SM.
@@ -669,14 +728,34 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   prm.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
-  static size_t smem_attr = 0;
-  if (smem > smem_attr) {
-    CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
+  static size_t smem_attr[2] = {0, 0};
+  if (smem > smem_attr[pl.pair]) {
+    if (pl.pair) CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr[pl.pair] = smem;
   }
-  const int items = pl.n_groups * pl.m_tiles * pl.n_tiles * pl.splits;
-  int grid = items < sm_count() ? items : sm_count();
-  wgrad_kernel<<<grid, 256, smem, stream>>>(maps, prm);
+  if (pl.pair) {
+    const int items = pl.n_groups * (pl.m_tiles / 2) * pl.n_tiles * pl.splits;
+    const int clusters = items < sm_count() / 2 ? items : sm_count() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CDB_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_kernel<true>, maps, prm));
+  } else {
+    const int items = pl.n_groups * pl.m_tiles * pl.n_tiles * pl.splits;
+    int grid = items < sm_count() ? items : sm_count();
+    wgrad_kernel<false><<<grid, 256, smem, stream>>>(maps, prm);
+  }
   CDB_LAUNCH_OK();
 
   const int64_t total = (int64_t)d0 * d1 * g->r * g->s;

@@ -846,10 +846,16 @@ template <bool kApply, int ACT, bool HAS_SKIP, bool WRITE_GSUM, int OCC>
 __global__ void __launch_bounds__(256, OCC) norm_bwd_stream_kernel(NormBwdParams p) {
   __shared__ float red[kApply ? 1 : 256 * 16];
   const int v = threadIdx.x % p.vt, lane = threadIdx.x / p.vt, lanes = 256 / p.vt;
-  const int cvec = blockIdx.z * p.vt + v;
+  // The apply pass walks the tensor in the REVERSE block order of the reduce pass: what the reduce pass read last is
+  // still in L2 (y + dout of a 16-image residual layer are 69 MB; a second cyclic sweep in the same order would find
+  // every line already evicted).
+  const int bx = kApply ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int by = kApply ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int bz = kApply ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+  const int cvec = bz * p.vt + v;
   const bool active = cvec * 8 < p.C;
-  const int n = blockIdx.y;
-  const int r0 = blockIdx.x * p.rows_per_block;
+  const int n = by;
+  const int r0 = bx * p.rows_per_block;
   const int r1 = min(p.H, r0 + p.rows_per_block);
   const int grp = p.per_image ? n : 0;
   float2 mean2[4], A2[kApply ? 4 : 1], B2[kApply ? 4 : 1], D2[kApply ? 4 : 1];
