@@ -80,6 +80,7 @@ def lib():
     L.cdb_depth_metrics_workspace.restype = C.c_size_t
     L.cdb_validation_workspace.restype = C.c_size_t
     L.cdb_depth_labels_workspace.restype = C.c_size_t
+    L.cdb_pil_resample_workspace.restype = C.c_size_t
     _lib = L
     return L
 

@@ -19,6 +19,10 @@ NVCC_FLAGS = [
 ]
 
 
+# experiments: extra nvcc flags (e.g. CDB_EXTRA_NVCC_FLAGS="-DCDB_WAIT_SPIN=1"); objects are rebuilt when it changes
+EXTRA = os.environ.get("CDB_EXTRA_NVCC_FLAGS", "").split()
+
+
 def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -44,7 +48,7 @@ def _compile(src, force, verbose):
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
         return obj, ""
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    cmd = [nvcc] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, proc.stdout, proc.stderr))

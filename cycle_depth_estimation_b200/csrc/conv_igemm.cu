@@ -39,6 +39,7 @@ struct IgemmParams {
   int32_t out_dtype, act;
   float slope;
   int32_t stages;
+  int32_t kgroup;    // (tap, chunk) K blocks per pipeline stage: one barrier round trip of the producer / MMA threads per group
   int32_t stats_on;
   int32_t stats_batch;  // 1: one statistics group for the whole batch (BatchNorm)
   int32_t fast_out;
@@ -51,6 +52,7 @@ struct IgemmParams {
   int64_t o_sn, o_sh, o_sw, o_sc;
   float* stats;
   int* abort_flag;
+  long long* dbg;  // optional per-role wait cycles of CTA 0 (CDB_IGEMM_DEBUG=1)
   IgemmTap taps[kMaxTaps];
 };
 
@@ -90,12 +92,19 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const uint32_t b_bytes = static_cast<uint32_t>(kPair ? p.bn / 2 : p.bn) * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t kblock_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.kgroup) * kblock_bytes;
   const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
   // work units: (pixel tile, channel tile); pair: (two neighbouring pixel tiles, channel tile)
   const int total_tiles = (kPair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles_n;
-  const int tile_first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // every CTA (pair) walks a CONTIGUOUS range of work units: consecutive pixel tiles belong to the same image, so the
+  // InstanceNorm sums are kept in registers across tiles and reach memory once per image (the per-tile atomics of 592
+  // warps onto 64 cache lines took 40 % of the u64 layer)
+  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int per_worker = (total_tiles + n_workers - 1) / n_workers;
+  const int tile_first = worker * per_worker;
+  const int tile_last = min(total_tiles, tile_first + per_worker);
   const int k_blocks = p.n_taps * p.k_chunks;
 
   if (threadIdx.x == 0) {
@@ -129,6 +138,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   volatile int* abort_flag = &abort_smem;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -136,7 +146,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = tile_first; tile < total_tiles && ok; tile += tile_step) {
+      long long prod_wait = 0;
+      const long long tp0 = dbg ? clock64() : 0;
+      for (int tile = tile_first; tile < tile_last && ok; ++tile) {
         const int n_tile = tile % p.n_tiles_n;
         // an odd tile count leaves the last pair's second CTA with a tile beyond the batch: TMA zero-fills it
         int m_tile = kPair ? 2 * (tile / p.n_tiles_n) + static_cast<int>(rank) : tile / p.n_tiles_n;
@@ -146,33 +158,44 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const int tn = m_tile / p.tiles_h;
         const int q0 = tw * p.tile_w, p0 = th * p.tile_h, img0 = tn * p.tile_n;
         const int n0 = n_tile * p.bn + (kPair ? static_cast<int>(rank) * (p.bn / 2) : 0);
-        for (int t = 0; t < p.n_taps && ok; ++t) {
-          const IgemmTap tap = p.taps[t];
-          const CUtensorMap* amap = &maps.a[tap.map];
-          for (int c = 0; c < p.k_chunks; ++c) {
-            if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u, abort_flag)) {
-              ok = false;
-              break;
-            }
-            const uint32_t full = smem_u32(&bar_full[stage]);
-            const uint32_t sa = smem_base + stage * stage_bytes;
+        // The single producer thread and the single MMA thread each spend ~500-700 cycles per pipeline stage on the
+        // barrier round trip (measured, tools/igemm_dbg.py), more than the 272 cycles of tensor work a 64 / 128-channel
+        // K block carries: a stage therefore holds kgroup K blocks.
+        for (int g0 = 0; g0 < k_blocks && ok; g0 += p.kgroup) {
+          const int cnt = min(p.kgroup, k_blocks - g0);
+          const long long tw0 = dbg ? clock64() : 0;
+          if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u, abort_flag)) {
+            ok = false;
+            break;
+          }
+          if (dbg) prod_wait += clock64() - tw0;
+          const uint32_t full = smem_u32(&bar_full[stage]);
+          const uint32_t full0 = kPair ? mapa_shared(full, 0) : full;
+          // pair: both CTAs' loads complete on the issuing (even) CTA's barrier, armed by it with the bytes of both
+          if (rank == 0) mbar_arrive_expect_tx(full, (kPair ? 2u : 1u) * static_cast<uint32_t>(cnt) * kblock_bytes);
+          for (int j = 0; j < cnt; ++j) {
+            const int kb = g0 + j;
+            const int t = kb / p.k_chunks, c = kb - t * p.k_chunks;
+            const IgemmTap tap = p.taps[t];
+            const CUtensorMap* amap = &maps.a[tap.map];
+            const uint32_t sa = smem_base + stage * stage_bytes + static_cast<uint32_t>(j) * kblock_bytes;
             if (kPair) {
-              // both CTAs' loads complete on the issuing (even) CTA's barrier, armed by it with the bytes of both
-              const uint32_t full0 = mapa_shared(full, 0);
-              if (rank == 0) mbar_arrive_expect_tx(full, 2u * stage_bytes);
               tma_load_4d_pair(amap, full0, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
               tma_load_2d_pair(&maps.b, full0, sa + kABytes, tap.wk + c * p.kelems, n0);
             } else {
-              mbar_arrive_expect_tx(full, stage_bytes);
               tma_load_4d(amap, full, sa, c * p.kelems, q0 + tap.dw, p0 + tap.dh, img0);
               tma_load_2d(&maps.b, full, sa + kABytes, tap.wk + c * p.kelems, n0);
             }
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
+      }
+      if (dbg) {
+        p.dbg[1] = prod_wait;
+        p.dbg[2] = clock64() - tp0;
       }
     }
   } else if (warp == 1) {
@@ -186,45 +209,49 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       uint32_t phase = 0;
       int local = 0;
       bool ok = true;
-      for (int tile = tile_first; tile < total_tiles && ok; tile += tile_step, ++local) {
+      long long w_tempty = 0, w_full = 0;
+      const bool dbgl = dbg && lane == 0;
+      const long long tm0 = dbgl ? clock64() : 0;
+      for (int tile = tile_first; tile < tile_last && ok; ++tile, ++local) {
         const int buf = local & 1;
         const uint32_t tphase = (local >> 1) & 1u;
+        long long tw0 = dbgl ? clock64() : 0;
         ok = mbar_wait(smem_u32(&bar_tempty[buf]), tphase ^ 1u, abort_flag);
         if (kPair) ok = __all_sync(0xffffffffu, ok);
         if (!ok) break;
+        if (dbgl) w_tempty += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf) * 256u;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int g0 = 0; g0 < k_blocks; g0 += p.kgroup) {
+          const int cnt = min(p.kgroup, k_blocks - g0);
+          tw0 = dbgl ? clock64() : 0;
           ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
           if (kPair) ok = __all_sync(0xffffffffu, ok);
           if (!ok) break;
+          if (dbgl) w_full += clock64() - tw0;
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024, kLayoutSW128);
           // one instruction consumes 32 bytes of K per row in both precisions: 16 bf16 or 8 tf32
-          if (kPair) {
-            if (elect_one()) {
+          if (!kPair || elect_one()) {
+            for (int j = 0; j < cnt; ++j) {
+              const uint32_t sa = smem_base + stage * stage_bytes + static_cast<uint32_t>(j) * kblock_bytes;
+              const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+              const uint64_t db = make_smem_desc(sa + kABytes, 16, 1024, kLayoutSW128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                if (tf32) umma2_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                else umma2_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                const uint32_t acc = (g0 | j | k) != 0 ? 1u : 0u;
+                if (kPair) {
+                  if (tf32) umma2_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, acc);
+                  else umma2_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, acc);
+                } else {
+                  if (tf32) umma_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, acc);
+                  else umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, acc);
+                }
               }
-              umma2_commit(smem_u32(&bar_empty[stage]));
             }
-            __syncwarp();
-          } else {
-            if (tf32) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_tf32(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(smem_u32(&bar_empty[stage]));
+            if (kPair) umma2_commit(smem_u32(&bar_empty[stage]));
+            else umma_commit(smem_u32(&bar_empty[stage]));
           }
+          if (kPair) __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -239,6 +266,12 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           }
         }
       }
+      if (dbgl) {
+        p.dbg[3] = w_tempty;
+        p.dbg[4] = w_full;
+        p.dbg[5] = clock64() - tm0;
+        p.dbg[9] = local;
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
@@ -251,19 +284,57 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int m0 = ew * 32;
     const int w_off = m0 % p.tile_w, h_off = (m0 / p.tile_w) % p.tile_h, n_off = m0 / (p.tile_w * p.tile_h);
     const bool one_image = p.tile_w * p.tile_h >= 32;  // all 32 rows of a warp belong to one image
-    const uint32_t stage_addr = smem_base + p.stages * stage_bytes + ew * 4096;
-    float* slab = reinterpret_cast<float*>(smem_raw + (stage_addr - smem_u32(smem_raw)));
+    const uint32_t stage_addr = smem_base + p.stages * stage_bytes + ew * 8192;   // two 4 KB staging buffers per warp
+    float* slab0 = reinterpret_cast<float*>(smem_raw + (stage_addr - smem_u32(smem_raw)));
+    float* slab = slab0;
     const bool has_bias = p.bias != nullptr;
     const int act = p.act;
     const float slope = p.slope;
     const int cout = p.cout, cstore = p.cstore;
     const bool stats_on = p.stats_on != 0;
     const uint32_t tempty_remote = kPair ? mapa_shared(smem_u32(&bar_tempty[0]), 0) : 0u;
+    auto mbar_arrive_tempty = [&](int b) {
+      if (kPair) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(b) * 8u);
+      else mbar_arrive(smem_u32(&bar_tempty[b]));
+    };
+    // InstanceNorm / BatchNorm sums of this warp's rows, per 64-column slab and 16-column quarter (lanes 0-15 hold one
+    // channel each), carried across the tiles of one image and added to memory when the image (or channel tile) changes
+    float acc1[4][4], acc2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc1[i][j] = acc2[i][j] = 0.f;
+    int acc_img = -1, acc_ntile = -1;
+    auto flush_stats = [&]() {
+      if (acc_img >= 0 && lane < 16 && acc_img < p.dom_n) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = acc_ntile * p.bn + i * 64 + j * 16 + lane;
+            if (i * 64 + j * 16 < p.bn && ch < cout) {
+              atomicAdd(p.stats + (static_cast<int64_t>(acc_img) * cout + ch) * 2, acc1[i][j]);
+              atomicAdd(p.stats + (static_cast<int64_t>(acc_img) * cout + ch) * 2 + 1, acc2[i][j]);
+            }
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc1[i][j] = acc2[i][j] = 0.f;
+    };
+    uint32_t slab_count = 0;
     int local = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+    long long w_tfull = 0, w_store = 0;
+    const bool dbge = dbg && threadIdx.x == 128;
+    const long long te0 = dbge ? clock64() : 0;
+    for (int tile = tile_first; tile < tile_last; ++tile, ++local) {
+      bool released = false;
+      const long long twf = dbge ? clock64() : 0;
       const int buf = local & 1;
       const uint32_t tphase = (local >> 1) & 1u;
       if (!mbar_wait(smem_u32(&bar_tfull[buf]), tphase, abort_flag)) break;
+      if (dbge) w_tfull += clock64() - twf;
       tc_fence_after();
       const int n_tile = tile % p.n_tiles_n;
       int m_tile = kPair ? 2 * (tile / p.n_tiles_n) + static_cast<int>(rank) : tile / p.n_tiles_n;
@@ -278,12 +349,27 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                              static_cast<uint32_t>(buf) * 256u;
       if (p.fast_out) {
         // ---- bf16 NHWC: 64-column slabs -> swizzled staging -> TMA store (clips the tile edges)
-        for (int c0 = 0; c0 < p.bn; c0 += 64) {
-          if (n0 + c0 >= cstore) break;
+        const int simg = p.stats_batch ? 0 : tn * p.tile_n + n_off;
+        const bool reg_stats = stats_on && (one_image || p.stats_batch);
+        if (reg_stats && (simg != acc_img || n_tile != acc_ntile)) {
+          flush_stats();
+          acc_img = simg;
+          acc_ntile = n_tile;
+        }
+#pragma unroll
+        for (int si = 0; si < 4; ++si) {
+          const int c0 = si * 64;
+          if (c0 >= p.bn || n0 + c0 >= cstore) break;
           uint32_t v[64];
           tmem_ld32(taddr + c0, v);
           tmem_ld32(taddr + c0 + 32, v + 32);
           tmem_ld_wait();
+          if (c0 + 64 >= p.bn || n0 + c0 + 64 >= cstore) {
+            // last slab: the accumulator is in registers, the MMA warp may refill this TMEM buffer
+            tc_fence_before();
+            mbar_arrive_tempty(buf);
+            released = true;
+          }
           if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 64; ++j) {
@@ -314,10 +400,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             for (int j = 0; j < 64; ++j)
               if (n0 + c0 + j >= cout || c0 + j >= p.bn) v[j] = 0u;
           }
-          if (lane == 0) bulk_wait_read0();
+          // two staging buffers per warp: the TMA store of the previous slab may still be reading the other one
+          const uint32_t sbuf = stage_addr + (slab_count & 1u) * 4096u;
+          float* slab = slab0 + (slab_count & 1u) * 1024u;
+          ++slab_count;
+          const long long tws = dbge ? clock64() : 0;
+          if (lane == 0) bulk_wait_read1();
           __syncwarp();
+          if (dbge) w_store += clock64() - tws;
           if (stats_on) {
-            if (one_image || p.stats_batch) {
+            if (reg_stats) {
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
                 if (c0 + qd * 16 >= p.bn) break;
@@ -332,12 +424,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                     s1 += t;
                     s2 = fmaf(t, t, s2);
                   }
-                  const int ch = n0 + c0 + qd * 16 + lane;
-                  const int simg = p.stats_batch ? 0 : tn * p.tile_n + n_off;
-                  if (ch < cout && simg < p.dom_n) {
-                    atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2, s1);
-                    atomicAdd(p.stats + (static_cast<int64_t>(simg) * cout + ch) * 2 + 1, s2);
-                  }
+                  acc1[si][qd] += s1;
+                  acc2[si][qd] += s2;
                 }
                 __syncwarp();
               }
@@ -353,7 +441,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               }
             }
           }
-          const uint32_t rbase = stage_addr + lane * 128;
+          const uint32_t rbase = sbuf + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t a = rbase + ((static_cast<uint32_t>(j) ^ (lane & 7u)) << 4);
@@ -365,13 +453,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&maps.out, stage_addr, n0 + c0, tw * p.tile_w + w_off, th * p.tile_h + h_off,
+            tma_store_4d(&maps.out, sbuf, n0 + c0, tw * p.tile_w + w_off, th * p.tile_h + h_off,
                          tn * p.tile_n + n_off);
             bulk_commit();
           }
         }
-        if (lane == 0) bulk_wait_read0();
-        __syncwarp();
       } else {
         // ---- generic path: strided / fp32 / NCHW outputs, 16 columns at a time
         const int64_t obase = img * p.o_sn + pp * p.o_sh + q * p.o_sw;
@@ -444,9 +530,18 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           }
         }
       }
-      tc_fence_before();
-      if (kPair) mbar_arrive_cluster(tempty_remote + static_cast<uint32_t>(buf) * 8u);
-      else mbar_arrive(smem_u32(&bar_tempty[buf]));
+      if (!released) {
+        tc_fence_before();
+        mbar_arrive_tempty(buf);
+      }
+    }
+    flush_stats();
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    if (dbge) {
+      p.dbg[6] = w_tfull;
+      p.dbg[7] = w_store;
+      p.dbg[8] = clock64() - te0;
     }
   }
 
@@ -528,12 +623,21 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
     int rc = make_tmap(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, prm.out, dims, str, box);
     if (rc != CDB_OK) return rc;
   }
-  const int stage_bytes = kABytes + (pair ? prm.bn / 2 : prm.bn) * 128;
-  int stages = (200 * 1024 - 16384) / stage_bytes;
+  const int kblock_bytes = kABytes + (pair ? prm.bn / 2 : prm.bn) * 128;
+  // of the 227 KB per CTA: 32 KB epilogue staging + alignment stay free
+  const int budget = (getenv("CDB_IGEMM_SMEM_KB") ? atoi(getenv("CDB_IGEMM_SMEM_KB")) : 194) * 1024;
+  int kgroup = budget / (3 * kblock_bytes);
+  if (getenv("CDB_IGEMM_KGROUP")) kgroup = atoi(getenv("CDB_IGEMM_KGROUP"));
+  if (kgroup > 4) kgroup = 4;
+  if (kgroup > prm.n_taps * prm.k_chunks) kgroup = prm.n_taps * prm.k_chunks;
+  if (kgroup < 1) kgroup = 1;
+  prm.kgroup = kgroup;
+  const int stage_bytes = kgroup * kblock_bytes;
+  int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   prm.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 16384 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 32768 + 1024;
   static size_t smem_attr[2] = {0, 0};
   if (smem > smem_attr[pair ? 1 : 0]) {
     if (pair) CDB_CUDA_OK(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -541,6 +645,11 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
     smem_attr[pair ? 1 : 0] = smem;
   }
   prm.abort_flag = device_abort_flag_ptr();
+  static long long* dbg_buf = nullptr;
+  if (getenv("CDB_IGEMM_DEBUG")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 128);
+    prm.dbg = dbg_buf;
+  }
   if (pair) {
     const int total = ((m_tiles + 1) / 2) * prm.n_tiles_n;
     if (total < 1) return CDB_OK;
@@ -566,6 +675,17 @@ static int launch_igemm(const SrcView* views, int n_views, const void* wpacked, 
     igemm_kernel<false><<<grid, 256, smem, stream>>>(maps, prm);
   }
   CDB_LAUNCH_OK();
+  if (prm.dbg) {
+    long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg_buf, 128, cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "[igemm dbg] pair=%d m_tiles=%d bn=%d taps=%d chunks=%d stages=%d x %d K blocks | CTA0 tiles %lld | producer: total %lld, waiting for "
+            "empty %lld | mma: total %lld, waiting tempty %lld, full %lld | epilogue warp 0: total %lld, waiting tfull %lld, store "
+            "%lld\n",
+            (int)pair, m_tiles, prm.bn, prm.n_taps, prm.k_chunks, prm.stages, prm.kgroup, h[9], h[2], h[1], h[5], h[3], h[4], h[8], h[6],
+            h[7]);
+  }
   return CDB_OK;
 }
 

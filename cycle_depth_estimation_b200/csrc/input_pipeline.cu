@@ -111,6 +111,77 @@ image_normalize_kernel(const uint8_t* __restrict__ src, int64_t hw, int c, float
   }
 }
 
+
+// ---- Pillow's ImagingResample, 8 bits per channel (third-party arithmetic behind Image.resize(size, BILINEAR) of
+// datasets/dataset_synthia.py:154-161 / new_multi/try_data.py:164-167): a separable filter whose per-output-coordinate
+// windows [xmin, xmin + xmax) and 22-bit fixed-point coefficients are built on the host in double precision exactly as
+// precompute_coeffs / normalize_coeffs_8bpc do; each pass accumulates in int32 from 1 << 21 and clips (ss >> 22) to a byte.
+constexpr int kPilPrecisionBits = 32 - 8 - 2;
+
+__device__ __forceinline__ uint8_t pil_clip8(int v) {
+  v >>= kPilPrecisionBits;  // arithmetic shift, as the table index of clip8_lookups
+  return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// horizontal pass: src [n][h][sw][c] -> dst [n][h][dw][c]; one thread per output byte
+__global__ void __launch_bounds__(256)
+pil_resample_h_kernel(const uint8_t* __restrict__ src, int64_t rows, int sw, int dw, int c, const int32_t* __restrict__ bounds,
+                      const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ dst) {
+  const int64_t total = rows * dw * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    const int64_t t = i / c;
+    const int xx = static_cast<int>(t % dw);
+    const int64_t row = t / dw;
+    const int xmin = bounds[2 * xx], xmax = bounds[2 * xx + 1];
+    const int32_t* k = kk + static_cast<int64_t>(xx) * ksize;
+    const uint8_t* s = src + (row * sw + xmin) * c + ch;
+    int ss = 1 << (kPilPrecisionBits - 1);
+    for (int x = 0; x < xmax; ++x) ss += static_cast<int>(s[static_cast<int64_t>(x) * c]) * k[x];
+    dst[i] = pil_clip8(ss);
+  }
+}
+
+// vertical pass: src [n][sh][w][c] -> dst [n][dh][w][c]
+__global__ void __launch_bounds__(256)
+pil_resample_v_kernel(const uint8_t* __restrict__ src, int n, int sh, int dh, int64_t wc, const int32_t* __restrict__ bounds,
+                      const int32_t* __restrict__ kk, int ksize, uint8_t* __restrict__ dst) {
+  const int64_t total = static_cast<int64_t>(n) * dh * wc;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t col = i % wc;
+    const int64_t t = i / wc;
+    const int yy = static_cast<int>(t % dh);
+    const int64_t img = t / dh;
+    const int ymin = bounds[2 * yy], ymax = bounds[2 * yy + 1];
+    const int32_t* k = kk + static_cast<int64_t>(yy) * ksize;
+    const uint8_t* s = src + (img * sh + ymin) * wc + col;
+    int ss = 1 << (kPilPrecisionBits - 1);
+    for (int y = 0; y < ymax; ++y) ss += static_cast<int>(s[static_cast<int64_t>(y) * wc]) * k[y];
+    dst[i] = pil_clip8(ss);
+  }
+}
+
+// dst[n][y][x][:] = src[n][ytab[y]][xtab[x]][:] (a negative table entry writes zeros): Pillow's NEAREST resize
+// (ImagingScaleAffine's pretabulated positions, built on the host) and FLIP_LEFT_RIGHT / FLIP_TOP_BOTTOM.
+__global__ void __launch_bounds__(256)
+gather_rows_cols_kernel(const uint8_t* __restrict__ src, int n, int sh, int sw, int c, int dh, int dw,
+                        const int32_t* __restrict__ ytab, const int32_t* __restrict__ xtab, uint8_t* __restrict__ dst) {
+  const int64_t total = static_cast<int64_t>(n) * dh * dw * c;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    int64_t t = i / c;
+    const int x = static_cast<int>(t % dw);
+    t /= dw;
+    const int y = static_cast<int>(t % dh);
+    const int64_t img = t / dh;
+    const int sy = ytab[y], sx = xtab[x];
+    dst[i] = (sy < 0 || sx < 0) ? 0 : src[((img * sh + sy) * sw + sx) * c + ch];
+  }
+}
+
 static int grid_for(int64_t per_image, int n) {
   int64_t b = (per_image + 256 * 8 - 1) / (256 * 8);
   const int64_t cap = (int64_t)sm_count() * 8 / (n > 0 ? n : 1) + 1;
@@ -164,6 +235,72 @@ extern "C" int cdb_image_normalize_u8(const uint8_t* src, int32_t n_img, int64_t
   if (n_img == 0) return CDB_OK;
   dim3 grid(grid_for(hw, n_img), n_img);
   image_normalize_kernel<<<grid, 256, 0, stream>>>(src, hw, channels, mean, stdv, dst);
+  CDB_LAUNCH_OK();
+  return CDB_OK;
+}
+
+extern "C" size_t cdb_pil_resample_workspace(int32_t n_img, int32_t sh, int32_t dw, int32_t channels) {
+  if (n_img <= 0 || sh <= 0 || dw <= 0 || channels <= 0) return 0;
+  return (size_t)n_img * sh * dw * channels;
+}
+
+extern "C" int cdb_pil_resample_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, int32_t channels,
+                                   uint8_t* dst, int32_t dh, int32_t dw, const int32_t* bounds_x, const int32_t* kk_x,
+                                   int32_t ksize_x, const int32_t* bounds_y, const int32_t* kk_y, int32_t ksize_y,
+                                   void* workspace, size_t ws_bytes, cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(src && dst, CDB_ERR_BAD_DESC, "pil_resample_u8: null argument");
+  CDB_REQUIRE(n_img >= 0 && sh >= 1 && sw >= 1 && dh >= 1 && dw >= 1 && channels >= 1 && channels <= 8, CDB_ERR_BAD_DESC,
+              "pil_resample_u8: bad sizes");
+  // Pillow runs a pass only when the size changes along it (ImagingResample: need_horizontal / need_vertical)
+  const bool horiz = dw != sw, vert = dh != sh;
+  CDB_REQUIRE(!horiz || (bounds_x && kk_x && ksize_x >= 1), CDB_ERR_BAD_DESC, "pil_resample_u8: horizontal tables missing");
+  CDB_REQUIRE(!vert || (bounds_y && kk_y && ksize_y >= 1), CDB_ERR_BAD_DESC, "pil_resample_u8: vertical tables missing");
+  if (n_img == 0) return CDB_OK;
+  const int64_t out_bytes = (int64_t)n_img * dh * dw * channels;
+  auto blocks = [](int64_t total) {
+    int64_t b = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+  };
+  if (!horiz && !vert) {
+    CDB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)out_bytes, cudaMemcpyDeviceToDevice, stream));
+    return CDB_OK;
+  }
+  const uint8_t* mid = src;
+  if (horiz) {
+    uint8_t* hout = dst;
+    if (vert) {
+      CDB_REQUIRE(workspace && ws_bytes >= cdb_pil_resample_workspace(n_img, sh, dw, channels), CDB_ERR_WORKSPACE,
+                  "pil_resample_u8: workspace too small");
+      hout = static_cast<uint8_t*>(workspace);
+    }
+    const int64_t total = (int64_t)n_img * sh * dw * channels;
+    pil_resample_h_kernel<<<blocks(total), 256, 0, stream>>>(src, (int64_t)n_img * sh, sw, dw, channels, bounds_x, kk_x,
+                                                            ksize_x, hout);
+    CDB_LAUNCH_OK();
+    mid = hout;
+  }
+  if (vert) {
+    pil_resample_v_kernel<<<blocks(out_bytes), 256, 0, stream>>>(mid, n_img, sh, dh, (int64_t)dw * channels, bounds_y, kk_y,
+                                                               ksize_y, dst);
+    CDB_LAUNCH_OK();
+  }
+  return CDB_OK;
+}
+
+extern "C" int cdb_gather_rows_cols_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, int32_t channels,
+                                       uint8_t* dst, int32_t dh, int32_t dw, const int32_t* ytab, const int32_t* xtab,
+                                       cdbStream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CDB_REQUIRE(src && dst && ytab && xtab, CDB_ERR_BAD_DESC, "gather_rows_cols_u8: null argument");
+  CDB_REQUIRE(n_img >= 0 && sh >= 1 && sw >= 1 && dh >= 1 && dw >= 1 && channels >= 1, CDB_ERR_BAD_DESC,
+              "gather_rows_cols_u8: bad sizes");
+  if (n_img == 0) return CDB_OK;
+  const int64_t total = (int64_t)n_img * dh * dw * channels;
+  int64_t b = (total + 255) / 256;
+  if (b > (int64_t)sm_count() * 16) b = (int64_t)sm_count() * 16;
+  gather_rows_cols_kernel<<<(int)b, 256, 0, stream>>>(src, n_img, sh, sw, channels, dh, dw, ytab, xtab, dst);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

@@ -414,6 +414,25 @@ int cdb_label_lut_i64(const uint8_t* src, int64_t numel, const uint8_t* lut_dev,
 int cdb_image_normalize_u8(const uint8_t* src, int32_t n_img, int64_t hw, int32_t channels, float mean, float stdv,
                            float* dst, cdbStream_t stream);
 
+/* cdb_pil_resample_u8: Image.resize(size, Image.BILINEAR) of datasets/dataset_synthia.py:154-161 and
+ *   new_multi/try_data.py:164-167 on n_img uint8 images src[n][sh][sw][channels] -> dst[n][dh][dw][channels], bit-exact
+ *   with Pillow's ImagingResample 8-bit path (third-party dependency of the reference; Pillow 12.2 here): a horizontal
+ *   then a vertical pass, each an int32 sum of byte x 22-bit fixed-point coefficient from 1 << 21, shifted and clipped to
+ *   a byte.  The windows bounds_*[2*i] = first source index, bounds_*[2*i+1] = taps and the coefficients
+ *   kk_*[i*ksize_* + j] (device pointers) are Pillow's precompute_coeffs + normalize_coeffs_8bpc, evaluated in double
+ *   on the host (input_pipeline.pil_coeffs — any filter Pillow offers).  A pass whose size does not change is skipped, as
+ *   Pillow does; its tables may be null.  workspace: cdb_pil_resample_workspace() bytes when both passes run.
+ * cdb_gather_rows_cols_u8: dst[n][y][x][:] = src[n][ytab[y]][xtab[x]][:] (negative entry -> 0): Image.resize(size,
+ *   Image.NEAREST) of the label images (:166-167; tables = ImagingScaleAffine's accumulated positions,
+ *   input_pipeline.pil_nearest_table) and the F.hflip of paired_transform (:228-232; reversed identity table). */
+size_t cdb_pil_resample_workspace(int32_t n_img, int32_t sh, int32_t dw, int32_t channels);
+int cdb_pil_resample_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, int32_t channels, uint8_t* dst,
+                        int32_t dh, int32_t dw, const int32_t* bounds_x, const int32_t* kk_x, int32_t ksize_x,
+                        const int32_t* bounds_y, const int32_t* kk_y, int32_t ksize_y, void* workspace, size_t ws_bytes,
+                        cdbStream_t stream);
+int cdb_gather_rows_cols_u8(const uint8_t* src, int32_t n_img, int32_t sh, int32_t sw, int32_t channels, uint8_t* dst,
+                            int32_t dh, int32_t dw, const int32_t* ytab, const int32_t* xtab, cdbStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

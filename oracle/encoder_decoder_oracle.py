@@ -5,6 +5,7 @@ Plain-PyTorch fp32 functional restatement of the U-Net task network of the refer
 
 * ``unet_encoder``   models/encoder_decoder.py:122-162 (+ _EncoderBlock :30-46, _InceptionBlock :47-82)
 * ``unet_decoder``   models/encoder_decoder.py:164-208 (+ _DecoderUpBlock :84-101, _OutputBlock :103-117)
+* ``unet_generator`` models/seg_network.py:441-559 (the two-headed U-Net of models/seg_model.py)
 * ``SegCycleStepOracle``   models/seg_cycle.py:87-180 (Seg_basic, backward_G with the four task losses, ONE
   discriminator update per generator update)
 
@@ -29,6 +30,18 @@ def tie_prelu(sd):
             and not k.endswith('num_batches_tracked')]
     for k in keys[1:]:
         sd[k] = sd[keys[0]]
+    return sd
+
+
+def tie_prelu_prefixed(sd):
+    """tie_prelu for a state_dict whose networks sit under prefixes ('scale0.'): ties within each prefix."""
+    groups = {}
+    for k, v in sd.items():
+        if v.dim() == 1 and v.numel() == 1 and k.endswith('.weight'):
+            groups.setdefault(k.split('.')[0], []).append(k)
+    for keys in groups.values():
+        for k in keys[1:]:
+            sd[k] = sd[keys[0]]
     return sd
 
 
@@ -106,6 +119,29 @@ def unet_decoder(sd, feats, training=True, weight=0.1):
     output2 = _out_block(sd, 'output2.', cat2)
     output1 = _out_block(sd, 'output1.', torch.cat([deconv2, _up2(output2)], 1))
     return [center_in, output4, output3, output2, output1]
+
+
+def unet_generator(sd, x, head, training=True, layers=4, weight=0.1):
+    """models/seg_network.py:441-559 (_UNetGenerator.forward(input, syn_or_real)): the encoder of unet_encoder, the
+    inception centre followed by the centre up-block (``center.<7-layers>``), then the ``*_syn`` (22 classes) or
+    ``*_real`` (28 classes) decoder; every value other than 'syn' selects the real head, as the reference's else branch
+    does.  Returns [center_in, output1].  The blocks are the same statements as models/encoder_decoder.py (the reference
+    file repeats them, :155-285), so the helpers above are reused with this module's key names."""
+    a = sd[ENC_SLOPE]
+    conv1, conv2, conv3, center_in, cur = unet_encoder(sd, x, training, layers)
+    center_out = _up_block(sd, 'center.%d.' % (7 - layers), cur, a, training)
+    h = 'syn' if head == 'syn' else 'real'
+    cat4 = torch.cat([center_out, conv3 * weight], 1)
+    deconv4 = _up_block(sd, 'deconv4_%s.' % h, cat4, a, training)
+    output4 = _out_block(sd, 'output4_%s.' % h, cat4)
+    cat3 = torch.cat([deconv4, conv2 * weight * 0.5, _up2(output4)], 1)
+    deconv3 = _up_block(sd, 'deconv3_%s.' % h, cat3, a, training)
+    output3 = _out_block(sd, 'output3_%s.' % h, cat3)
+    cat2 = torch.cat([deconv3, conv1 * weight * 0.1, _up2(output3)], 1)
+    deconv2 = _up_block(sd, 'deconv2_%s.' % h, cat2, a, training)
+    output2 = _out_block(sd, 'output2_%s.' % h, cat2)
+    output1 = _out_block(sd, 'output1_%s.' % h, torch.cat([deconv2, _up2(output2)], 1))
+    return [center_in, output1]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -178,6 +178,39 @@ def make_encoder_decoder(ED):
                 g_dec_out1=dec.output1.model[1].weight.grad.clone())
 
 
+def make_seg_network(SN):
+    """Outputs and gradients of the reference's own models/seg_network.py::_UNetGenerator (CPU, training-mode BatchNorm,
+    ngf=8) for both heads on name-keyed synthetic weights with the shared PReLU tied."""
+    from oracle import encoder_decoder_oracle as OE
+    from oracle import networks5_oracle as O5
+    net = SN._UNetGenerator(input_nc=3, output_nc=22, ngf=8)
+    net.load_state_dict(OE.tie_prelu(O5.synth_state_dict(net.state_dict(), 21)), strict=True)
+    net.train()
+    fx = dict(keys=list(net.state_dict().keys()), heads={})
+    for head, nc, seed in (('syn', 22, 61), ('real', 28, 62)):
+        net.zero_grad()
+        x = image(1, 3, 96, 96, seed).requires_grad_(True)          # inputs are regenerated from their seeds by the test
+        center_in, out1 = net(x, head)
+        gout = image(1, nc, 96, 96, seed + 10)
+        (out1 * gout).sum().backward()
+        fx['heads'][head] = dict(seed=seed, center_in=center_in.detach(), out1=out1.detach()[:, :, ::3, ::3].clone(),
+                                 gx=x.grad.clone(), g_slope=net.conv1[3].weight.grad.clone(),
+                                 g_out1=getattr(net, 'output1_' + head).model[1].weight.grad.clone(),
+                                 g_conv1=net.conv1[1].weight.grad.clone())
+    # _MultiscaleDiscriminator(num_D=1) / _Discriminator (models/seg_network.py:561-627), ndf=8
+    D = SN._MultiscaleDiscriminator(input_nc=5, ndf=8)
+    D.load_state_dict(OE.tie_prelu_prefixed(O5.synth_state_dict(D.state_dict(), 23)), strict=True)
+    D.train()
+    x = image(2, 5, 64, 64, 63).requires_grad_(True)
+    out = D(x)
+    assert isinstance(out, list) and len(out) == 1
+    gout = image(*out[0].shape, 64)
+    (out[0] * gout).sum().backward()
+    fx['disc'] = dict(keys=list(D.state_dict().keys()), x=x.detach(), out=out[0].detach(), gout=gout, gx=x.grad.clone(),
+                      g_slope=D.scale0.model[1].weight.grad.clone(), g_w0=D.scale0.model[0].weight.grad.clone())
+    return fx
+
+
 def _ref_lines(rel, first, last):
     """Source lines [first, last] (1-based) of a reference file with comment-only lines dropped, dedented."""
     import textwrap
@@ -233,7 +266,48 @@ def make_input_pipeline():
     return fx
 
 
+def make_pil_resize():
+    """Calls Pillow itself (the reference's third-party dependency) with the reference's call-site arguments
+    (datasets/dataset_synthia.py:154-167: resize([640, 192], BILINEAR / NEAREST); new_multi/try_data.py:164-167:
+    resize([576, 192], BILINEAR); paired_transform's F.hflip = transpose(FLIP_LEFT_RIGHT)) on small seeded images whose
+    aspect ratios are those of the datasets (Synthia 1280x760, KITTI 1242x375 scaled down by 1/5), plus an upscaling and
+    a one-axis case."""
+    import PIL
+    from PIL import Image
+    rng = np.random.default_rng(2024)
+    fx = {'pillow': PIL.__version__, 'cases': []}
+    for (h, w, dw, dh) in [(152, 256, 128, 38), (75, 248, 128, 38), (75, 248, 115, 38), (40, 56, 90, 71), (48, 64, 64, 20),
+                           (33, 47, 47, 33), (760, 1280, 640, 192)]:
+        full = h >= 700      # full Synthia size: the input is regenerated from its seed, the outputs are stored subsampled
+        r = np.random.default_rng(9) if full else rng
+        img = r.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        lab = r.integers(0, 34, (h, w), dtype=np.uint8)
+        pim, plab = Image.fromarray(img).convert('RGB'), Image.fromarray(lab)
+        bil = np.array(pim.resize([dw, dh], Image.BILINEAR))
+        near = np.array(plab.resize([dw, dh], Image.NEAREST))
+        flip = np.array(pim.resize([dw, dh], Image.BILINEAR).transpose(Image.FLIP_LEFT_RIGHT))
+        if full:
+            case = dict(size=(dw, dh), shape=(h, w), seed=9, sub=(7, 11), bilinear=bil[::7, ::11].copy(),
+                        nearest=near[::7, ::11].copy(), bilinear_flipped=flip[::7, ::11].copy())
+        else:
+            case = dict(size=(dw, dh), shape=(h, w), img=img, lab=lab, bilinear=bil, nearest=near, bilinear_flipped=flip)
+        fx['cases'].append(case)
+    return fx
+
+
 def main():
+    if "--seg-network-only" in sys.argv:
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
+        SN = load_ref("ref_seg_network", "models/seg_network.py")
+        torch.save(make_seg_network(SN), os.path.join(OUT, "seg_network.pt"))
+        print("seg_network.pt", os.path.getsize(os.path.join(OUT, "seg_network.pt")))
+        return
+    if "--pil-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        torch.save(make_pil_resize(), os.path.join(OUT, "pil_resize.pt"))
+        print("pil_resize.pt", os.path.getsize(os.path.join(OUT, "pil_resize.pt")))
+        return
     if not available():
         raise SystemExit("reference not found at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
@@ -249,7 +323,10 @@ def main():
     torch.save(make_networks5(N5), os.path.join(OUT, "networks5.pt"))
     ED = load_ref("ref_encoder_decoder", "models/encoder_decoder.py")
     torch.save(make_encoder_decoder(ED), os.path.join(OUT, "encoder_decoder.pt"))
+    SN = load_ref("ref_seg_network", "models/seg_network.py")
+    torch.save(make_seg_network(SN), os.path.join(OUT, "seg_network.pt"))
     torch.save(make_input_pipeline(), os.path.join(OUT, "input_pipeline.pt"))
+    torch.save(make_pil_resize(), os.path.join(OUT, "pil_resize.pt"))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -59,7 +59,7 @@ def test_generator_outputs_do_not_depend_on_batch_composition():
 def test_depth_metrics_over_all_697_pairs_are_chunking_and_order_invariant():
     """BASELINE configs[4]: 697 pairs of 375x1242. Per-image results must not depend on which other images share
     the launch, the threshold fractions must be ordered (a1 <= a2 <= a3 <= 1) and consistent with exact counts,
-    and a handful of images is compared with the numpy oracle (1e-5)."""
+    and every one of the 697 images is compared with the numpy oracle (values 1e-5, threshold fractions exact)."""
     from cycle_depth_estimation_b200 import ops
     from oracle import networks_oracle as O
     rng = np.random.default_rng(2019)
@@ -79,6 +79,10 @@ def test_depth_metrics_over_all_697_pairs_are_chunking_and_order_invariant():
     assert np.allclose(counts, np.rint(counts), atol=1e-6)          # fractions of exact integer counts
     mask_counts = np.logical_and(gt > 1, gt < 50).reshape(n, -1).sum(1)
     assert np.array_equal(full[:, 7].astype(np.int64), mask_counts)
-    idx = [0, 333, 696]
-    _, ref = O.eval_metric_arrays([gt[i] for i in idx], [pred[i] for i in idx])
-    assert np.allclose(full[idx, :7].astype(np.float32), ref, rtol=0, atol=1e-5)
+    # ALL 697 images against the numpy oracle (new_multi/my_eval.py:7-108 restated; ~10 s of host time): metric values
+    # within 1e-5, the three threshold fractions exactly (they are ratios of exact integer counts)
+    _, ref = O.eval_metric_arrays([gt[i] for i in range(n)], [pred[i] for i in range(n)])
+    ref = np.asarray(ref)
+    assert ref.shape == (n, 7)
+    assert np.allclose(full[:, :7].astype(np.float32), ref, rtol=0, atol=1e-5)
+    assert np.array_equal(full[:, 4:7].astype(np.float32), ref[:, 4:7].astype(np.float32))

@@ -120,3 +120,89 @@ def test_image_normalize_kernel_bit_exact(fx):
     for i in range(4):
         assert torch.equal(out[i].cpu(), OI.normalize(imgs[i])), i
     assert float(out.min()) >= -1.0 and float(out.max()) <= 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pillow resizes / flip (datasets/dataset_synthia.py:154-167, 228-232; new_multi/try_data.py:164-167)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def pil_fx():
+    return torch.load(os.path.join(GOLD, "pil_resize.pt"), weights_only=False)
+
+
+def _case_inputs(case):
+    if 'img' in case:
+        return case['img'], case['lab'], (1, 1)
+    h, w = case['shape']
+    r = np.random.default_rng(case['seed'])
+    return r.integers(0, 256, (h, w, 3), dtype=np.uint8), r.integers(0, 34, (h, w), dtype=np.uint8), case['sub']
+
+
+def test_oracle_pil_resize_matches_pillow_fixtures(pil_fx):
+    """The numpy restatement against outputs of Pillow itself (oracle/make_golden.py::make_pil_resize), bit for bit:
+    antialiased down-scaling at the datasets' aspect ratios, up-scaling, one-axis resizes, the full 1280x760 -> 640x192."""
+    assert len(pil_fx['cases']) >= 7
+    for case in pil_fx['cases']:
+        img, lab, (sy, sx) = _case_inputs(case)
+        bil = OI.pil_resize_bilinear(img, case['size'])
+        assert _same(bil[::sy, ::sx], case['bilinear']), case['shape']
+        assert _same(OI.pil_resize_nearest(lab, case['size'])[::sy, ::sx], case['nearest']), case['shape']
+        assert _same(OI.hflip(bil)[::sy, ::sx], case['bilinear_flipped']), case['shape']
+
+
+def test_oracle_pil_resize_matches_the_installed_pillow():
+    """Live pin where Pillow is importable (it is in this image): KITTI-sized input at both reference target sizes."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (375, 1242, 3), dtype=np.uint8)
+    lab = rng.integers(0, 34, (375, 1242), dtype=np.uint8)
+    for size in ([640, 192], [576, 192]):
+        assert _same(OI.pil_resize_bilinear(img, size), np.array(Image.fromarray(img).resize(size, Image.BILINEAR)))
+        assert _same(OI.pil_resize_nearest(lab, size), np.array(Image.fromarray(lab).resize(size, Image.NEAREST)))
+
+
+def test_host_tables_equal_the_oracle_windows():
+    """input_pipeline.pil_coeffs / pil_nearest_table (what the kernels consume) against the oracle's own construction."""
+    from cycle_depth_estimation_b200 import input_pipeline as IP
+    for (i, o) in [(1280, 640), (760, 192), (1242, 576), (375, 192), (47, 90), (64, 64), (5, 3), (3, 7)]:
+        bounds, kk, ksize = IP.pil_coeffs(i, o)
+        wins = OI._pil_windows(i, o)
+        assert bounds.shape == (o, 2) and kk.shape == (o, ksize)
+        for xx, (xmin, k) in enumerate(wins):
+            assert bounds[xx, 0] == xmin and bounds[xx, 1] == len(k)
+            assert np.array_equal(kk[xx, :len(k)], k) and not kk[xx, len(k):].any()
+        assert np.array_equal(IP.pil_nearest_table(i, o), OI._pil_nearest_index(i, o))
+
+
+@pytest.mark.gpu
+def test_pil_resize_kernels_bit_exact(pil_fx):
+    from cycle_depth_estimation_b200 import input_pipeline as IP
+    for case in pil_fx['cases']:
+        img, lab, (sy, sx) = _case_inputs(case)
+        d_img = torch.from_numpy(img).cuda()[None]
+        d_lab = torch.from_numpy(lab).cuda()[None, :, :, None]
+        bil = IP.resize_bilinear_u8(d_img, case['size'])
+        assert _same(bil[0].cpu().numpy()[::sy, ::sx], case['bilinear']), case['shape']
+        near = IP.resize_nearest_u8(d_lab, case['size'])
+        assert _same(near[0, :, :, 0].cpu().numpy()[::sy, ::sx], case['nearest']), case['shape']
+        assert _same(IP.hflip_u8(bil)[0].cpu().numpy()[::sy, ::sx], case['bilinear_flipped']), case['shape']
+
+
+@pytest.mark.gpu
+def test_pil_resize_kernels_on_batches_at_the_dataset_sizes():
+    """KITTI 1242x375 -> 640x192 and 576x192, batch of 3 against the oracle per image; per-sample flip decisions."""
+    from cycle_depth_estimation_b200 import input_pipeline as IP
+    rng = np.random.default_rng(11)
+    imgs = rng.integers(0, 256, (3, 375, 1242, 3), dtype=np.uint8)
+    labs = rng.integers(0, 34, (3, 375, 1242, 1), dtype=np.uint8)
+    d_imgs, d_labs = torch.from_numpy(imgs).cuda(), torch.from_numpy(labs).cuda()
+    for size in ((640, 192), (576, 192)):
+        bil = IP.resize_bilinear_u8(d_imgs, size).cpu().numpy()
+        near = IP.resize_nearest_u8(d_labs, size).cpu().numpy()
+        for i in range(3):
+            assert _same(bil[i], OI.pil_resize_bilinear(imgs[i], size))
+            assert _same(near[i, :, :, 0], OI.pil_resize_nearest(labs[i, :, :, 0], size))
+    flipped = IP.hflip_u8(d_imgs, [True, False, True]).cpu().numpy()
+    assert _same(flipped[0], OI.hflip(imgs[0])) and _same(flipped[1], imgs[1]) and _same(flipped[2], OI.hflip(imgs[2]))
+    one_axis = IP.resize_bilinear_u8(d_imgs, (1242, 192)).cpu().numpy()       # vertical pass only
+    assert _same(one_axis[1], OI.pil_resize_bilinear(imgs[1], (1242, 192)))

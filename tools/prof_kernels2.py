@@ -14,6 +14,13 @@ stats = torch.zeros((n, c, 2), device="cuda")
 for _ in range(2):
     stats.zero_()
     ops.conv2d_fwd(ops.geom(k, k), x, wp, rows_pad, kpad, ops.out_view_nhwc(y, c), None, ops.ACT_NONE, 0.0, stats)
+# the same layer at batch 16: two waves of tiles -> CTA pairs (igemm_flat_kernel<true>)
+x16 = torch.randn((16, hw + 2, hw + 2, c), device="cuda").to(torch.bfloat16)
+y16 = ops.alloc_flat_output(16, hw, hw, hw + 2, c, "cuda")
+stats16 = torch.zeros((16, c, 2), device="cuda")
+for _ in range(2):
+    stats16.zero_()
+    ops.conv2d_fwd(ops.geom(k, k), x16, wp, rows_pad, kpad, ops.out_view_nhwc(y16, c), None, ops.ACT_NONE, 0.0, stats16)
 dy = torch.randn((n, hw, hw, c), device="cuda").to(torch.bfloat16)
 dw = torch.empty_like(w)
 for _ in range(2):
