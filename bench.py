@@ -677,9 +677,9 @@ def secondary_arm(args):
     mp_world, mp_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     mp_dist = None
     if mp_world > 1:
-        if wl != "metrics":
-            raise SystemExit("--workload %s runs on one GPU (BatchNorm couples the batch); only the default CycleGAN "
-                             "workload and --workload metrics shard over ranks" % wl)
+        if wl not in ("metrics", "pix2pix"):
+            raise SystemExit("--workload %s runs on one GPU; the default CycleGAN workload, --workload pix2pix (BatchNorm "
+                             "statistics all-reduced per layer) and --workload metrics shard over ranks" % wl)
         import torch.distributed as mp_dist
         mp_dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -696,6 +696,12 @@ def secondary_arm(args):
         with contextlib.redirect_stdout(io.StringIO()):
             model.initialize(opt)
         a, bb = synthetic_batch(b, 256, 1234)
+        if mp_world > 1:
+            # strong scaling: the global batch is sharded; every BatchNorm layer all-reduces its (sum, sum of squares)
+            # forward and (sum dy, sum dy*xhat) backward, so the step equals the single-device one
+            per = b // mp_world
+            a, bb = a[mp_rank * per:(mp_rank + 1) * per].contiguous(), bb[mp_rank * per:(mp_rank + 1) * per].contiguous()
+            extra["parallelism"] = "dp%d: global batch %d sharded, BatchNorm statistics all-reduced per layer" % (mp_world, b)
         host = {'A': a.pin_memory(), 'B': bb.pin_memory(), 'A_paths': None}
         dev = {'A': a.cuda(), 'B': bb.cuda(), 'A_paths': None}
 
@@ -709,6 +715,10 @@ def secondary_arm(args):
             return model.get_current_losses()
         ms = _time_steps(step, args.steps, args.warmup)
         ms_e2e = _time_steps(step_e2e, args.steps, 1)
+        if mp_world > 1:
+            t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+            mp_dist.all_reduce(t, op=mp_dist.ReduceOp.MAX)
+            ms, ms_e2e = float(t[0]), float(t[1])
         tflop = 1.391 * b / 16.0
         metric, unit = "pix2pix_train_iters_per_s", "iters/s (batch-%d training steps at 256x256)" % b
         workload = ("pix2pix training step: UnetGenerator unet_256 (BatchNorm, dropout) + NLayerDiscriminator n_layers=3 on "

@@ -39,7 +39,8 @@ class CdbNormDesc(C.Structure):
                 ("channels", C.c_int32), ("pad", C.c_int32), ("use_running", C.c_int32),
                 ("update_running", C.c_int32), ("momentum", C.c_float), ("flags", C.c_int32),
                 ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
-                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("conv_bias", C.c_void_p)]
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("conv_bias", C.c_void_p),
+                ("count_scale", C.c_float), ("reserved_", C.c_int32)]
 
 
 class CdbAdamEntry(C.Structure):

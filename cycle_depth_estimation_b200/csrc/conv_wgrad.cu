@@ -33,6 +33,7 @@ struct WgParams {
   int32_t mpad, npad;
   int32_t tf32;                       // fp32 operands multiplied as TF32: 32 channels per 128-byte chunk row
   int32_t cpc;                        // channels per chunk: 64 (bf16) or 32 (tf32)
+  int32_t prewait;                    // MMA thread waits for the next stage before the last instruction of this one
   int32_t tg, n_groups;               // taps per item (their shifted tiles sit side by side in N) and tap groups
   float* ws;                          // [splits][taps][mpad][npad]
   int* abort_flag;
@@ -205,34 +206,55 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
         const int ntap = min(p.tg, p.n_taps - tap * p.tg);
         const uint32_t idesc =
             make_idesc(tf32 ? 2u : 1u, 1u, 1u, kPair ? 256u : 128u, static_cast<uint32_t>(p.bn * ntap));
+        // The tensor pipe accepts an instruction only shortly before it can start it, so whatever the issuing thread does
+        // between the last instruction of one stage and the first of the next (commit, barrier round trip, fence,
+        // descriptors: ~300 cycles) is idle tensor time per 512-cycle stage.  The wait for stage s + 1 is therefore made
+        // BEFORE the last instruction of stage s is issued, while the earlier ones execute (p.prewait).
+        bool ready = false;
         for (int kt = kt0; kt < kt1; ++kt) {
-          ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
-          if (kPair) ok = __all_sync(0xffffffffu, ok);
-          if (!ok) break;
-          tc_fence_after();
+          if (!ready) {
+            ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
+            if (kPair) ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            tc_fence_after();
+          }
+          ready = false;
           const uint32_t sa = smem_base + stage * stage_bytes;
-          if (!kPair || elect_one()) {
-            if (tf32) {
-              // MN-major TF32: 128B swizzle with 32-byte atoms (4 k-rows x 128 B per atom): LBO = distance between
-              // 32-channel chunks, SBO = 512 B between the two 4-row groups of one K = 8 instruction.
-              // (pinned on B200 with tools/probe_tf32_wgrad.py: any other LBO/SBO assignment gives O(1) errors)
-              const uint64_t ta = make_smem_desc(sa, kChunkBytes, 512, kLayoutSW128Base32);
-              const uint64_t tb = make_smem_desc(sa + a_bytes, kChunkBytes, 512, kLayoutSW128Base32);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {  // 8 pixels (= 8 rows x 128 B) per instruction
-                if (kPair) umma2_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-                else umma_tf32(d_tmem, ta + 64u * k, tb + 64u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-              }
+          const int n_instr = tf32 ? 8 : 4;
+          // MN-major operands.  bf16: 128B swizzle, LBO = distance between 64-channel chunks, SBO = 8 k-rows, 16 pixels
+          // (= 2048 B) per instruction.  TF32: 128B swizzle with 32-byte atoms (4 k-rows x 128 B per atom), LBO = distance
+          // between 32-channel chunks, SBO = 512 B between the two 4-row groups of one K = 8 instruction, 8 pixels
+          // (= 1024 B) per instruction (pinned on B200 with tools/probe_tf32_wgrad.py).
+          const uint64_t da = tf32 ? make_smem_desc(sa, kChunkBytes, 512, kLayoutSW128Base32)
+                                   : make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+          const uint64_t db = tf32 ? make_smem_desc(sa + a_bytes, kChunkBytes, 512, kLayoutSW128Base32)
+                                   : make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
+          const uint32_t kstep = tf32 ? 64u : 128u;
+          auto issue = [&](int k) {
+            const uint32_t acc = (kt > kt0 || k > 0) ? 1u : 0u;
+            if (kPair) {
+              if (tf32) umma2_tf32(d_tmem, da + kstep * k, db + kstep * k, idesc, acc);
+              else umma2_f16(d_tmem, da + kstep * k, db + kstep * k, idesc, acc);
             } else {
-              // MN-major, 128B swizzle: LBO = distance between 64-channel chunks, SBO = 8 k-rows.
-              const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
-              const uint64_t db = make_smem_desc(sa + a_bytes, kChunkBytes, 1024, kLayoutSW128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows x 128 B = 2048 B) per instruction
-                if (kPair) umma2_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-                else umma_f16(d_tmem, da + 128u * k, db + 128u * k, idesc, (kt > kt0 || k > 0) ? 1u : 0u);
-              }
+              if (tf32) umma_tf32(d_tmem, da + kstep * k, db + kstep * k, idesc, acc);
+              else umma_f16(d_tmem, da + kstep * k, db + kstep * k, idesc, acc);
             }
+          };
+          if (!kPair || elect_one()) {
+            for (int k = 0; k < n_instr - 1; ++k) issue(k);
+          }
+          if (kPair) __syncwarp();
+          if (p.prewait && kt + 1 < kt1) {
+            const int ns = stage + 1 == p.stages ? 0 : stage + 1;
+            const uint32_t nphase = stage + 1 == p.stages ? phase ^ 1u : phase;
+            ok = mbar_wait(smem_u32(&bar_full[ns]), nphase, abort_flag);
+            if (kPair) ok = __all_sync(0xffffffffu, ok);
+            if (!ok) break;
+            tc_fence_after();
+            ready = true;
+          }
+          if (!kPair || elect_one()) {
+            issue(n_instr - 1);
             if (kPair) umma2_commit(smem_u32(&bar_empty[stage]));
             else umma_commit(smem_u32(&bar_empty[stage]));
           }
@@ -716,6 +738,8 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.cpc = cpc;
   prm.tg = pl.tg;
   prm.n_groups = pl.n_groups;
+  static const int prewait_env = getenv("CDB_MMA_PREWAIT") ? atoi(getenv("CDB_MMA_PREWAIT")) : 0;  // measured neutral (same-box A/B, tools/ab_wgrad.sh): the kernel waits for data, not for its issuing thread
+  prm.prewait = prewait_env;
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
   const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes / (pl.pair ? 2 : 1);

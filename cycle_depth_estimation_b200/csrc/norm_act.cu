@@ -1151,8 +1151,13 @@ static int fill_common(const CdbNormDesc* d, const CdbAct* y, int* C) {
   return CDB_OK;
 }
 
+static float count_scale_of(const CdbNormDesc* d) {
+  return (d->norm == CDB_NORM_BATCH && d->count_scale > 1.f) ? d->count_scale : 1.f;
+}
+
 static float inv_count_of(const CdbNormDesc* d, const CdbAct* y) {
-  return 1.f / (d->norm == CDB_NORM_INSTANCE ? (float)(y->h * y->w) : (float)((int64_t)y->n * y->h * y->w));
+  return 1.f / (d->norm == CDB_NORM_INSTANCE ? (float)(y->h * y->w)
+                                             : (float)((int64_t)y->n * y->h * y->w) * count_scale_of(d));
 }
 
 extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const CdbAct* residual,
@@ -1209,7 +1214,7 @@ extern "C" int cdb_norm_act_fwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   }
   CDB_LAUNCH_OK();
   if (d->norm == CDB_NORM_BATCH && !d->use_running && d->update_running && d->running_mean && d->running_var) {
-    const float count = (float)((int64_t)y->n * y->h * y->w);
+    const float count = (float)((int64_t)y->n * y->h * y->w) * count_scale_of(d);
     bn_running_kernel<<<ceil_div(d->channels, 128), 128, 0, stream>>>(d->stats, d->channels, count, d->momentum,
                                                                       d->running_mean, d->running_var, d->conv_bias);
     CDB_LAUNCH_OK();
@@ -1279,6 +1284,22 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
   p.bstats = bstats;
   p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, 2);
   dim3 grid(ceil_div(y->h, p.rows_per_block), y->n, m.cv_tiles);
+  const bool reduce_only = (d->flags & CDB_NORM_FLAG_BWD_REDUCE_ONLY) != 0;
+  const bool apply_only = (d->flags & CDB_NORM_FLAG_BWD_APPLY_ONLY) != 0;
+  if (reduce_only || apply_only) {
+    // data-parallel BatchNorm: the caller all-reduces bstats between the two passes (generic two-pass kernels)
+    CDB_REQUIRE(!(reduce_only && apply_only) && need_reduce, CDB_ERR_BAD_DESC,
+                "norm_act_bwd: REDUCE_ONLY / APPLY_ONLY need a batch-statistics normalisation and exclude each other");
+    if (reduce_only) {
+      if (dt == CDB_F32) launch_norm_bwd<float, false>(p, grid, stream);
+      else launch_norm_bwd<__nv_bfloat16, false>(p, grid, stream);
+    } else {
+      if (dt == CDB_F32) launch_norm_bwd<float, true>(p, grid, stream);
+      else launch_norm_bwd<__nv_bfloat16, true>(p, grid, stream);
+    }
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
   if (stream_eligible(d, p, accum_f32, dt)) {
     // three resident blocks per SM (the kernels are compiled for <= 85 registers)
     p.rows_per_block = rows_per_block_for(y->h, y->n, m.cv_tiles, stream_occ() >= 3 ? 3 : 2);

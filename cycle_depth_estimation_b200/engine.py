@@ -506,6 +506,9 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
             if not use_running:
                 ops.channel_stats(y, co, False, stats)
         affine = getattr(st.norm, "affine", False)
+        bn_world = ops.bn_world() if (nk == NORM_BATCH and not use_running) else 1
+        if bn_world > 1:
+            ops.bn_all_reduce(stats)      # batch statistics over the shards of all ranks
         desc = ops.norm_desc(nk, st.act, st.slope, float(st.norm.eps), co, halo, stats,
                              st.norm.weight if affine else None, st.norm.bias if affine else None,
                              st.norm.running_mean if nk == NORM_BATCH else None,
@@ -513,7 +516,7 @@ def forward(plan, x, training, need_input_grad, needs_param_grad):
                              use_running=use_running,
                              update_running=(nk == NORM_BATCH and training and st.norm.track_running_stats),
                              momentum=float(st.norm.momentum) if getattr(st.norm, "momentum", None) is not None else 0.1,
-                             conv_bias=conv.bias if bias is None else None)
+                             conv_bias=conv.bias if bias is None else None, count_scale=bn_world)
         if nk == NORM_BATCH and training and st.norm.track_running_stats and st.norm.num_batches_tracked is not None:
             st.norm.num_batches_tracked += 1
         res = run.inner[st.res] if st.res is not None else None
@@ -636,16 +639,23 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
             groups = n if nk == NORM_INSTANCE else 1
             need_b = (nk != NORM_NONE and not use_running) or (nk == NORM_NONE and want_b) or affine
             bstats = arena.take((groups, co, 2)) if need_b else None
-            desc = ops.norm_desc(nk, st.act, st.slope, float(st.norm.eps) if st.norm is not None else 0.0, co, halo,
-                                 run.stats[idx], st.norm.weight if affine else None,
-                                 st.norm.bias if affine else None,
-                                 st.norm.running_mean if nk == NORM_BATCH else None,
-                                 st.norm.running_var if nk == NORM_BATCH else None, use_running=use_running)
+            bn_world = ops.bn_world() if (nk == NORM_BATCH and not use_running) else 1
+
+            def desc_of(extra_flags):
+                return ops.norm_desc(nk, st.act, st.slope, float(st.norm.eps) if st.norm is not None else 0.0, co, halo,
+                                     run.stats[idx], st.norm.weight if affine else None,
+                                     st.norm.bias if affine else None,
+                                     st.norm.running_mean if nk == NORM_BATCH else None,
+                                     st.norm.running_var if nk == NORM_BATCH else None, use_running=use_running,
+                                     flags=extra_flags, count_scale=bn_world)
             yv = run.y[idx] if nk != NORM_NONE else run.inner[st.dst]
             gsum = None
             if st.res is not None:
                 gsum = torch.empty((n, ho, wo, cs), dtype=BF16, device=dev)
-            ops.norm_act_bwd(desc, yv, dy, dout_inner, dskip[st.dst], bstats, gsum)
+            if bn_world > 1:
+                ops.norm_act_bwd_synced(desc_of, yv, dy, dout_inner, dskip[st.dst], bstats, gsum, bn_world)
+            else:
+                ops.norm_act_bwd(desc_of(0), yv, dy, dout_inner, dskip[st.dst], bstats, gsum)
             if st.res is not None:
                 if dskip[st.res] is not None:
                     raise NotImplementedError("value with two skip gradients")

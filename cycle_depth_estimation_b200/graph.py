@@ -83,6 +83,8 @@ class Tape:
         # storage + kind::tf32 (single pass, or error-compensated 'tf32x3')
         self.prec = ops.get_precision()
         self.dtype = BF16 if self.prec == 'bf16' else torch.float32
+        # data parallelism: BatchNorm layers normalise over the shards of all ranks (statistics all-reduced per layer)
+        self.bn_world = ops.bn_world()
 
     # ---------------------------------------------------------------- convolution calls (precision dispatch)
     def _operand(self, x, mode_x3, mode_tf32=3):
@@ -360,6 +362,8 @@ class Tape:
                 stats = self.arena.take((groups, co, 2))
             self._conv(g, xin, conv.weight, not transposed, ops.out_view_nhwc(y, co), bias,
                        act if act_first else ACT_NONE, slope, stats, stats_batch=(nk == NORM_BATCH), rowpack=rowpack)
+            if nk == NORM_BATCH and stats is not None and self.bn_world > 1:
+                ops.bn_all_reduce(stats)          # batch statistics over the shards of all ranks
             affine = getattr(norm, "affine", False)
             desc = self._norm_desc(nk, norm, act, slope, co, outv.halo if outv.halo_kind == 'reflect' else 0, stats,
                                    use_running, update=True, flags=NORM_FLAG_ACT_FIRST if act_first else 0,
@@ -391,7 +395,7 @@ class Tape:
                              norm.weight if affine else None, norm.bias if affine else None,
                              norm.running_mean if bn else None, norm.running_var if bn else None,
                              use_running=use_running, update_running=upd, momentum=mom, flags=flags,
-                             conv_bias=conv_bias)
+                             conv_bias=conv_bias, count_scale=self.bn_world if (bn and not use_running) else 1)
 
     def _stage_backward(self, x, conv, transposed, norm, nk, act, slope, act_first, res, reflect, outv, slot, o_nchw,
                         y, stats, xin, pad, materialised, rowpack, flat, use_running, dims):
@@ -447,12 +451,18 @@ class Tape:
                     dy = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
                 groups = n if nk == NORM_INSTANCE else 1
                 bstats = self.arena.take((groups, co, 2))
-                desc = self._norm_desc(nk, norm, act, slope, co, halo_fold, stats, use_running,
-                                       flags=NORM_FLAG_ACT_FIRST if act_first else 0)
+                base_flags = NORM_FLAG_ACT_FIRST if act_first else 0
                 gsum = None
                 if res is not None and (dskip is not None or halo_fold):
                     gsum = torch.empty((n, ho, wo, cs), dtype=self.dtype, device=dev)
-                ops.norm_act_bwd(desc, y, dy, dout, dskip, bstats, gsum)
+                if nk == NORM_BATCH and not use_running and self.bn_world > 1:
+                    ops.norm_act_bwd_synced(
+                        lambda extra: self._norm_desc(nk, norm, act, slope, co, halo_fold, stats, use_running,
+                                                      flags=base_flags | extra),
+                        y, dy, dout, dskip, bstats, gsum, self.bn_world)
+                else:
+                    desc = self._norm_desc(nk, norm, act, slope, co, halo_fold, stats, use_running, flags=base_flags)
+                    ops.norm_act_bwd(desc, y, dy, dout, dskip, bstats, gsum)
                 if res is not None:
                     self.add_grad(res, gsum if gsum is not None else dout)
                 if want_b:
@@ -532,10 +542,15 @@ class Tape:
         if nk != NORM_NONE and not use_running:
             if nk == NORM_BATCH and x.stats is not None:
                 stats = x.stats
+                if self.bn_world > 1:
+                    stats = x.stats.clone()       # the producers' slice holds this rank's sums; consumers sum a copy
+                    ops.bn_all_reduce(stats)
             else:
                 groups = n if nk == NORM_INSTANCE else 1
                 stats = self.arena.take((groups, c, 2))
                 ops.channel_stats(x.t, c, nk == NORM_INSTANCE, stats)
+                if nk == NORM_BATCH and self.bn_world > 1:
+                    ops.bn_all_reduce(stats)
         outv = out if out is not None else self.new_val(n, h, w, c, halo, halo_kind)
         desc = self._norm_desc(nk, norm, act, slope, c, outv.halo if outv.halo_kind == 'reflect' else 0, stats,
                                use_running, update=True)
@@ -556,12 +571,23 @@ class Tape:
                     bstats = self.arena.take((groups, c, 2))
                 fold = outv.halo if outv.halo_kind == 'reflect' else 0
                 flags = NORM_FLAG_ACCUM_F32 if x.grad32 is not None else 0
-                desc_b = self._norm_desc(nk, norm, act, slope, c, fold, stats, use_running, flags=flags)
+                synced = nk == NORM_BATCH and not use_running and self.bn_world > 1
+
+                def run_bwd(dy_target):
+                    if synced:
+                        ops.norm_act_bwd_synced(
+                            lambda extra: self._norm_desc(nk, norm, act, slope, c, fold, stats, use_running,
+                                                          flags=flags | extra),
+                            x.t, dy_target, dout, dskip, bstats, None, self.bn_world)
+                    else:
+                        desc_b = self._norm_desc(nk, norm, act, slope, c, fold, stats, use_running, flags=flags)
+                        ops.norm_act_bwd(desc_b, x.t, dy_target, dout, dskip, bstats, None)
+
                 if x.grad32 is not None:
-                    ops.norm_act_bwd(desc_b, x.t, x.grad32, dout, dskip, bstats, None)
+                    run_bwd(x.grad32)
                 else:
                     dy = torch.empty((n, h, w, ops.round_up(c, 8)), dtype=self.dtype, device=self.dev)
-                    ops.norm_act_bwd(desc_b, x.t, dy, dout, dskip, bstats, None)
+                    run_bwd(dy)
                     x.grads.append((dy, False))
                 if affine:
                     self.add_param_grad(norm.weight, bstats[0, :, 1].contiguous())

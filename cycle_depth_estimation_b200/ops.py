@@ -250,14 +250,16 @@ def _p(t):
 
 
 def norm_desc(norm, act, slope, eps, channels, pad, stats=None, gamma=None, beta=None, running_mean=None,
-              running_var=None, use_running=False, update_running=False, momentum=0.1, flags=0, conv_bias=None):
+              running_var=None, use_running=False, update_running=False, momentum=0.1, flags=0, conv_bias=None,
+              count_scale=1.0):
     return CdbNormDesc(norm, act, slope, eps, channels, pad, 1 if use_running else 0, 1 if update_running else 0,
                        momentum, flags, stats.data_ptr() if stats is not None else None,
                        gamma.data_ptr() if gamma is not None else None,
                        beta.data_ptr() if beta is not None else None,
                        running_mean.data_ptr() if running_mean is not None else None,
                        running_var.data_ptr() if running_var is not None else None,
-                       conv_bias.data_ptr() if (conv_bias is not None and update_running) else None)
+                       conv_bias.data_ptr() if (conv_bias is not None and update_running) else None,
+                       float(count_scale), 0)
 
 
 def channel_stats(y, c_real, per_image, stats):
@@ -375,6 +377,37 @@ def depth_metrics(gt, pred):
 # ---------------------------------------------------------------------------------------------
 EP_STATS_BATCH = 1
 NORM_FLAG_ACT_FIRST, NORM_FLAG_ACCUM_F32 = 1, 2
+NORM_FLAG_BWD_REDUCE_ONLY, NORM_FLAG_BWD_APPLY_ONLY = 4, 8
+
+
+def bn_world():
+    """Number of data-parallel ranks whose batch shards one BatchNorm normalises over: the
+    process-group size, or 1 without torch.distributed.  CDB_BN_SYNC=0 keeps per-rank statistics (what the reference's
+    own nn.DataParallel does, new_multi/networks5_ds.py:259)."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("CDB_BN_SYNC", "1") == "0":
+        return 1
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+def bn_all_reduce(t):
+    """Sums a [groups, C, 2] statistics tensor over the ranks (in place, on the current stream; capturable)."""
+    import torch.distributed as dist
+    dist.all_reduce(t)
+
+
+def norm_act_bwd_synced(desc_of, y, dy, dout, dskip, bstats, gsum, world):
+    """BatchNorm backward over a sharded batch: reduction pass, all-reduce of (sum ga, sum ga*xhat), apply pass.
+    desc_of(extra_flags) builds the descriptor.  Afterwards bstats holds the GLOBAL sums divided by world: every rank's
+    dy is scaled by world relative to the gradient of the global-mean loss (each rank differentiates its local mean), so
+    sum/world is the rank-independent value whose average over the ranks is the single-device affine gradient."""
+    norm_act_bwd(desc_of(NORM_FLAG_BWD_REDUCE_ONLY), y, dy, dout, dskip, bstats, gsum)
+    bn_all_reduce(bstats)
+    norm_act_bwd(desc_of(NORM_FLAG_BWD_APPLY_ONLY), y, dy, dout, dskip, bstats, gsum)
+    bstats.mul_(1.0 / world)
 
 
 def conv2d_fwd_ex(g, x, wpacked, rows_pad, kpad, out, bias=None, act=ACT_NONE, slope=0.0, stats=None,
@@ -575,10 +608,10 @@ def image_pool_apply(fake, pool, plan_dev, out):
 
 class ZeroArena:
     """Zero-initialised fp32 scratch for the many small accumulators of a network call (per-channel sums,
-    bias / affine gradients): one memset per ~256 KB instead of one fill kernel per accumulator. Slices keep
+    bias / affine gradients): one memset per 2 MB instead of one fill kernel per accumulator. Slices keep
     the chunk alive for as long as they are referenced (the statistics are saved for the backward pass)."""
 
-    CHUNK = 1 << 16
+    CHUNK = 1 << 19     # 2 MB per fill: ~25 fills per CycleGAN step instead of ~200 (each a graph node of its own)
 
     def __init__(self, device):
         self.device = device

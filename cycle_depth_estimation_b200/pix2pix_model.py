@@ -5,8 +5,10 @@ vanilla GAN loss (BCE) + ``lambda_L1`` * L1, Adam(lr, (beta1, 0.999)); D is upda
 ``Pix2PixModel`` mirrors the reference class (``initialize(opt)``, ``set_input``, ``forward``,
 ``backward_D``, ``backward_G``, ``optimize_parameters()``); like ``cycle_gan_model.CycleGANModel`` it does
 not inherit the reference's BaseModel (broken as shipped, SURVEY B-12).  Under ``torch.distributed`` the
-gradients are averaged with the bucketed all-reduce of ``cycle_gan_model.GradBuckets``; BatchNorm statistics
-stay per rank, as they do under the reference's own nn.DataParallel.
+gradients are averaged with the all-reduce of ``cycle_gan_model.GradBuckets`` and every BatchNorm layer normalises over
+the shards of ALL ranks (``ops.bn_world``: per-layer all-reduce of the sums forward and backward), so a
+sharded step equals the single-device step on the global batch (``tools/dp_bn_parity.py``; CDB_BN_SYNC=0 keeps the
+per-replica statistics of the reference's own nn.DataParallel).
 """
 from collections import OrderedDict
 

@@ -204,13 +204,22 @@ typedef struct CdbNormDesc {
   const float* conv_bias; /* [channels] or NULL: bias of the convolution in front of a training-mode BatchNorm. The
                            * convolution skips it (it cancels in the normalised output), but torch's running_mean
                            * tracks mean(conv + bias): the running update adds it back. */
+  float count_scale;      /* data-parallel BatchNorm: `stats` (and, in the apply pass, `bstats`) were summed over this many
+                           * equal shards of the batch (the per-layer all-reduce of sum, sum of squares
+                           * forward and sum dy, sum dy*xhat backward), so the element count is count_scale * n*h*w.
+                           * 0 or 1: single process. */
+  int32_t reserved_;
 } CdbNormDesc;
 /* ACT_FIRST: the layer is conv -> act -> norm (new_multi/networks5_ds.py:636-638,661-676): y is the
  *   ACTIVATED convolution output (the conv epilogue applied `act`), forward = norm only, backward
  *   multiplies the gradient w.r.t. y by act'(y) so that dy is the gradient of the raw convolution.
  * ACCUM_F32: backward only: dy is an fp32 view and receives dy += value (dense-block concatenation
  *   gradients, new_multi/networks5_ds.py:122-146, summed over all consumers of a channel prefix). */
-enum { CDB_NORM_FLAG_ACT_FIRST = 1, CDB_NORM_FLAG_ACCUM_F32 = 2 };
+/* BWD_REDUCE_ONLY / BWD_APPLY_ONLY: cdb_norm_act_bwd runs only its reduction pass (fills bstats, writes nothing else) /
+ *   only its apply pass (bstats as given), so that the caller can all-reduce bstats over the data-parallel ranks in
+ *   between. */
+enum { CDB_NORM_FLAG_ACT_FIRST = 1, CDB_NORM_FLAG_ACCUM_F32 = 2, CDB_NORM_FLAG_BWD_REDUCE_ONLY = 4,
+       CDB_NORM_FLAG_BWD_APPLY_ONLY = 8 };
 
 /* stats[g][c][2] += (sum, sum of squares) of y over pixels; g = image if per_image else 0. */
 int cdb_channel_stats(const CdbAct* y, int32_t c_real, int32_t per_image, float* stats, cdbStream_t stream);
