@@ -27,12 +27,9 @@ class SegCycle(CycleGANModel):
         if not opt.isTrain:
             raise NotImplementedError("SegCycle is a training-time model (models/seg_cycle.py:38-41 loads only the "
                                       "generators at test time: use CycleGANModel)")
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            # the task networks use BatchNorm: per-rank batch statistics would differ from the single-process step
-            # (a per-layer all-reduce of the statistics is not built)
-            raise NotImplementedError("SegCycle under data parallelism: the BatchNorm statistics of the task networks "
-                                      "are not synchronised across ranks")
+        # data parallelism: the CycleGAN part shards as in CycleGANModel; the task networks use BatchNorm, whose statistics
+        # the tape all-reduces per layer (ops.bn_world), so a sharded step equals the single-process one
+        # (tools/dp_bn_parity.py with DP_MODEL=segcycle)
         self._seg_ngf = int(getattr(opt, 'seg_ngf', 64))
         nc_a, nc_b = int(getattr(opt, 'seg_classes_A', 22)), int(getattr(opt, 'seg_classes_B', 28))
         dev = torch.device(getattr(opt, 'device', 'cuda'))

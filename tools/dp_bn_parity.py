@@ -19,7 +19,50 @@ from cycle_depth_estimation_b200 import ops
 from cycle_depth_estimation_b200.pix2pix_model import Pix2PixModel
 
 PREC = os.environ.get("DP_PREC", "tf32x3")
+MODEL = os.environ.get("DP_MODEL", "pix2pix")
 torch.manual_seed(0)
+if MODEL == "segcycle":
+    # SegCycle (CycleGAN + four task-network passes with BatchNorm): global batch 4 at 128x128, eager steps, 12 losses
+    import random
+    import bench
+    from cycle_depth_estimation_b200.seg_cycle import SegCycle
+    random.seed(1234)
+    m = SegCycle()
+    o = bench.make_opt("cuda", False)
+    o.seg_ngf = 16
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.initialize(o)
+    g = torch.Generator().manual_seed(5)
+    B = 4
+    A, Bt = torch.rand((B, 3, 128, 128), generator=g) * 2 - 1, torch.rand((B, 3, 128, 128), generator=g) * 2 - 1
+    la = torch.randint(0, 22, (B, 1, 128, 128), generator=g)
+    lb = torch.randint(0, 28, (B, 1, 128, 128), generator=g)
+    per = B // world
+    sl = slice(rank * per, (rank + 1) * per)
+    losses = []
+    with ops.precision(PREC):
+        for _ in range(2):
+            m.set_input({'img_source': A[sl].cuda(), 'img_target': Bt[sl].cuda(), 'lab_source': la[sl].cuda(),
+                         'lab_target': lb[sl].cuda()})
+            m.optimize_parameters('train')
+            l = torch.tensor(list(m.get_current_losses().values()), dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(l)
+                l /= world
+            losses.append(l.cpu())
+    path = os.path.join(ROOT, "gpurun_out", "dp_bn_ref_segcycle_%s.pt" % PREC)
+    if world == 1:
+        torch.save({'losses': losses}, path)
+        print("segcycle reference written:", [round(float(x), 5) for x in losses[1]])
+    else:
+        if rank == 0:
+            ref = torch.load(path)
+            worst = max(float(((a - b).abs() / b.abs().clamp_min(1e-12)).max()) for a, b in zip(losses, ref['losses']))
+            print("segcycle precision %s, world %d, CDB_BN_SYNC=%s: worst relative error of the 12 losses over 2 steps %.3e"
+                  % (PREC, world, os.environ.get("CDB_BN_SYNC", "1"), worst))
+        dist.barrier()
+        dist.destroy_process_group()
+    sys.exit(0)
 opt = argparse.Namespace(input_nc=3, output_nc=3, ngf=32, ndf=32, netG='unet_128', netD='basic', n_layers_D=3, norm='batch',
                          no_dropout=True, init_type='normal', init_gain=0.02, no_lsgan=True, pool_size=0, lr=2e-4, beta1=0.5,
                          lambda_L1=100.0, isTrain=True, device='cuda', direction='AtoB')
