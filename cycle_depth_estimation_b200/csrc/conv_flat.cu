@@ -31,7 +31,7 @@ struct FlatParams {
   int32_t tiles_per_img, n_img, n_tiles_n, bn;
   int32_t dom_h, dom_w;              // valid outputs: h < dom_h, w < dom_w with (h, w) = divmod(f, wp)
   int32_t halo_rows;                 // extra rows after the BM block (multiple of 8)
-  int32_t a_stages, b_stages, b_taps;
+  int32_t a_stages, b_stages, b_taps, prewait;
   int32_t cout, cstore, out_dtype, act, stats_on, stats_batch, use_base_offset, sleep_ns, rotate, fast_out, out_rows_per_img;
   int32_t tf32, kelems;              // TF32 variant: fp32 operands, 32 channels per 128-byte K block (else 64 bf16)
   int32_t vec_out, round_out;        // fp32 NHWC output: float4 stores; round stored values to TF32
@@ -235,6 +235,73 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
         const uint32_t d1 = d0 + static_cast<uint32_t>(acc_cols);
         bool first = true;
         if (dbgl && local == 0) p.dbg[1] = clock64();
+        if (kPair && p.prewait && b_taps == p.S) {
+          // Pair mode with the S weight tiles of a filter row in one stage: the barriers of group g + 1 are waited for
+          // BEFORE the last instruction of group g is issued, so the round trips (two mbarrier polls by 32 lanes, a vote,
+          // a fence: ~450 cycles) run while the instructions of group g execute instead of leaving the tensor pipe idle
+          // between groups (tools/flat_dbg.py: 149 cycles per instruction against the 128 of the tile shape).
+          const int groups = p.k_chunks * p.R;
+          bool ready = false;
+          for (int gi = 0; gi < groups && ok; ++gi) {
+            if (!ready) {
+              tw0 = dbgl ? clock64() : 0;
+              ok = mbar_wait(smem_u32(&bar_afull[sa]), pa, abort_flag);
+              ok = __all_sync(0xffffffffu, ok);
+              if (!ok) break;
+              if (dbgl) wait_a += clock64() - tw0;
+              tw0 = dbgl ? clock64() : 0;
+              ok = mbar_wait(smem_u32(&bar_bfull[sb]), pb, abort_flag);
+              ok = __all_sync(0xffffffffu, ok);
+              if (!ok) break;
+              if (dbgl) wait_b += clock64() - tw0;
+              tc_fence_after();
+            }
+            ready = false;
+            const uint32_t abase = a_ring + sa * a_bytes;
+            if (dbgl && first) p.dbg[2] = clock64();
+            const int n_instr = 4 * b_taps;
+            auto issue = [&](int i) {
+              const int j = i >> 2, k = i & 3;
+              const uint32_t a0 = abase + static_cast<uint32_t>(j * p.dil) * 128u;
+              const uint64_t da0 = make_smem_desc_unaligned(a0, 16, 1024, kLayoutSW128, p.use_base_offset);
+              const uint64_t db = make_smem_desc(b_ring + (sb * b_taps + j) * b_bytes, 16, 1024, kLayoutSW128);
+              const uint32_t acc = (first && i == 0) ? 0u : 1u;
+              if (tf32) umma2_tf32(d0, da0 + 2u * k, db + 2u * k, idesc, acc);
+              else umma2_f16(d0, da0 + 2u * k, db + 2u * k, idesc, acc);
+            };
+            if (elect_one()) {
+              for (int i = 0; i < n_instr - 1; ++i) issue(i);
+            }
+            __syncwarp();
+            const int nsa = sa + 1 == p.a_stages ? 0 : sa + 1, nsb = sb + 1 == p.b_stages ? 0 : sb + 1;
+            const uint32_t npa = sa + 1 == p.a_stages ? pa ^ 1u : pa, npb = sb + 1 == p.b_stages ? pb ^ 1u : pb;
+            if (gi + 1 < groups) {
+              tw0 = dbgl ? clock64() : 0;
+              ok = mbar_wait(smem_u32(&bar_afull[nsa]), npa, abort_flag);
+              ok = __all_sync(0xffffffffu, ok);
+              if (!ok) break;
+              if (dbgl) wait_a += clock64() - tw0;
+              tw0 = dbgl ? clock64() : 0;
+              ok = mbar_wait(smem_u32(&bar_bfull[nsb]), npb, abort_flag);
+              ok = __all_sync(0xffffffffu, ok);
+              if (!ok) break;
+              if (dbgl) wait_b += clock64() - tw0;
+              tc_fence_after();
+              ready = true;
+            }
+            if (elect_one()) {
+              issue(n_instr - 1);
+              umma2_commit(smem_u32(&bar_bempty[sb]));
+              umma2_commit(smem_u32(&bar_aempty[sa]));
+            }
+            __syncwarp();
+            first = false;
+            sa = nsa;
+            pa = npa;
+            sb = nsb;
+            pb = npb;
+          }
+        } else
         for (int c = 0; c < p.k_chunks && ok; ++c) {
           for (int r = 0; r < p.R && ok; ++r) {
             tw0 = dbgl ? clock64() : 0;
@@ -687,6 +754,7 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   if (b_stages < 2) return fail(CDB_ERR_UNSUPPORTED, "flat conv: shared memory budget");
   prm.a_stages = a_stages;
   prm.b_stages = b_stages;
+  prm.prewait = getenv("CDB_MMA_PREWAIT") ? atoi(getenv("CDB_MMA_PREWAIT")) : 1;
   const size_t smem = (size_t)a_stages * a_bytes + (size_t)b_stages * prm.b_taps * b_bytes + slab_bytes + 1024;
   static size_t smem_attr[2] = {0, 0};
   if (smem > smem_attr[pair ? 1 : 0]) {
