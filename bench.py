@@ -193,9 +193,12 @@ def time_dominant_kernel(peaks, iters=40):
     achieved = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_burst"],
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this launch
-            # (profiles/r01_ncu_full_flat_r01b.json): 19.10 MB read, 0 written (the output stays in L2)
-            "traffic": 19101696, "kernel": "igemm_flat_kernel",
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the round-2 ncu --set full capture of this very
+            # launch (profiles/r02_ncu_full_kernels.json, igemm_flat_kernel<0>, grid 136): 19.12 MB read, 0 written (the
+            # 16.8 MB output stays in L2).  A profiler counter cannot be read inside an unprofiled run: the figure is the
+            # committed capture's, not a live measurement; the algorithmic bytes are 17.8 MB input + 1.2 MB weights.
+            "traffic": 19121664, "traffic_source": "profiles/r02_ncu_full_kernels.json (ncu --set full of this launch)",
+            "kernel": "igemm_flat_kernel",
             "shape": "3x3 conv 256->256, 64x64, batch 8 (M=32768 N=256 K=2304), fused IN statistics",
             "us_per_launch": ms * 1e3, "peak_source": peaks["source"] + " (burst: kernel timed alone)"}
 
