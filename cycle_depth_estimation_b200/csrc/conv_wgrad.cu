@@ -324,6 +324,195 @@ wgrad_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgPara
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Row-sharing weight gradient (stride-1 layers over a materialised-padding input whose S-side rows are exactly one
+// 64-pixel K block: the 3x3 256 -> 256 residual-block layers at 64 x 64).  The S taps of a filter row read
+// OVERLAPPING windows of ONE input row: the row (W + S - 1 pixels, padded to 72) is staged once per K block and the taps
+// address it through MN-major descriptors whose start is moved by s rows of 128 B — the trick of the flat forward
+// kernel, on the K axis.  A CTA pair (cta_group::2, M = 256 = all dy channels) holds S accumulators of 128 x-channels
+// (S * 128 <= 512 TMEM columns): per K block each SM pulls 16 KB of dy + 9 KB of x for S * 256 tensor cycles
+// (33 B/clk) instead of 16 + 16 KB per 512 cycles for ONE tap (64 B/clk, above what an SM gets from L2).
+// Work item = (filter row r, 128-channel half of x, split of the image rows); partials go to the same workspace
+// layout as wgrad_kernel's, so wgrad_finalize_kernel is shared.
+// -------------------------------------------------------------------------------------------------
+struct WgRowParams {
+  int32_t H, n_img, R, S, n_halves, splits, rows_per_split, stages, mpad, npad, n_taps;
+  int32_t x_wp, x_rows_per_img;   // pitch (pixels) and pixel rows per image of the padded input
+  float* ws;
+  int* abort_flag;
+};
+struct WgRowMaps {
+  CUtensorMap dy;  // box {64 ch, 64 px, 1, 1}
+  CUtensorMap x;   // the padded input as a flat pixel matrix [n * Hp * Wp, C]: box {64 ch, 72 px}
+};
+constexpr int kRowABytes = 2 * kChunkBytes;     // 128 dy channels x 64 pixels
+constexpr int kRowBBytes = 72 * 128;            // 64 x channels x 72 pixels
+constexpr int kRowStageBytes = kRowABytes + kRowBBytes;
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_rowshare_kernel(const __grid_constant__ WgRowMaps maps, const __grid_constant__ WgRowParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kWgMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kWgMaxStages];
+  __shared__ __align__(8) uint64_t bar_tfull;
+  __shared__ __align__(8) uint64_t bar_tempty;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ int abort_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = cluster_ctarank();
+  const int total_items = p.R * p.n_halves * p.splits;
+  const int item_first = static_cast<int>(blockIdx.x >> 1), item_step = static_cast<int>(gridDim.x >> 1);
+  const int k_total = p.n_img * p.H;   // K blocks = image rows
+
+  if (threadIdx.x == 0) {
+    abort_smem = 0;
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&bar_tfull), 1);
+    mbar_init(smem_u32(&bar_tempty), 256);   // the epilogue threads of both CTAs
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(smem_u32(&tmem_base_smem), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  volatile int* abort_flag = &abort_smem;
+
+  auto decode = [&](int item, int& split, int& half, int& r) {
+    split = item % p.splits;
+    item /= p.splits;
+    half = item % p.n_halves;
+    r = item / p.n_halves;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int item = item_first; item < total_items && ok; item += item_step) {
+        int split, half, r;
+        decode(item, split, half, r);
+        const int kt0 = split * p.rows_per_split;
+        const int kt1 = min(k_total, kt0 + p.rows_per_split);
+        for (int kt = kt0; kt < kt1; ++kt) {
+          const int n = kt / p.H, h = kt - n * p.H;
+          if (!mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u, abort_flag)) {
+            ok = false;
+            break;
+          }
+          const uint32_t full_local = smem_u32(&bar_full[stage]);
+          const uint32_t full0 = mapa_shared(full_local, 0);
+          const uint32_t sa = smem_base + stage * kRowStageBytes;
+          if (rank == 0) mbar_arrive_expect_tx(full_local, 2u * kRowStageBytes);
+          // this CTA's 128 dy channels (two 64-channel chunks) of image row (n, h)
+          tma_load_4d_pair(&maps.dy, full0, sa, static_cast<int>(rank) * 128, 0, h, n);
+          tma_load_4d_pair(&maps.dy, full0, sa + kChunkBytes, static_cast<int>(rank) * 128 + 64, 0, h, n);
+          // this CTA's 64 of the item's 128 x channels, padded-input row h + r, pixels 0 .. 71 (beyond the row: zero fill)
+          // (the 72-pixel box runs past the 66-pixel row into the next one: those rows are never addressed)
+          tma_load_2d_pair(&maps.x, full0, sa + kRowABytes, half * 128 + static_cast<int>(rank) * 64,
+                           n * p.x_rows_per_img + (h + r) * p.x_wp);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {   // whole warp; the elected lane issues (see wgrad_kernel)
+      const uint32_t idesc = make_idesc(1u, 1u, 1u, 256u, 128u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      bool ok = true;
+      for (int item = item_first; item < total_items && ok; item += item_step, ++local) {
+        int split, half, r;
+        decode(item, split, half, r);
+        const int kt0 = split * p.rows_per_split;
+        const int kt1 = min(k_total, kt0 + p.rows_per_split);
+        ok = mbar_wait(smem_u32(&bar_tempty), (local & 1u) ^ 1u, abort_flag);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        tc_fence_after();
+        for (int kt = kt0; kt < kt1; ++kt) {
+          ok = mbar_wait(smem_u32(&bar_full[stage]), phase, abort_flag);
+          ok = __all_sync(0xffffffffu, ok);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kRowStageBytes;
+          if (elect_one()) {
+            // MN-major, 128B swizzle: A = 128 channels (LBO = chunk distance) x 16 pixels per instruction (2048 B step);
+            // B = 64 channels of this CTA, start moved by s pixel rows of 128 B for tap s
+            const uint64_t da = make_smem_desc(sa, kChunkBytes, 1024, kLayoutSW128);
+            for (int s = 0; s < p.S; ++s) {
+              const uint64_t db = make_smem_desc(sa + kRowABytes + static_cast<uint32_t>(s) * 128u, kChunkBytes, 1024,
+                                                 kLayoutSW128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma2_f16(tmem_base + static_cast<uint32_t>(s) * 128u, da + 128u * k, db + 128u * k, idesc,
+                          (kt > kt0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit(smem_u32(&bar_empty[stage]));
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (ok) {
+          if (elect_one()) umma2_commit(smem_u32(&bar_tfull));
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const uint32_t tempty_remote = mapa_shared(smem_u32(&bar_tempty), 0);
+    int local = 0;
+    for (int item = item_first; item < total_items; item += item_step, ++local) {
+      int split, half, r;
+      decode(item, split, half, r);
+      if (!mbar_wait(smem_u32(&bar_tfull), local & 1u, abort_flag)) break;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      for (int c0 = 0; c0 < p.S * 128; c0 += 16) {
+        const int s = c0 >> 7, cn = c0 & 127;
+        float* dst = p.ws + ((static_cast<int64_t>(split) * p.n_taps + r * p.S + s) * p.mpad +
+                             static_cast<int>(rank) * 128 + row) * p.npad + half * 128 + cn;
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(tempty_remote);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0 && abort_smem && p.abort_flag) atomicExch(p.abort_flag, 1);
+  if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // Sums the split-K partials and scatters them into the fp32 filter gradient W4[d0][d1][R][S].
 // m_is_d0: the M side of the GEMM holds d0 (else d1). rowpack: tap = r, the d1-side index is
 // s*rowpack + ch.
@@ -459,6 +648,7 @@ struct WgPlan {
   int cM, cN, mpad, npad, bn, m_tiles, n_tiles;
   int tile_w, tile_h, tile_n, tiles_w, tiles_h, tiles_n, k_tiles, splits, k_per_split, n_taps;
   int pair;  // CTA pairs (cta_group::2): two row tiles per work item, the N-side operand split between the CTAs
+  int rowshare;  // wgrad_rowshare_kernel: the S taps of a filter row share one staged input row (see the kernel)
 };
 
 static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g_act, WgPlan* pl) {
@@ -510,6 +700,25 @@ static int plan_wgrad(const CdbConvGeom* g, const CdbAct* s_act, const CdbAct* g
   if (splits > max_splits) splits = max_splits;
   pl->k_per_split = ceil_div(pl->k_tiles, splits);
   pl->splits = ceil_div(pl->k_tiles, pl->k_per_split);
+  // row-sharing kernel: bf16, stride-1 Conv2d over a materialised-padding input, the dy rows are exactly one 64-pixel K
+  // block, M = the 256 dy channels (one CTA pair), x channels in halves of 128, S accumulators of 128 columns in TMEM
+  static const int rowshare_env = getenv("CDB_WGRAD_ROWSHARE") ? atoi(getenv("CDB_WGRAD_ROWSHARE")) : 1;
+  pl->rowshare = (rowshare_env && pl->pair && !tf32 && !g->transposed && g->stride == 1 && g->dil == 1 && g->pad_h == 0 &&
+                  g->pad_w == 0 && pl->m_is_s && s_act->w == 64 && pl->tile_w == 64 && pl->tile_h == 1 && pl->cM == 256 &&
+                  pl->cN % 128 == 0 && g->s * 128 <= 512 && g->s <= 8 && g_act->w >= s_act->w + g->s - 1 &&
+                  g_act->h >= s_act->h + g->r - 1 && g_act->sh == (int64_t)g_act->w * g_act->sw &&
+                  g_act->sn == (int64_t)g_act->h * g_act->w * g_act->sw)
+                     ? 1
+                     : 0;
+  if (pl->rowshare) {
+    const int k_rows = s_act->n * s_act->h;
+    const int row_items = g->r * (pl->cN / 128);
+    int rs = (sm_count() / 2) / (row_items > 0 ? row_items : 1);
+    if (rs < 1) rs = 1;
+    if (rs > k_rows / 8) rs = k_rows / 8 > 0 ? k_rows / 8 : 1;
+    pl->k_per_split = ceil_div(k_rows, rs);
+    pl->splits = ceil_div(k_rows, pl->k_per_split);
+  }
   return CDB_OK;
 }
 
@@ -742,6 +951,73 @@ extern "C" int cdb_conv2d_wgrad(const CdbConvGeom* g, const CdbAct* x, const Cdb
   prm.prewait = prewait_env;
   prm.ws = static_cast<float*>(workspace);
   prm.abort_flag = device_abort_flag_ptr();
+  if (pl.rowshare) {
+    WgRowMaps rmaps;
+    memset(&rmaps, 0, sizeof(rmaps));
+    {
+      uint64_t dims[4] = {(uint64_t)s_act->c, (uint64_t)s_act->w, (uint64_t)s_act->h, (uint64_t)s_act->n};
+      uint64_t str[3] = {(uint64_t)s_act->sw * 2, (uint64_t)s_act->sh * 2, (uint64_t)s_act->sn * 2};
+      const uint32_t rbox[4] = {64u, 64u, 1u, 1u};
+      int rc = make_tmap(&rmaps.dy, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, s_act->ptr, dims, str, rbox);
+      if (rc) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)g_act->c, (uint64_t)g_act->n * g_act->h * g_act->w};
+      uint64_t str[1] = {(uint64_t)g_act->sw * 2};
+      const uint32_t rbox[2] = {64u, 72u};
+      int rc = make_tmap(&rmaps.x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_act->ptr, dims, str, rbox);
+      if (rc) return rc;
+    }
+    WgRowParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.H = s_act->h;
+    rp.n_img = s_act->n;
+    rp.R = g->r;
+    rp.S = g->s;
+    rp.n_halves = pl.cN / 128;
+    rp.splits = pl.splits;
+    rp.rows_per_split = pl.k_per_split;
+    rp.mpad = pl.mpad;
+    rp.npad = pl.npad;
+    rp.n_taps = pl.n_taps;
+    rp.x_wp = g_act->w;
+    rp.x_rows_per_img = g_act->h * g_act->w;
+    rp.ws = static_cast<float*>(workspace);
+    rp.abort_flag = device_abort_flag_ptr();
+    int rstages = (200 * 1024) / kRowStageBytes;
+    if (rstages > kWgMaxStages) rstages = kWgMaxStages;
+    rp.stages = rstages;
+    const size_t rsmem = (size_t)rstages * kRowStageBytes + 1024;
+    static size_t rsmem_attr = 0;
+    if (rsmem > rsmem_attr) {
+      CDB_CUDA_OK(cudaFuncSetAttribute(wgrad_rowshare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+      rsmem_attr = rsmem;
+    }
+    const int items = rp.R * rp.n_halves * rp.splits;
+    const int clusters = items < sm_count() / 2 ? items : sm_count() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = rsmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CDB_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_rowshare_kernel, rmaps, rp));
+    CDB_LAUNCH_OK();
+    const int64_t rtotal = (int64_t)d0 * d1 * g->r * g->s;
+    int rblocks = (int)((rtotal + 255) / 256);
+    if (rblocks > 148 * 8) rblocks = 148 * 8;
+    wgrad_finalize_kernel<<<rblocks, 256, 0, stream>>>(static_cast<const float*>(workspace), dw4, d0, d1, g->r, g->s,
+                                                      pl.n_taps, pl.splits, pl.mpad, pl.npad, pl.m_is_s, 0, accumulate);
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
   const int stage_bytes = (128 / cpc) * kChunkBytes + pl.tg * (pl.bn / cpc) * kChunkBytes / (pl.pair ? 2 : 1);
   // shared-memory budget of the operand ring.  The weight gradients run on a companion stream next to the norm /
   // activation backward kernels of the main stream (engine._SideStream): a ring that leaves room for one of their CTAs
