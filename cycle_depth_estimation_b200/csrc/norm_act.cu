@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace cdb {
 
@@ -987,9 +988,266 @@ __global__ void __launch_bounds__(256, OCC) norm_bwd_stream_kernel(NormBwdParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged form of the streaming backward.  The register-load kernel above exposes one DRAM round trip per loop
+// iteration of every warp (8 iterations per thread on the residual-block shape) and one more for the reflect-fold
+// reads of every border pixel: 2.5-3.2 TB/s of 6.5 on the padded layers against 4.8 TB/s on the unpadded ones.
+// Here the operands are contiguous row segments (every view has pixel stride == C), so ONE thread streams them with
+// cp.async.bulk into a ring of shared-memory stages, `stages` chunks ahead of the eight warps, which read 16-byte
+// vectors from shared memory (thread t owns vectors t, t + 256 of a chunk: conflict-free, and t % cv is the thread's
+// channel vector for the whole kernel) and write dy / gsum straight from registers.
+//   * chunk = kTmaV * 256 / cv pixels of one image row (8 KB per operand); the dout segment is staged together with
+//     its `pad` halo pixels on either side, so the column images of the reflect fold are shared-memory reads; only
+//     the 2 * pad mirror rows of an image still come from global memory;
+//   * a block owns a contiguous chunk range of ONE image, the grid is (blocks per image, images), ~2 blocks per SM;
+//   * the apply pass walks its range backwards: what the reduce pass read last is still in L2;
+//   * same arithmetic as norm_bwd_stream_kernel (sum ga / sum ga*y, y > mean mask, 3-coefficient apply, f32x2 pairs).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaMaxStages = 8;
+
+struct TmaGeom {
+  int cpr;           // chunks per image row
+  int stages;
+  int off_d, off_s;  // byte offsets of the dout / dskip slots inside a stage (y at 0)
+  int stage_bytes;
+  int hint;
+};
+
+__device__ __forceinline__ void add_vec_pairs(uint32_t saddr, float2* g) {
+  float2 t[4];
+  unpack8_pairs(ld_shared_v4(saddr), t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = __fadd2_rn(g[i], t[i]);
+}
+__device__ __forceinline__ void add_vec_pairs(const __nv_bfloat16* gptr, float2* g) {
+  float2 t[4];
+  unpack8_pairs(ld16(gptr), t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = __fadd2_rn(g[i], t[i]);
+}
+
+// V = 16-byte vectors per thread, operand and chunk (chunk = V * 4 KB per operand)
+template <bool kApply, int ACT, bool HAS_SKIP, bool WRITE_GSUM, int V>
+__global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, TmaGeom tg, int* abort_global) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  __shared__ uint64_t bars[2 * kTmaMaxStages];   // full[s] = bars[s], empty[s] = bars[kTmaMaxStages + s]
+  __shared__ int abort_smem;
+  const int stages = tg.stages, cpr = tg.cpr;
+  float* red = reinterpret_cast<float*>(tma_smem + stages * tg.stage_bytes);   // reduce pass only (16 KB)
+  const int tid = threadIdx.x;
+  const int cv = p.vt;                             // channel vectors per pixel (C / 8, a power of two <= 256)
+  const int lanes = 256 / cv, PX = V * lanes;      // pixels per chunk
+  const int n = blockIdx.y;
+  const int cpi = p.H * cpr;                       // chunks per image
+  const int k0 = static_cast<int>(static_cast<int64_t>(blockIdx.x) * cpi / gridDim.x);
+  const int k1 = static_cast<int>(static_cast<int64_t>(blockIdx.x + 1) * cpi / gridDim.x);
+  const int nk = k1 - k0;
+  const int W = p.W, C = p.C, pad = p.pad, H = p.H;
+  const int ysh = static_cast<int>(p.y.sh), dsh = static_cast<int>(p.dout.sh), ssh = static_cast<int>(p.dskip.sh);
+  const __nv_bfloat16* yimg = static_cast<const __nv_bfloat16*>(p.y.ptr) + n * p.y.sn;
+  const __nv_bfloat16* dimg = static_cast<const __nv_bfloat16*>(p.dout.ptr) + n * p.dout.sn;
+  const __nv_bfloat16* simg = HAS_SKIP ? static_cast<const __nv_bfloat16*>(p.dskip.ptr) + n * p.dskip.sn : nullptr;
+  const uint32_t stage_base = smem_u32(tma_smem);
+  const uint32_t bar_base = smem_u32(&bars[0]);
+  uint64_t pol = 0;
+  if (tg.hint) pol = kApply ? l2_policy_evict_first() : l2_policy_evict_last();
+
+  // the block walks its chunks k0 .. k1-1 (reduce) or k1-1 .. k0 (apply); (h, c) = (row, chunk of the row)
+  const int kfirst = kApply ? k1 - 1 : k0;
+  int h = kfirst / cpr, c = kfirst - h * cpr;
+  int ih = h, ic = c;                              // producer position (thread 0)
+  auto issue = [&](int stage) {
+    const int w0 = ic * PX;
+    const int npx = min(PX, W - w0);
+    const uint32_t bytes = static_cast<uint32_t>(npx * C * 2);
+    const int right = min(2 * pad, W + pad - (w0 + npx));           // halo / neighbour pixels staged after the segment
+    const uint32_t dbytes = static_cast<uint32_t>((npx + pad + right) * C * 2);
+    const uint32_t full = bar_base + stage * 8;
+    const uint32_t dst = stage_base + stage * tg.stage_bytes;
+    mbar_arrive_expect_tx(full, bytes * (HAS_SKIP ? 2 : 1) + dbytes);
+    if (tg.hint) {
+      bulk_load_1d_hint(dst, yimg + ih * ysh + w0 * C, bytes, full, pol);
+      bulk_load_1d_hint(dst + tg.off_d, dimg + ih * dsh + (w0 - pad) * C, dbytes, full, pol);
+      if (HAS_SKIP) bulk_load_1d_hint(dst + tg.off_s, simg + ih * ssh + w0 * C, bytes, full, pol);
+    } else {
+      bulk_load_1d(dst, yimg + ih * ysh + w0 * C, bytes, full);
+      bulk_load_1d(dst + tg.off_d, dimg + ih * dsh + (w0 - pad) * C, dbytes, full);
+      if (HAS_SKIP) bulk_load_1d(dst + tg.off_s, simg + ih * ssh + w0 * C, bytes, full);
+    }
+    if (kApply) {
+      if (--ic < 0) { ic = cpr - 1; --ih; }
+    } else {
+      if (++ic == cpr) { ic = 0; ++ih; }
+    }
+  };
+
+  int issued = 0;
+  if (tid == 0) {
+    abort_smem = 0;
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(bar_base + s * 8, 1);
+      mbar_init(bar_base + (kTmaMaxStages + s) * 8, 8);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    for (; issued < stages && issued < nk; ++issued) issue(issued);   // the ring is filled before the coefficients are read
+  }
+  __syncthreads();
+  volatile int* abort_flag = &abort_smem;
+
+  const int v = tid % cv, lane = tid / cv;
+  const int grp = p.per_image ? n : 0;
+  float2 mean2[4], A2[kApply ? 4 : 1], B2[kApply ? 4 : 1], D2[kApply ? 4 : 1];
+  float2 sg[kApply ? 1 : 4], sgy[kApply ? 1 : 4];
+  if (!kApply) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sg[kApply ? 0 : i] = sgy[kApply ? 0 : i] = make_float2(0.f, 0.f);
+  }
+  {
+    const float4* st4 = reinterpret_cast<const float4*>(p.stats + (static_cast<int64_t>(grp) * C + v * 8) * 2);
+    const float4* bs4 = reinterpret_cast<const float4*>(p.bstats + (static_cast<int64_t>(grp) * C + v * 8) * 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 st = st4[i];                      // (s1, s2) of channels 2i, 2i + 1
+      float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kApply) bs = bs4[i];
+      const float s1[2] = {st.x, st.z}, s2[2] = {st.y, st.w}, b1[2] = {bs.x, bs.z}, b2[2] = {bs.y, bs.w};
+      float mean[2], a[2], b[2], dd[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        mean[e] = s1[e] * p.inv_count;
+        const float var = fmaxf(s2[e] * p.inv_count - mean[e] * mean[e], 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const float m1 = b1[e] * p.inv_count, m2 = b2[e] * p.inv_count;
+        a[e] = rstd;
+        b[e] = -rstd * rstd * m2;
+        dd[e] = rstd * rstd * m2 * mean[e] - rstd * m1;
+      }
+      mean2[i] = make_float2(mean[0], mean[1]);
+      if (kApply) {
+        A2[kApply ? i : 0] = make_float2(a[0], a[1]);
+        B2[kApply ? i : 0] = make_float2(b[0], b[1]);
+        D2[kApply ? i : 0] = make_float2(dd[0], dd[1]);
+      }
+    }
+  }
+  const __nv_bfloat16* db = dimg + v * 8;   // mirror rows of the reflect fold (global memory, 2 * pad rows per image)
+  __nv_bfloat16* ob = kApply ? static_cast<__nv_bfloat16*>(p.dy.ptr) + n * p.dy.sn + v * 8 : nullptr;
+  __nv_bfloat16* gb = (kApply && WRITE_GSUM) ? static_cast<__nv_bfloat16*>(p.gsum.ptr) + n * p.gsum.sn + v * 8 : nullptr;
+  const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
+  const int osh = static_cast<int>(p.dy.sh), osw = static_cast<int>(p.dy.sw);
+  const float slope = p.slope;
+  const uint32_t pad_bytes = static_cast<uint32_t>(pad * C * 2);
+  int s = 0, ps = 0;            // stage of this chunk / of the previous one
+  uint32_t ph = 0, pph = 0;     // and their phase parities
+  for (int i = 0; i < nk; ++i) {
+    if (tid == 0 && i >= 1 && issued < nk) {
+      // refill the stage the previous chunk was read from, once all eight warps have released it
+      if (mbar_wait(bar_base + (kTmaMaxStages + ps) * 8, pph, abort_flag)) {
+        issue(ps);
+        ++issued;
+      }
+    }
+    const int w0 = c * PX;
+    const int npx = min(PX, W - w0);
+    if (!mbar_wait(bar_base + s * 8, ph, abort_flag)) break;
+    const uint32_t sbase = stage_base + s * tg.stage_bytes;
+    const uint32_t src = sbase + tid * 16;
+    const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const int px = lane + u * lanes;
+      if (px >= npx) break;
+      const int w = w0 + px;
+      float2 y2[4], g2[4];
+      unpack8_pairs(ld_shared_v4(src + u * 4096), y2);
+      unpack8_pairs(ld_shared_v4(src + tg.off_d + pad_bytes + u * 4096), g2);
+      if (HAS_SKIP) add_vec_pairs(src + tg.off_s + u * 4096, g2);
+      if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) {
+        constexpr int kNone = -(1 << 30);
+        const int w1 = (w >= 1 && w <= pad) ? -w : kNone;
+        const int w2 = (w <= W - 2 && w >= W - 1 - pad) ? 2 * (W - 1) - w : kNone;
+        // column images: inside the staged segment (position of pixel ww: ww - (w0 - pad))
+        const uint32_t dslot = sbase + tg.off_d + v * 16;
+        if (w1 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w1 - w0 + pad) * C * 2), g2);
+        if (w2 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w2 - w0 + pad) * C * 2), g2);
+        if (hborder) {
+          const int h1 = (h >= 1 && h <= pad) ? -h : kNone;
+          const int h2 = (h <= H - 2 && h >= H - 1 - pad) ? 2 * (H - 1) - h : kNone;
+          if (h1 != kNone) {
+            add_vec_pairs(db + h1 * dsh + w * C, g2);
+            if (w1 != kNone) add_vec_pairs(db + h1 * dsh + w1 * C, g2);
+            if (w2 != kNone) add_vec_pairs(db + h1 * dsh + w2 * C, g2);
+          }
+          if (h2 != kNone) {
+            add_vec_pairs(db + h2 * dsh + w * C, g2);
+            if (w1 != kNone) add_vec_pairs(db + h2 * dsh + w1 * C, g2);
+            if (w2 != kNone) add_vec_pairs(db + h2 * dsh + w2 * C, g2);
+          }
+        }
+      }
+      if (kApply) {
+        if (WRITE_GSUM) st16(gb + h * gsh + w * gsw, pack8_pairs(g2));
+        float2 o2[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 ga = mask_pair<ACT>(g2[q], y2[q], mean2[q], slope);
+          o2[q] = __ffma2_rn(ga, A2[kApply ? q : 0], __ffma2_rn(y2[q], B2[kApply ? q : 0], D2[kApply ? q : 0]));
+        }
+        st16(ob + h * osh + w * osw, pack8_pairs(o2));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 ga = mask_pair<ACT>(g2[q], y2[q], mean2[q], slope);
+          sg[kApply ? 0 : q] = __fadd2_rn(sg[kApply ? 0 : q], ga);
+          sgy[kApply ? 0 : q] = __ffma2_rn(ga, y2[q], sgy[kApply ? 0 : q]);
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(bar_base + (kTmaMaxStages + s) * 8);   // the stage may be refilled
+    ps = s;
+    pph = ph;
+    if (++s == stages) { s = 0; ph ^= 1u; }
+    if (kApply) {
+      if (--c < 0) { c = cpr - 1; --h; }
+    } else {
+      if (++c == cpr) { c = 0; ++h; }
+    }
+  }
+  if (!kApply) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      red[((2 * q) * 2) * 256 + tid] = sg[kApply ? 0 : q].x;
+      red[((2 * q) * 2 + 1) * 256 + tid] = sgy[kApply ? 0 : q].x;
+      red[((2 * q + 1) * 2) * 256 + tid] = sg[kApply ? 0 : q].y;
+      red[((2 * q + 1) * 2 + 1) * 256 + tid] = sgy[kApply ? 0 : q].y;
+    }
+    __syncthreads();
+    if (!abort_smem) {
+      // block reduction over the pixel lanes, then  (sum ga, rstd * (sum ga y - mean sum ga))  per channel
+      for (int t = tid; t < cv * 8; t += 256) {
+        const int vv = t % cv, j = t / cv;     // channel j of vector vv
+        float a_g = 0.f, a_gy = 0.f;
+        for (int l = 0; l < lanes; ++l) {
+          a_g += red[(j * 2) * 256 + l * cv + vv];
+          a_gy += red[(j * 2 + 1) * 256 + l * cv + vv];
+        }
+        const int ch = vv * 8 + j;
+        const float s1 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2];
+        const float s2 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2 + 1];
+        const float mean = s1 * p.inv_count;
+        const float rstd = rsqrtf(fmaxf(s2 * p.inv_count - mean * mean, 0.f) + p.eps);
+        atomicAdd(p.bstats + (static_cast<int64_t>(grp) * C + ch) * 2, a_g);
+        atomicAdd(p.bstats + (static_cast<int64_t>(grp) * C + ch) * 2 + 1, rstd * (a_gy - mean * a_g));
+      }
+    }
+  }
+  if (tid == 0 && abort_smem && abort_global) atomicExch(abort_global, 1);
+}
+
 static bool stream_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32, int dt) {
-  static const int mode = getenv("CDB_NORM_BWD_IMPL") ? atoi(getenv("CDB_NORM_BWD_IMPL")) : 1;   // 0: old kernels
-  if (mode == 0) return false;
+  if (getenv("CDB_NORM_BWD_IMPL") && atoi(getenv("CDB_NORM_BWD_IMPL")) == 0) return false;   // 0: old kernels
   return dt == CDB_BF16 && d->norm != CDB_NORM_NONE && !d->use_running && d->gamma == nullptr && d->beta == nullptr &&
          !accum_f32 && p.pre_act == CDB_ACT_NONE && p.has_dout &&
          (p.act == CDB_ACT_NONE || p.act == CDB_ACT_RELU || p.act == CDB_ACT_LEAKY) &&
@@ -1024,6 +1282,90 @@ static void launch_stream(const NormBwdParams& p, dim3 grid, cudaStream_t stream
     case CDB_ACT_LEAKY: launch_stream_act<kApply, CDB_ACT_LEAKY>(p, grid, stream); break;
     default: launch_stream_act<kApply, CDB_ACT_NONE>(p, grid, stream); break;
   }
+}
+
+static int norm_bwd_impl() {
+  static const int mode = getenv("CDB_NORM_BWD_IMPL") ? atoi(getenv("CDB_NORM_BWD_IMPL")) : 2;   // 2: TMA-staged
+  return mode;
+}
+// the TMA-staged kernels need whole pixels contiguous along a row in every operand they stage, the column images of
+// the reflect fold inside the first / last chunk of a row, and 16-byte aligned statistics rows
+static bool tma_eligible(const NormBwdParams& p) {
+  if (norm_bwd_impl() < 2) return false;
+  const int cv = p.C / 8;
+  if (!(p.C % 8 == 0 && p.C >= 64 && p.C <= 2048 && (cv & (cv - 1)) == 0)) return false;
+  const int px = 2 * (256 / cv);
+  return p.y.sw == p.C && p.dout.sw == p.C && (!p.has_dskip || p.dskip.sw == p.C) &&
+         p.W * p.C * 2 >= 4096 && (p.pad == 0 || (px > p.pad && p.H > 2 * p.pad + 1 && p.W > 2 * p.pad + 1)) &&
+         (reinterpret_cast<uintptr_t>(p.stats) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.bstats) & 15) == 0;
+}
+
+template <bool kApply, int ACT, bool HAS_SKIP, bool WRITE_GSUM, int V>
+static void launch_tma_one(const NormBwdParams& p, dim3 grid, TmaGeom tg, cudaStream_t stream) {
+  const size_t smem = (size_t)tg.stages * tg.stage_bytes + (kApply ? 0 : 16384);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V>,
+                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_smem = smem;
+  }
+  norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V><<<grid, 256, smem, stream>>>(p, tg, device_abort_flag_ptr());
+}
+template <bool kApply, int ACT, int V>
+static void launch_tma_act(const NormBwdParams& p, dim3 grid, const TmaGeom& tg, cudaStream_t stream) {
+  if (p.has_dskip) {
+    if (kApply && p.write_gsum) launch_tma_one<kApply, ACT, true, kApply, V>(p, grid, tg, stream);
+    else launch_tma_one<kApply, ACT, true, false, V>(p, grid, tg, stream);
+  } else {
+    if (kApply && p.write_gsum) launch_tma_one<kApply, ACT, false, kApply, V>(p, grid, tg, stream);
+    else launch_tma_one<kApply, ACT, false, false, V>(p, grid, tg, stream);
+  }
+}
+template <bool kApply, int V>
+static void launch_tma_v(const NormBwdParams& p, dim3 grid, const TmaGeom& tg, cudaStream_t stream) {
+  switch (p.act) {
+    case CDB_ACT_RELU: launch_tma_act<kApply, CDB_ACT_RELU, V>(p, grid, tg, stream); break;
+    case CDB_ACT_LEAKY: launch_tma_act<kApply, CDB_ACT_LEAKY, V>(p, grid, tg, stream); break;
+    default: launch_tma_act<kApply, CDB_ACT_NONE, V>(p, grid, tg, stream); break;
+  }
+}
+static void tma_geom(const NormBwdParams& p, int V, int stages_want, int budget, TmaGeom* tg) {
+  const int cb = V * 4096;
+  tg->cpr = ceil_div(p.W, V * (256 / (p.C / 8)));
+  tg->off_d = cb;
+  tg->off_s = tg->off_d + round_up(cb + 3 * p.pad * p.C * 2, 128);
+  tg->stage_bytes = tg->off_s + (p.has_dskip ? cb : 0);
+  int stages = stages_want < 2 ? 2 : (stages_want > kTmaMaxStages ? kTmaMaxStages : stages_want);
+  if (stages > budget / tg->stage_bytes) stages = budget / tg->stage_bytes;
+  tg->stages = stages;
+}
+template <bool kApply>
+static void launch_tma(NormBwdParams p, int n, cudaStream_t stream) {
+  static const int stages_env = getenv("CDB_NORM_TMA_STAGES") ? atoi(getenv("CDB_NORM_TMA_STAGES")) : 4;
+  static const int per_sm = getenv("CDB_NORM_TMA_BLOCKS_PER_SM") ? atoi(getenv("CDB_NORM_TMA_BLOCKS_PER_SM")) : 2;
+  static const int hint = getenv("CDB_NORM_TMA_HINT") ? atoi(getenv("CDB_NORM_TMA_HINT")) : 0;
+  static const int v_env = getenv("CDB_NORM_TMA_V") ? atoi(getenv("CDB_NORM_TMA_V")) : 4;
+  p.vt = p.C / 8;
+  // two resident blocks per SM: 227 KB less 1 KB per block of system use, the reduction scratch and the static part
+  const int budget = (per_sm >= 2 ? 110 : 220) * 1024 - (kApply ? 0 : 16384);
+  TmaGeom tg;
+  int V = v_env == 4 ? 4 : 2;
+  tma_geom(p, V, stages_env, budget, &tg);
+  if (V == 4 && (tg.stages < 2 || p.W * p.C * 2 < 16384)) {   // 16 KB chunks do not fit twice (or rows are shorter)
+    V = 2;
+    tma_geom(p, V, stages_env, budget, &tg);
+  }
+  if (tg.stages < 2) tg.stages = 2;
+  tg.hint = hint;
+  const int cpi = p.H * tg.cpr;
+  int bpi = (per_sm * sm_count()) / (n > 0 ? n : 1);
+  if (bpi > cpi / 4) bpi = cpi / 4;
+  if (bpi < 1) bpi = 1;
+  dim3 grid(bpi, n, 1);
+  if (V == 4) launch_tma_v<kApply, 4>(p, grid, tg, stream);
+  else launch_tma_v<kApply, 2>(p, grid, tg, stream);
 }
 
 static bool fused_in_eligible(const CdbNormDesc* d, const NormBwdParams& p, bool accum_f32) {
@@ -1297,6 +1639,13 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
       if (dt == CDB_F32) launch_norm_bwd<float, true>(p, grid, stream);
       else launch_norm_bwd<__nv_bfloat16, true>(p, grid, stream);
     }
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
+  if (stream_eligible(d, p, accum_f32, dt) && tma_eligible(p)) {
+    launch_tma<false>(p, y->n, stream);
+    CDB_LAUNCH_OK();
+    launch_tma<true>(p, y->n, stream);
     CDB_LAUNCH_OK();
     return CDB_OK;
   }

@@ -108,6 +108,54 @@ def test_norm_act_forward_backward(norm, act, pad, use_res, c, h, w):
         assert rel_l2(bstats[0, :, 0], yr.grad.sum((0, 2, 3))) <= 1e-3
 
 
+@pytest.mark.parametrize("act,pad,use_res,use_skip,c,h,w,n,ypad_w", [
+    ('relu', 1, False, False, 256, 20, 40, 3, 2),     # 16-pixel chunks, 8-pixel tail, y in a wider (flat-conv) frame
+    ('none', 1, True, False, 256, 64, 64, 2, 2),      # the residual-block shape (gsum written)
+    ('leaky', 0, False, False, 512, 31, 31, 2, 0),    # PatchGAN: 8-pixel chunks, 7-pixel tail
+    ('relu', 3, False, True, 64, 37, 200, 2, 0),      # 64-pixel chunks, pad 3 fold, skip gradient added
+    ('none', 0, True, True, 128, 24, 72, 5, 0),       # skip + gsum, 32-pixel chunks with an 8-pixel tail
+    ('relu', 0, False, False, 2048, 6, 9, 2, 0),      # one pixel per thread group
+])
+def test_norm_bwd_staged_rows(act, pad, use_res, use_skip, c, h, w, n, ypad_w):
+    """The TMA-staged backward (norm_bwd_tma_kernel: InstanceNorm, bf16, contiguous pixel rows): chunk tails, the
+    reflect fold at every border, the skip gradient and gsum, against torch fp32 autograd on identical bf16 inputs."""
+    from cycle_depth_estimation_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(c + h + w)
+    y = (torch.randn((n, c, h, w), generator=g, device='cuda') * 1.3 - 0.2).to(torch.bfloat16).float()
+    res = torch.randn((n, c, h, w), generator=g, device='cuda').to(torch.bfloat16).float() if use_res else None
+    skip = torch.randn((n, c, h, w), generator=g, device='cuda').to(torch.bfloat16).float() if use_skip else None
+    yr = y.clone().requires_grad_(True)
+    rr = res.clone().requires_grad_(True) if use_res else None
+    z = _ref_forward(yr, 'instance', act, 0.2, rr, 0)
+    zp = F.pad(z, (pad, pad, pad, pad), mode='reflect') if pad else z
+    dout = torch.randn(zp.shape, generator=g, device='cuda').to(torch.bfloat16).float()
+    loss = (zp * dout).sum()
+    if use_skip:
+        loss = loss + (z * skip).sum()
+    loss.backward()
+
+    ak = {'relu': ops.ACT_RELU, 'leaky': ops.ACT_LEAKY, 'none': ops.ACT_NONE}[act]
+    yframe = torch.full((n, h, w + ypad_w, c), 3.0, dtype=torch.bfloat16, device='cuda')
+    ys = yframe[:, :, :w, :]
+    ys.copy_(_nhwc(y))
+    stats = torch.zeros((n, c, 2), dtype=torch.float32, device='cuda')
+    ops.channel_stats(ys, c, True, stats)
+    desc = ops.norm_desc(ops.NORM_INSTANCE, ak, 0.2, 1e-5, c, pad, stats, None, None)
+    dfull = _nhwc(dout)
+    dinner = dfull[:, pad:pad + h, pad:pad + w, :]
+    dyf = torch.full((n, h + 2, w + 2, c), float('nan'), dtype=torch.bfloat16, device='cuda')
+    dy = dyf[:, 1:1 + h, 1:1 + w, :]
+    gsum = torch.empty((n, h, w, c), dtype=torch.bfloat16, device='cuda') if use_res else None
+    bstats = torch.zeros((n, c, 2), dtype=torch.float32, device='cuda')
+    ops.norm_act_bwd(desc, ys, dy, dinner, _nhwc(skip) if use_skip else None, bstats, gsum)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dy.float()).all()
+    assert rel_l2(_nchw(dy), yr.grad) <= TOL, rel_l2(_nchw(dy), yr.grad)
+    if use_res:
+        assert rel_l2(_nchw(gsum), rr.grad) <= TOL
+    assert ops._lib.lib().cdb_device_abort_flag() == 0
+
+
 def test_nchw_to_nhwc_reflect_and_fold_roundtrip():
     from cycle_depth_estimation_b200 import ops
     g = torch.Generator(device='cuda').manual_seed(0)

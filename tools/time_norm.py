@@ -33,5 +33,6 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 print("batch", B, {k: v for k, v in os.environ.items() if k.startswith("CDB_")}, flush=True)
 run(B, 64, 64, 256, 1, False)
 run(B, 64, 64, 256, 1, True)
+run(B, 64, 64, 256, 0, False)
 run(B, 256, 256, 64, 3, False, iters=10)
 run(B, 128, 128, 128, 0, False, iters=10)
