@@ -812,10 +812,31 @@ norm_bwd_fused_in_kernel(NormBwdParams p, int ppc) {
 // kernels (and the cluster-fused one) are bound by instruction latency at 16 warps per SM
 // (profiles/r01_norm_bwd_experiments.txt).
 // ------------------------------------------------------------------------------------------------
+// bf16 pair -> fp32 pair in two integer instructions (shift, mask): the fp32 bits of a bf16 are its 16 bits followed by
+// zeros
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t x) {
+  return make_float2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u));
+}
 __device__ __forceinline__ void unpack8_pairs(const uint4& r, float2* f) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) f[i] = __bfloat1622float2(p[i]);
+  f[0] = bf16x2_to_float2(r.x);
+  f[1] = bf16x2_to_float2(r.y);
+  f[2] = bf16x2_to_float2(r.z);
+  f[3] = bf16x2_to_float2(r.w);
+}
+// Bits of the smallest bf16 strictly greater than m: for a bf16 value y,  y > m  <=>  y >= bf16_above(m)  exactly, so
+// the ReLU mask of four channel pairs is four packed bf16 comparisons instead of eight fp32 compare + select pairs.
+__device__ __forceinline__ uint32_t bf16_above(float m) {
+  const __nv_bfloat16 c = __float2bfloat16_ru(m);   // smallest bf16 >= m
+  uint32_t b = __bfloat16_as_ushort(c);
+  if (__bfloat162float(c) == m) {                   // m is a bf16 value itself: the next one up
+    if (m == 0.f) b = 0x0001u;
+    else if (m > 0.f) b += 1u;
+    else b -= 1u;
+  }
+  return b;
+}
+__device__ __forceinline__ uint32_t bf16x2_ge_mask(uint32_t y, uint32_t thr) {
+  return __hge2_mask(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&thr));
 }
 __device__ __forceinline__ uint4 pack8_pairs(const float2* f) {
   uint4 r;
@@ -1008,7 +1029,7 @@ constexpr int kTmaMaxStages = 8;
 struct TmaGeom {
   int cpr;           // chunks per image row
   int stages;
-  int off_d, off_s;  // byte offsets of the dout / dskip slots inside a stage (y at 0)
+  int off_d, off_m, off_s;  // byte offsets of the dout / mirror-row / dskip slots inside a stage (y at 0)
   int stage_bytes;
   int hint;
 };
@@ -1033,7 +1054,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
   __shared__ uint64_t bars[2 * kTmaMaxStages];   // full[s] = bars[s], empty[s] = bars[kTmaMaxStages + s]
   __shared__ int abort_smem;
   const int stages = tg.stages, cpr = tg.cpr;
-  float* red = reinterpret_cast<float*>(tma_smem + stages * tg.stage_bytes);   // reduce pass only (16 KB)
+  float* red = reinterpret_cast<float*>(tma_smem);   // reduce pass: 16 KB over the ring once every chunk is consumed
   const int tid = threadIdx.x;
   const int cv = p.vt;                             // channel vectors per pixel (C / 8, a power of two <= 256)
   const int lanes = 256 / cv, PX = V * lanes;      // pixels per chunk
@@ -1064,14 +1085,18 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
     const uint32_t dbytes = static_cast<uint32_t>((npx + pad + right) * C * 2);
     const uint32_t full = bar_base + stage * 8;
     const uint32_t dst = stage_base + stage * tg.stage_bytes;
-    mbar_arrive_expect_tx(full, bytes * (HAS_SKIP ? 2 : 1) + dbytes);
+    // the one row whose reflect image row ih is (rows 1..pad and H-1-pad..H-2 have one; H > 2 pad + 1)
+    const int mh = pad == 0 ? 0 : ((ih >= 1 && ih <= pad) ? -ih : ((ih <= H - 2 && ih >= H - 1 - pad) ? 2 * (H - 1) - ih : 0));
+    mbar_arrive_expect_tx(full, bytes * (HAS_SKIP ? 2 : 1) + dbytes * (mh != 0 ? 2 : 1));
     if (tg.hint) {
       bulk_load_1d_hint(dst, yimg + ih * ysh + w0 * C, bytes, full, pol);
       bulk_load_1d_hint(dst + tg.off_d, dimg + ih * dsh + (w0 - pad) * C, dbytes, full, pol);
+      if (mh != 0) bulk_load_1d_hint(dst + tg.off_m, dimg + mh * dsh + (w0 - pad) * C, dbytes, full, pol);
       if (HAS_SKIP) bulk_load_1d_hint(dst + tg.off_s, simg + ih * ssh + w0 * C, bytes, full, pol);
     } else {
       bulk_load_1d(dst, yimg + ih * ysh + w0 * C, bytes, full);
       bulk_load_1d(dst + tg.off_d, dimg + ih * dsh + (w0 - pad) * C, dbytes, full);
+      if (mh != 0) bulk_load_1d(dst + tg.off_m, dimg + mh * dsh + (w0 - pad) * C, dbytes, full);
       if (HAS_SKIP) bulk_load_1d(dst + tg.off_s, simg + ih * ssh + w0 * C, bytes, full);
     }
     if (kApply) {
@@ -1099,6 +1124,9 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
   const int grp = p.per_image ? n : 0;
   float2 mean2[4], A2[kApply ? 4 : 1], B2[kApply ? 4 : 1], D2[kApply ? 4 : 1];
   float2 sg[kApply ? 1 : 4], sgy[kApply ? 1 : 4];
+  // ReLU of a gradient that is still the stored bf16 value (no skip term, interior pixel): packed bf16 mask
+  constexpr bool kFastMask = ACT == CDB_ACT_RELU && !HAS_SKIP;
+  uint32_t thr[kFastMask ? 4 : 1];
   if (!kApply) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) sg[kApply ? 0 : i] = sgy[kApply ? 0 : i] = make_float2(0.f, 0.f);
@@ -1124,6 +1152,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
         dd[e] = rstd * rstd * m2 * mean[e] - rstd * m1;
       }
       mean2[i] = make_float2(mean[0], mean[1]);
+      if (kFastMask) thr[kFastMask ? i : 0] = bf16_above(mean[0]) | (bf16_above(mean[1]) << 16);
       if (kApply) {
         A2[kApply ? i : 0] = make_float2(a[0], a[1]);
         B2[kApply ? i : 0] = make_float2(b[0], b[1]);
@@ -1131,7 +1160,6 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
       }
     }
   }
-  const __nv_bfloat16* db = dimg + v * 8;   // mirror rows of the reflect fold (global memory, 2 * pad rows per image)
   __nv_bfloat16* ob = kApply ? static_cast<__nv_bfloat16*>(p.dy.ptr) + n * p.dy.sn + v * 8 : nullptr;
   __nv_bfloat16* gb = (kApply && WRITE_GSUM) ? static_cast<__nv_bfloat16*>(p.gsum.ptr) + n * p.gsum.sn + v * 8 : nullptr;
   const int gsh = static_cast<int>(p.gsum.sh), gsw = static_cast<int>(p.gsum.sw);
@@ -1153,54 +1181,60 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
     if (!mbar_wait(bar_base + s * 8, ph, abort_flag)) break;
     const uint32_t sbase = stage_base + s * tg.stage_bytes;
     const uint32_t src = sbase + tid * 16;
-    const bool hborder = pad > 0 && (h <= pad || h >= H - 1 - pad);
+    const bool hmirror = pad > 0 && ((h >= 1 && h <= pad) || (h <= H - 2 && h >= H - 1 - pad));
 #pragma unroll
     for (int u = 0; u < V; ++u) {
       const int px = lane + u * lanes;
       if (px >= npx) break;
       const int w = w0 + px;
-      float2 y2[4], g2[4];
-      unpack8_pairs(ld_shared_v4(src + u * 4096), y2);
-      unpack8_pairs(ld_shared_v4(src + tg.off_d + pad_bytes + u * 4096), g2);
-      if (HAS_SKIP) add_vec_pairs(src + tg.off_s + u * 4096, g2);
-      if (pad > 0 && (hborder || w <= pad || w >= W - 1 - pad)) {
-        constexpr int kNone = -(1 << 30);
-        const int w1 = (w >= 1 && w <= pad) ? -w : kNone;
-        const int w2 = (w <= W - 2 && w >= W - 1 - pad) ? 2 * (W - 1) - w : kNone;
-        // column images: inside the staged segment (position of pixel ww: ww - (w0 - pad))
-        const uint32_t dslot = sbase + tg.off_d + v * 16;
-        if (w1 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w1 - w0 + pad) * C * 2), g2);
-        if (w2 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w2 - w0 + pad) * C * 2), g2);
-        if (hborder) {
-          const int h1 = (h >= 1 && h <= pad) ? -h : kNone;
-          const int h2 = (h <= H - 2 && h >= H - 1 - pad) ? 2 * (H - 1) - h : kNone;
-          if (h1 != kNone) {
-            add_vec_pairs(db + h1 * dsh + w * C, g2);
-            if (w1 != kNone) add_vec_pairs(db + h1 * dsh + w1 * C, g2);
-            if (w2 != kNone) add_vec_pairs(db + h1 * dsh + w2 * C, g2);
-          }
-          if (h2 != kNone) {
-            add_vec_pairs(db + h2 * dsh + w * C, g2);
-            if (w1 != kNone) add_vec_pairs(db + h2 * dsh + w1 * C, g2);
-            if (w2 != kNone) add_vec_pairs(db + h2 * dsh + w2 * C, g2);
+      const uint4 yv = ld_shared_v4(src + u * 4096);
+      const uint4 dv = ld_shared_v4(src + tg.off_d + pad_bytes + u * 4096);
+      const bool border = pad > 0 && (hmirror || w <= pad || w >= W - 1 - pad);
+      float2 y2[4], ga2[4];
+      uint4 gv = dv;                       // the summed gradient, bf16 (gsum)
+      unpack8_pairs(yv, y2);
+      if (kFastMask && !border) {
+        uint4 m;
+        m.x = dv.x & bf16x2_ge_mask(yv.x, thr[0]);
+        m.y = dv.y & bf16x2_ge_mask(yv.y, thr[kFastMask ? 1 : 0]);
+        m.z = dv.z & bf16x2_ge_mask(yv.z, thr[kFastMask ? 2 : 0]);
+        m.w = dv.w & bf16x2_ge_mask(yv.w, thr[kFastMask ? 3 : 0]);
+        unpack8_pairs(m, ga2);
+      } else {
+        float2 g2[4];
+        unpack8_pairs(dv, g2);
+        if (HAS_SKIP) add_vec_pairs(src + tg.off_s + u * 4096, g2);
+        if (border) {
+          constexpr int kNone = -(1 << 30);
+          const int w1 = (w >= 1 && w <= pad) ? -w : kNone;
+          const int w2 = (w <= W - 2 && w >= W - 1 - pad) ? 2 * (W - 1) - w : kNone;
+          // column images: inside the staged segment (position of pixel ww: ww - (w0 - pad))
+          const uint32_t dslot = sbase + tg.off_d + v * 16;
+          if (w1 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w1 - w0 + pad) * C * 2), g2);
+          if (w2 != kNone) add_vec_pairs(dslot + static_cast<uint32_t>((w2 - w0 + pad) * C * 2), g2);
+          if (hmirror) {   // the mirror row, staged with the same extents
+            const uint32_t mslot = sbase + tg.off_m + v * 16;
+            add_vec_pairs(mslot + static_cast<uint32_t>((w - w0 + pad) * C * 2), g2);
+            if (w1 != kNone) add_vec_pairs(mslot + static_cast<uint32_t>((w1 - w0 + pad) * C * 2), g2);
+            if (w2 != kNone) add_vec_pairs(mslot + static_cast<uint32_t>((w2 - w0 + pad) * C * 2), g2);
           }
         }
+        if (kApply && WRITE_GSUM && (HAS_SKIP || border)) gv = pack8_pairs(g2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ga2[q] = mask_pair<ACT>(g2[q], y2[q], mean2[q], slope);
       }
       if (kApply) {
-        if (WRITE_GSUM) st16(gb + h * gsh + w * gsw, pack8_pairs(g2));
+        if (WRITE_GSUM) st16(gb + h * gsh + w * gsw, gv);
         float2 o2[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 ga = mask_pair<ACT>(g2[q], y2[q], mean2[q], slope);
-          o2[q] = __ffma2_rn(ga, A2[kApply ? q : 0], __ffma2_rn(y2[q], B2[kApply ? q : 0], D2[kApply ? q : 0]));
-        }
+        for (int q = 0; q < 4; ++q)
+          o2[q] = __ffma2_rn(ga2[q], A2[kApply ? q : 0], __ffma2_rn(y2[q], B2[kApply ? q : 0], D2[kApply ? q : 0]));
         st16(ob + h * osh + w * osw, pack8_pairs(o2));
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 ga = mask_pair<ACT>(g2[q], y2[q], mean2[q], slope);
-          sg[kApply ? 0 : q] = __fadd2_rn(sg[kApply ? 0 : q], ga);
-          sgy[kApply ? 0 : q] = __ffma2_rn(ga, y2[q], sgy[kApply ? 0 : q]);
+          sg[kApply ? 0 : q] = __fadd2_rn(sg[kApply ? 0 : q], ga2[q]);
+          sgy[kApply ? 0 : q] = __ffma2_rn(ga2[q], y2[q], sgy[kApply ? 0 : q]);
         }
       }
     }
@@ -1216,6 +1250,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
     }
   }
   if (!kApply) {
+    __syncthreads();   // every staged chunk has been consumed: the ring is free for the block reduction
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       red[((2 * q) * 2) * 256 + tid] = sg[kApply ? 0 : q].x;
@@ -1302,7 +1337,8 @@ static bool tma_eligible(const NormBwdParams& p) {
 
 template <bool kApply, int ACT, bool HAS_SKIP, bool WRITE_GSUM, int V>
 static void launch_tma_one(const NormBwdParams& p, dim3 grid, TmaGeom tg, cudaStream_t stream) {
-  const size_t smem = (size_t)tg.stages * tg.stage_bytes + (kApply ? 0 : 16384);
+  size_t smem = (size_t)tg.stages * tg.stage_bytes;
+  if (!kApply && smem < 16384) smem = 16384;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V>,
@@ -1334,8 +1370,10 @@ static void launch_tma_v(const NormBwdParams& p, dim3 grid, const TmaGeom& tg, c
 static void tma_geom(const NormBwdParams& p, int V, int stages_want, int budget, TmaGeom* tg) {
   const int cb = V * 4096;
   tg->cpr = ceil_div(p.W, V * (256 / (p.C / 8)));
+  const int dslot = round_up(cb + 3 * p.pad * p.C * 2, 128);
   tg->off_d = cb;
-  tg->off_s = tg->off_d + round_up(cb + 3 * p.pad * p.C * 2, 128);
+  tg->off_m = tg->off_d + dslot;
+  tg->off_s = tg->off_m + (p.pad > 0 ? dslot : 0);
   tg->stage_bytes = tg->off_s + (p.has_dskip ? cb : 0);
   int stages = stages_want < 2 ? 2 : (stages_want > kTmaMaxStages ? kTmaMaxStages : stages_want);
   if (stages > budget / tg->stage_bytes) stages = budget / tg->stage_bytes;
@@ -1348,8 +1386,8 @@ static void launch_tma(NormBwdParams p, int n, cudaStream_t stream) {
   static const int hint = getenv("CDB_NORM_TMA_HINT") ? atoi(getenv("CDB_NORM_TMA_HINT")) : 0;
   static const int v_env = getenv("CDB_NORM_TMA_V") ? atoi(getenv("CDB_NORM_TMA_V")) : 4;
   p.vt = p.C / 8;
-  // two resident blocks per SM: 227 KB less 1 KB per block of system use, the reduction scratch and the static part
-  const int budget = (per_sm >= 2 ? 110 : 220) * 1024 - (kApply ? 0 : 16384);
+  // two resident blocks per SM: 227 KB less 1 KB per block of system use and the static part
+  const int budget = (per_sm >= 2 ? 110 : 220) * 1024;
   TmaGeom tg;
   int V = v_env == 4 ? 4 : 2;
   tma_geom(p, V, stages_env, budget, &tg);
