@@ -141,6 +141,16 @@ def test_norm_bwd_staged_rows(act, pad, use_res, use_skip, c, h, w, n, ypad_w):
     stats = torch.zeros((n, c, 2), dtype=torch.float32, device='cuda')
     ops.channel_stats(ys, c, True, stats)
     desc = ops.norm_desc(ops.NORM_INSTANCE, ak, 0.2, 1e-5, c, pad, stats, None, None)
+    # forward through the TMA-staged kernel: output + reflect halo, residual read from a wider frame
+    full = torch.full((n, h + 2 * pad, w + 2 * pad, c), float('nan'), dtype=torch.bfloat16, device='cuda')
+    rs = None
+    if use_res:
+        rframe = torch.zeros((n, h + 2, w + 4, c), dtype=torch.bfloat16, device='cuda')
+        rs = rframe[:, 1:1 + h, 2:2 + w, :]
+        rs.copy_(_nhwc(res))
+    ops.norm_act_fwd(desc, ys, full[:, pad:pad + h, pad:pad + w, :], rs)
+    assert torch.isfinite(full.float()).all()
+    assert rel_l2(_nchw(full), zp) <= TOL, rel_l2(_nchw(full), zp)
     dfull = _nhwc(dout)
     dinner = dfull[:, pad:pad + h, pad:pad + w, :]
     dyf = torch.full((n, h + 2, w + 2, c), float('nan'), dtype=torch.bfloat16, device='cuda')
