@@ -668,7 +668,9 @@ def backward(plan, run, gout, need_input_grad, needs_param_grad):
                     ops.channel_stats(dy, co, False, bs)
                     grads[conv.bias] = bs[0, :, 0].contiguous()
                 else:
-                    grads[conv.bias] = torch.zeros_like(conv.bias)
+                    # exactly zero (a bias in front of a statistics-normalised layer): a slice of the zero arena, no
+                    # fill kernel of its own (autograd takes the fresh view over as .grad without a copy)
+                    grads[conv.bias] = arena.take(tuple(conv.bias.shape))
             if affine:
                 if needs_param_grad.get(st.norm.weight, False):
                     grads[st.norm.weight] = bstats[0, :, 1].contiguous()
