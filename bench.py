@@ -231,6 +231,58 @@ def time_tf32_kernel(iters=20):
             "frac_of_nominal_tf32_peak": tf / 1100.0, "peak_source": "nominal dense TF32 1.1 PFLOP/s (fallback)"}
 
 
+def time_norm_backward(peaks, n=16, hw=64, c=256, pad=1, sets=3, rounds=4):
+    """The second HBM-bound kernel family of the step: the InstanceNorm + ReLU backward of a residual-block layer
+    (norm_bwd_tma_kernel reduce + apply, reflect fold of the padded gradient) at the batch the step runs it on (16).
+    `sets` buffer sets (> 126 MB L2 together) are walked in turn inside one CUDA graph, so every launch streams from
+    HBM and the Python launch rate is out of the measurement.  Algorithmic bytes: 2 reads + 1 write of the tensor."""
+    from cycle_depth_estimation_b200 import ops
+    bufs = []
+    for _ in range(sets):
+        y = ops.alloc_flat_output(n, hw, hw, hw + 2, c, "cuda")
+        y.normal_()
+        stats = torch.zeros((n, c, 2), device="cuda")
+        ops.channel_stats(y, c, True, stats)
+        dfull = torch.randn((n, hw + 2 * pad, hw + 2 * pad, c), device="cuda").to(torch.bfloat16)
+        dyp = torch.zeros((n, hw + 4, hw + 4, c), dtype=torch.bfloat16, device="cuda")
+        bst = torch.zeros((n, c, 2), device="cuda")
+        desc = ops.norm_desc(ops.NORM_INSTANCE, ops.ACT_RELU, 0.0, 1e-5, c, pad, stats)
+        bufs.append((desc, y, dyp[:, 2:2 + hw, 2:2 + hw, :], dfull[:, pad:pad + hw, pad:pad + hw, :], bst, stats))
+
+    def once():
+        for desc, y, dy, dinner, bst, _ in bufs:
+            ops.norm_act_bwd(desc, y, dy, dinner, None, bst, None)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        once()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(rounds):
+            once()
+    graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * rounds * sets)
+    t_bytes = n * hw * hw * c * 2
+    return {"kernel": "norm_bwd_tma_kernel reduce + apply", "shape": "InstanceNorm + ReLU backward, %dx%dx%d, pad %d, batch %d"
+            % (hw, hw, c, pad, n), "us_per_call": us, "algorithmic_bytes": 3 * t_bytes, "bytes_moved": 5 * t_bytes,
+            "algorithmic_gbs": 3 * t_bytes / us * 1e-3, "moved_gbs": 5 * t_bytes / us * 1e-3,
+            "frac_of_hbm_peak_algorithmic": 3 * t_bytes / us * 1e-3 / peaks["hbm"],
+            "frac_of_hbm_peak_moved": 5 * t_bytes / us * 1e-3 / peaks["hbm"], "hbm_peak_gbs": peaks["hbm"],
+            "peak_source": peaks["source"], "launches_per_call": 2,
+            "how": "%d buffer sets of %.0f MB walked in turn inside one CUDA graph (no L2 reuse between calls)"
+            % (sets, 3 * t_bytes / 1e6)}
+
+
 def cudnn_same_box(batch, size, steps=3, warmup=2):
     """The bar SURVEY 2.3 / BASELINE.md 3 name: the SAME training step through stock PyTorch on this GPU — the
     oracle restatement of models/cycle_gan_model.py:80-160 around torch.nn.functional, i.e. cuDNN convolutions and
@@ -480,6 +532,7 @@ def b200_arm(args):
     g1, g8 = time_g_inference(1), time_g_inference(8)
     roof = time_dominant_kernel(peaks)
     tf32 = time_tf32_kernel()
+    norm_bwd = time_norm_backward(peaks)
     step_tflops = TFLOP_PER_SAMPLE * batch / (ms_step * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -507,6 +560,7 @@ def b200_arm(args):
             "g_forward_img_per_s_batch8": 8e3 / g8["graph"],
             "g_forward_tflops_batch8": 8 * G_FWD_GFLOP / g8["graph"],
             "tf32_variant_r256_conv": tf32,
+            "norm_backward_r256": norm_bwd,
             "device_abort_flag": abort,
         },
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

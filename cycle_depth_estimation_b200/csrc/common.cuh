@@ -8,6 +8,9 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/cdb200.h"
 
@@ -54,6 +57,38 @@ int make_tmap_swz(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base
 
 int sm_count();
 void note_launch();
+
+// CDB_PDL=1 switches programmatic dependent launches on (off by default: see api.cu).
+bool pdl_enabled();
+
+// Launch with optional thread-block cluster (x dimension) and programmatic stream serialization (see ptx.cuh pdl_*).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             int cluster_x, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -132,6 +132,8 @@ igemm_flat_kernel(const __grid_constant__ FlatMaps maps, const __grid_constant__
   __syncthreads();
   if (kPair) cluster_sync_all();  // the peer's barriers exist before any TMA / commit / arrive reaches them
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();   // everything above overlapped the tail of the previous kernel in the stream
   const uint32_t tmem_base = tmem_base_smem;
   volatile int* abort_flag = &abort_smem;
   const int n_taps = p.R * p.S;
@@ -773,23 +775,11 @@ int launch_flat_conv(const CdbConvGeom* g, const CdbAct* x, const void* wpacked,
   }
   if (pair) {
     const int clusters = total < sm_count() / 2 ? total : sm_count() / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters, 1, 1);
-    cfg.blockDim = dim3(384, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CDB_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_flat_kernel<true>, maps, prm));
+    CDB_CUDA_OK(launch_ex(igemm_flat_kernel<true>, dim3(2 * clusters, 1, 1), dim3(384, 1, 1), smem, stream, 2, true, maps,
+                          prm));
   } else {
     const int grid = total < sm_count() ? total : sm_count();
-    igemm_flat_kernel<false><<<grid, 384, smem, stream>>>(maps, prm);
+    CDB_CUDA_OK(launch_ex(igemm_flat_kernel<false>, dim3(grid, 1, 1), dim3(384, 1, 1), smem, stream, 1, true, maps, prm));
   }
   CDB_LAUNCH_OK();
   if (prm.dbg) {

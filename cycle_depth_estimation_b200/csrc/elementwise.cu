@@ -271,7 +271,16 @@ struct AdamMultiParams {
   int32_t cum[kAdamMaxEntries + 1];
 };
 
+// Filters that emit packed operands (no rowpack, R * S <= kAdamTileRS) are walked in tiles of 32 d0 x 32 d1 filters
+// with all their taps: the fp32 state is read / written in runs of 32 * R * S contiguous floats, the updated values
+// go through shared memory as bf16 and each packed operand is written in runs of 32 consecutive k (64 bytes).  The
+// element-order walk below stores every packed value as a lone 2-byte write at a stride of kpad (one 32-byte sector
+// each, twice per parameter): 132 us per 11.4 M-parameter generator = 1.7 TB/s of algorithmic traffic.
+constexpr int kAdamTile = 32;
+constexpr int kAdamTileRS = 16;
+
 __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__ AdamMultiParams q) {
+  __shared__ __nv_bfloat16 tile_sb[kAdamTile * kAdamTileRS * (kAdamTile + 1)];
   int lo = 0, hi = q.n_entries;            // largest t with cum[t] <= blockIdx.x
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -296,6 +305,47 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const __grid_constant__
   const float* __restrict__ g = en.grad;
   float* __restrict__ m = en.exp_avg;
   float* __restrict__ v = en.exp_avg_sq;
+  if (en.pad_ != 0) {
+    // ---- tiled walk (en.pad_ = d0)
+    const int d0 = en.pad_, d1 = en.d1, RS = en.R * en.S;
+    const int tiles1 = (d1 + kAdamTile - 1) / kAdamTile;
+    const int t = static_cast<int>(blockIdx.x) - q.cum[lo];
+    const int i0_0 = (t / tiles1) * kAdamTile, i1_0 = (t % tiles1) * kAdamTile;
+    const int n0 = min(kAdamTile, d0 - i0_0), n1 = min(kAdamTile, d1 - i1_0);
+    const int run = n1 * RS;
+    const float b1 = q.b1, b2 = q.b2, eps = q.eps;
+    for (int e = threadIdx.x; e < n0 * run; e += 256) {
+      const int i0_l = e / run, rem = e - i0_l * run;
+      const int i1_l = rem / RS, tap = rem - i1_l * RS;
+      const int64_t j = (static_cast<int64_t>(i0_0 + i0_l) * d1 + i1_0) * RS + rem;
+      const float gi = g[j];
+      float mi = m[j], vi = v[j];
+      mi = mi + (1.f - b1) * (gi - mi);
+      vi = b2 * vi + (1.f - b2) * gi * gi;
+      const float pn = p[j] - step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+      m[j] = mi;
+      v[j] = vi;
+      p[j] = pn;
+      tile_sb[(i0_l * RS + tap) * (kAdamTile + 1) + i1_l] = __float2bfloat16(pn);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const AdamPackDev& pk = en.pack[w];
+      if (pk.out == nullptr) continue;
+      const int nrow = pk.rows_are_dim0 ? n0 : n1, nk = pk.rows_are_dim0 ? n1 : n0;
+      const int row0 = pk.rows_are_dim0 ? i0_0 : i1_0, k0 = pk.rows_are_dim0 ? i1_0 : i0_0;
+      for (int e = threadIdx.x; e < nrow * RS * kAdamTile; e += 256) {
+        const int k_l = e % kAdamTile, rt = e / kAdamTile;
+        const int tap = rt % RS, row_l = rt / RS;
+        if (k_l >= nk) continue;
+        const int i0_l = pk.rows_are_dim0 ? row_l : k_l, i1_l = pk.rows_are_dim0 ? k_l : row_l;
+        pk.out[(static_cast<int64_t>(row0 + row_l) * pk.n_taps + tap) * pk.kpad + k0 + k_l] =
+            tile_sb[(i0_l * RS + tap) * (kAdamTile + 1) + i1_l];
+      }
+    }
+    return;
+  }
   const bool packs = en.pack[0].out != nullptr || en.pack[1].out != nullptr;
   const int rs = en.R * en.S;
   const float b1 = q.b1, b2 = q.b2, eps = q.eps;
@@ -541,6 +591,14 @@ static int adam_multi_launch(const CdbAdamEntry* plain, const CdbAdamPackEntry* 
       CDB_REQUIRE(d.param && d.grad && d.exp_avg && d.exp_avg_sq && d.numel > 0, CDB_ERR_BAD_DESC,
                   "adam_multi: bad entry %d", base + i);
       q.cum[i] = blocks;
+      static const bool tiled_on = !(getenv("CDB_ADAM_TILED") && atoi(getenv("CDB_ADAM_TILED")) == 0);
+      const bool has_pack = d.pack[0].out != nullptr || d.pack[1].out != nullptr;
+      if (tiled_on && has_pack && d.pack[0].rowpack == 0 && d.pack[1].rowpack == 0 && d.R * d.S <= kAdamTileRS) {
+        const int d0 = (int)(d.numel / ((int64_t)d.d1 * d.R * d.S));
+        d.pad_ = d0;
+        blocks += ((d0 + kAdamTile - 1) / kAdamTile) * ((d.d1 + kAdamTile - 1) / kAdamTile);
+        continue;
+      }
       blocks += (int)((d.numel + kAdamChunk - 1) / kAdamChunk);
     }
     q.cum[n] = blocks;

@@ -1107,6 +1107,7 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
   };
 
   int issued = 0;
+  pdl_trigger();
   if (tid == 0) {
     abort_smem = 0;
     for (int s = 0; s < stages; ++s) {
@@ -1115,8 +1116,10 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
     }
     fence_mbar_init();
     fence_proxy_async_smem();
-    for (; issued < stages && issued < nk; ++issued) issue(issued);   // the ring is filled before the coefficients are read
   }
+  pdl_wait();   // the previous kernel of the stream has completed: its output may be read, ours written
+  if (tid == 0)
+    for (; issued < stages && issued < nk; ++issued) issue(issued);   // the ring is filled before the coefficients are read
   __syncthreads();
   volatile int* abort_flag = &abort_smem;
 
@@ -1347,7 +1350,8 @@ static void launch_tma_one(const NormBwdParams& p, dim3 grid, TmaGeom tg, cudaSt
                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_smem = smem;
   }
-  norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V><<<grid, 256, smem, stream>>>(p, tg, device_abort_flag_ptr());
+  launch_ex(norm_bwd_tma_kernel<kApply, ACT, HAS_SKIP, WRITE_GSUM, V>, grid, dim3(256, 1, 1), smem, stream, 1, true, p, tg,
+            device_abort_flag_ptr());
 }
 template <bool kApply, int ACT, int V>
 static void launch_tma_act(const NormBwdParams& p, dim3 grid, const TmaGeom& tg, cudaStream_t stream) {
@@ -1444,6 +1448,7 @@ __global__ void __launch_bounds__(256, 2) norm_fwd_tma_kernel(NormFwdParams p, T
     if (++ic == cpr) { ic = 0; ++ih; }
   };
   int issued = 0;
+  pdl_trigger();
   if (tid == 0) {
     abort_smem = 0;
     for (int s = 0; s < stages; ++s) {
@@ -1452,8 +1457,10 @@ __global__ void __launch_bounds__(256, 2) norm_fwd_tma_kernel(NormFwdParams p, T
     }
     fence_mbar_init();
     fence_proxy_async_smem();
-    for (; issued < stages && issued < nk; ++issued) issue(issued);
   }
+  pdl_wait();
+  if (tid == 0)
+    for (; issued < stages && issued < nk; ++issued) issue(issued);
   __syncthreads();
   volatile int* abort_flag = &abort_smem;
   const int v = tid % cv, lane = tid / cv;
@@ -1533,7 +1540,8 @@ static void launch_fwd_tma_one(const NormFwdParams& p, dim3 grid, const TmaGeom&
                          cudaSharedmemCarveoutMaxShared);
     attr_smem = smem;
   }
-  norm_fwd_tma_kernel<ACT, HAS_RES, V><<<grid, 256, smem, stream>>>(p, tg, device_abort_flag_ptr());
+  launch_ex(norm_fwd_tma_kernel<ACT, HAS_RES, V>, grid, dim3(256, 1, 1), smem, stream, 1, true, p, tg,
+            device_abort_flag_ptr());
 }
 template <bool HAS_RES, int V>
 static void launch_fwd_tma_v(const NormFwdParams& p, dim3 grid, const TmaGeom& tg, cudaStream_t stream) {

@@ -847,6 +847,8 @@ extern "C" int cdb_shift_add_nchw(const float* t, int32_t n, int32_t p, int32_t 
 namespace cdb {
 __global__ void __launch_bounds__(256)
 zero_frame_kernel(PView full, int top, int left, int ih, int iw, int64_t frame_px, int64_t total, int cvn) {
+  pdl_trigger();
+  pdl_wait();
   const int W = full.w, H = full.h;
   const int64_t top_band = (int64_t)top * W, mid_band = (int64_t)ih * (W - iw);
   const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -886,8 +888,8 @@ extern "C" int cdb_zero_frame(const CdbAct* full, int32_t top, int32_t left, int
   const int64_t frame_px = (int64_t)full->h * full->w - (int64_t)inner_h * inner_w;
   const int64_t total = frame_px * full->n * (full->c / 8);
   if (total == 0) return CDB_OK;
-  zero_frame_kernel<<<pw_grid(total), 256, 0, stream>>>(pview(full), top, left, inner_h, inner_w, frame_px, total,
-                                                        full->c / 8);
+  launch_ex(zero_frame_kernel, dim3(pw_grid(total), 1, 1), dim3(256, 1, 1), 0, stream, 1, true, pview(full), top, left,
+            inner_h, inner_w, frame_px, total, full->c / 8);
   CDB_LAUNCH_OK();
   return CDB_OK;
 }

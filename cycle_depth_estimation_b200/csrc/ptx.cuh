@@ -137,6 +137,16 @@ __device__ __forceinline__ void tma_load_5d(const void* tmap, uint32_t bar, uint
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident while its predecessor in the stream is still running (once every CTA of the predecessor has executed
+// pdl_trigger or exited); pdl_wait blocks until the predecessor has completed and its writes are visible.  Every global
+// read or write of such a kernel comes after pdl_wait; barrier / TMEM / descriptor set-up before it overlaps the
+// predecessor's tail.  Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // Bulk (non-tensor) asynchronous copies: a contiguous run of bytes global -> shared, completion counted on an
 // mbarrier.  Size and both addresses are multiples of 16 bytes.  The _hint form carries an L2 eviction policy
 // (createpolicy): evict_last for data a following kernel re-reads, evict_first for data that is dead after the read.
