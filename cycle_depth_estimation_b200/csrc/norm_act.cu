@@ -1862,6 +1862,9 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
     return CDB_OK;
   }
   if (stream_eligible(d, p, accum_f32, dt) && tma_eligible(p)) {
+    // (walking the batch in groups of images whose operands stay in L2 between the two passes was measured: 40 MB
+    // groups 30.2 -> 31.9 ms per step, 24 MB groups 34.9 ms — the ramp and tail of the extra launches cost more than the
+    // HBM reads they save)
     launch_tma<false>(p, y->n, stream);
     CDB_LAUNCH_OK();
     launch_tma<true>(p, y->n, stream);
