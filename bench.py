@@ -379,11 +379,11 @@ def run_secondary_lines(steps=5):
     """The other BASELINE configs as sub-runs of this bench (one process each, this GPU), so that their numbers are
     recorded with the headline line instead of being builder-only claims."""
     out = []
-    for wl in ("g_infer", "pix2pix", "model5", "metrics"):
+    for wl in ("g_infer", "pix2pix", "model5", "metrics", "segcycle"):
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--workload", wl, "--steps", str(steps), "--warmup", "3",
                "--no-cpu-baseline"]
         try:
-            proc = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            proc = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
             line = json.loads([l for l in proc.stdout.splitlines() if l.startswith("{")][-1])
             out.append({"workload": wl, "metric": line["metric"], "value": line["value"], "unit": line["unit"],
                         "ms_per_step": line["ms_per_step"], "e2e_value": line["e2e"]["value"],
@@ -575,7 +575,7 @@ def b200_arm(args):
         except Exception as exc:  # noqa: BLE001
             cd = {"error": "%s: %s" % (type(exc).__name__, exc)}
         line["config"]["cudnn_same_box"] = cd
-    if world == 1 and args.secondary:
+    if world == 1 and not args.no_secondary:
         torch.cuda.empty_cache()
         line["secondary"] = run_secondary_lines()
     print(json.dumps(line), flush=True)
@@ -961,7 +961,9 @@ def main():
     ap.add_argument("--no-cudnn-baseline", action="store_true",
                     help="skip config.cudnn_same_box (the stock-PyTorch / cuDNN step timed on this GPU)")
     ap.add_argument("--secondary", action="store_true",
-                    help="also run the other BASELINE configs as sub-runs and attach their lines as `secondary`")
+                    help="(default at --gpus 1) also run the other BASELINE configs as sub-runs and attach their lines as "
+                         "`secondary`: ~10 s each")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary sub-runs")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch per GPU (default); strong: --batch is the global batch, sharded over the ranks")
     ap.add_argument("--no-cuda-graph", action="store_true", help="eager launches instead of replaying the captured step")
