@@ -98,9 +98,11 @@ class ClockSampler:
 
 
 def synthetic_batch(batch, size, seed):
+    """size: side of a square image, or (height, width)."""
+    h, w = size if isinstance(size, tuple) else (size, size)
     g = torch.Generator().manual_seed(seed)
-    return (torch.rand((batch, 3, size, size), generator=g) * 2 - 1,
-            torch.rand((batch, 3, size, size), generator=g) * 2 - 1)
+    return (torch.rand((batch, 3, h, w), generator=g) * 2 - 1,
+            torch.rand((batch, 3, h, w), generator=g) * 2 - 1)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -413,6 +415,10 @@ def b200_arm(args):
     lib = _lib.lib()
     peaks = load_peaks()
     batch, size = args.batch, args.size
+    img_h, img_w = args.size, (args.width or args.size)      # --width: the fork's 192 x 640 training shape (config 2b)
+    if img_w != img_h:
+        size = (img_h, img_w)
+    px_scale = img_h * img_w / 65536.0                       # TFLOP_PER_SAMPLE is counted at 256 x 256
     if args.scaling == "strong":
         # north_star: "the batch sharded" — the GLOBAL batch stays at --batch, every rank takes batch / world samples
         if batch % world:
@@ -533,7 +539,7 @@ def b200_arm(args):
     roof = time_dominant_kernel(peaks)
     tf32 = time_tf32_kernel()
     norm_bwd = time_norm_backward(peaks)
-    step_tflops = TFLOP_PER_SAMPLE * batch / (ms_step * 1e-3)
+    step_tflops = TFLOP_PER_SAMPLE * px_scale * batch / (ms_step * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         v, sample, _ = run_cpu_sample(steps=2, warmup=1, budget_s=40.0)
@@ -545,12 +551,14 @@ def b200_arm(args):
         "config": {
             "workload": "CycleGAN training step: G_A/G_B resnet_9blocks + D_A/D_B 70x70 PatchGAN, LSGAN + L1 "
                         "cycle/identity, ImagePool 50, Adam, 4 D updates per G update; batch %d per GPU at %dx%d "
-                        "(BASELINE configs[1])" % (batch, size, size),
-            "per_gpu_batch": batch, "image": size, "parallelism": "dp%d" % world, "launch_mode": graph_note,
+                        "(BASELINE configs[1]%s)" % (batch, img_h, img_w, "" if px_scale == 1.0 else
+                                                      "; other image shape, TFLOP scaled by the pixel count"),
+            "per_gpu_batch": batch, "image": img_h if img_w == img_h else [img_h, img_w], "parallelism": "dp%d" % world,
+            "launch_mode": graph_note,
             "batched_passes": not args.no_batch_passes,
             "l2": "working set per step (saved activations of 6 generator + 18 discriminator passes, > 5 GB) "
                   "exceeds the 126 MB L2; no explicit flush",
-            "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * batch,
+            "algorithmic_tflop_per_step": TFLOP_PER_SAMPLE * px_scale * batch,
             "step_tflops_per_gpu": step_tflops,
             "step_frac_of_sustained_bf16_peak": step_tflops / peaks["bf16_sustained"],
             "g_forward_img_per_s_batch1": 1e3 / g1["graph"],
@@ -956,7 +964,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--size", type=int, default=256, help="image height (and width unless --width is given)")
+    ap.add_argument("--width", type=int, default=0, help="image width for non-square shapes, e.g. --size 192 --width 640")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cudnn-baseline", action="store_true",
                     help="skip config.cudnn_same_box (the stock-PyTorch / cuDNN step timed on this GPU)")
