@@ -1135,20 +1135,24 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
     for (int i = 0; i < 4; ++i) sg[kApply ? 0 : i] = sgy[kApply ? 0 : i] = make_float2(0.f, 0.f);
   }
   {
+    // norm none (a convolution + activation layer): mean 0, rstd 1, no mean terms — dy = ga, the reduce pass yields the
+    // bias gradient sum ga, and the activation mask is taken from the stored OUTPUT y (act(x) > 0 <=> x > 0)
+    const bool norm_none = p.norm == CDB_NORM_NONE;
     const float4* st4 = reinterpret_cast<const float4*>(p.stats + (static_cast<int64_t>(grp) * C + v * 8) * 2);
     const float4* bs4 = reinterpret_cast<const float4*>(p.bstats + (static_cast<int64_t>(grp) * C + v * 8) * 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 st = st4[i];                      // (s1, s2) of channels 2i, 2i + 1
+      float4 st = make_float4(0.f, 0.f, 0.f, 0.f);   // (s1, s2) of channels 2i, 2i + 1
       float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kApply) bs = bs4[i];
+      if (!norm_none) st = st4[i];
+      if (kApply && !norm_none) bs = bs4[i];
       const float s1[2] = {st.x, st.z}, s2[2] = {st.y, st.w}, b1[2] = {bs.x, bs.z}, b2[2] = {bs.y, bs.w};
       float mean[2], a[2], b[2], dd[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         mean[e] = s1[e] * p.inv_count;
         const float var = fmaxf(s2[e] * p.inv_count - mean[e] * mean[e], 0.f);
-        const float rstd = rsqrtf(var + p.eps);
+        const float rstd = norm_none ? 1.f : rsqrtf(var + p.eps);
         const float m1 = b1[e] * p.inv_count, m2 = b2[e] * p.inv_count;
         a[e] = rstd;
         b[e] = -rstd * rstd * m2;
@@ -1272,10 +1276,13 @@ __global__ void __launch_bounds__(256, 2) norm_bwd_tma_kernel(NormBwdParams p, T
           a_gy += red[(j * 2 + 1) * 256 + l * cv + vv];
         }
         const int ch = vv * 8 + j;
-        const float s1 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2];
-        const float s2 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2 + 1];
-        const float mean = s1 * p.inv_count;
-        const float rstd = rsqrtf(fmaxf(s2 * p.inv_count - mean * mean, 0.f) + p.eps);
+        float mean = 0.f, rstd = 1.f;
+        if (p.norm != CDB_NORM_NONE) {
+          const float s1 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2];
+          const float s2 = p.stats[(static_cast<int64_t>(grp) * C + ch) * 2 + 1];
+          mean = s1 * p.inv_count;
+          rstd = rsqrtf(fmaxf(s2 * p.inv_count - mean * mean, 0.f) + p.eps);
+        }
         atomicAdd(p.bstats + (static_cast<int64_t>(grp) * C + ch) * 2, a_g);
         atomicAdd(p.bstats + (static_cast<int64_t>(grp) * C + ch) * 2 + 1, rstd * (a_gy - mean * a_g));
       }
@@ -1858,6 +1865,22 @@ extern "C" int cdb_norm_act_bwd(const CdbNormDesc* d, const CdbAct* y, const Cdb
       if (dt == CDB_F32) launch_norm_bwd<float, true>(p, grid, stream);
       else launch_norm_bwd<__nv_bfloat16, true>(p, grid, stream);
     }
+    CDB_LAUNCH_OK();
+    return CDB_OK;
+  }
+  // a convolution + activation layer without normalisation (the PatchGAN's first layer): same staged kernels, the
+  // reduce pass only when the bias gradient is wanted
+  const bool none_staged = dt == CDB_BF16 && d->norm == CDB_NORM_NONE && !accum_f32 && p.pre_act == CDB_ACT_NONE &&
+                           p.has_dout && d->gamma == nullptr && d->beta == nullptr &&
+                           (p.act == CDB_ACT_NONE || p.act == CDB_ACT_RELU || p.act == CDB_ACT_LEAKY) && tma_eligible(p) &&
+                           !(getenv("CDB_NORM_NONE_STAGED") && atoi(getenv("CDB_NORM_NONE_STAGED")) == 0);
+  if (none_staged) {
+    p.per_image = 0;   // one group: the bias gradient of the whole batch
+    if (bstats) {
+      launch_tma<false>(p, y->n, stream);
+      CDB_LAUNCH_OK();
+    }
+    launch_tma<true>(p, y->n, stream);
     CDB_LAUNCH_OK();
     return CDB_OK;
   }

@@ -45,6 +45,8 @@ def _ref_forward(y, norm, act, slope, res, pad, gamma=None, beta=None):
     ('batch', 'relu', 0, False, 72, 8, 12),
     ('batch', 'leaky', 0, False, 1664, 4, 6),
     ('none', 'leaky', 0, False, 64, 20, 20),
+    ('none', 'leaky', 0, False, 64, 24, 40),     # rows long enough for the staged backward (PatchGAN first layer)
+    ('none', 'relu', 1, False, 128, 12, 64),     # staged, reflect fold, packed ReLU mask from the stored output
 ])
 def test_norm_act_forward_backward(norm, act, pad, use_res, c, h, w):
     from cycle_depth_estimation_b200 import ops
