@@ -252,17 +252,25 @@ __device__ __forceinline__ float act_fwd_t(float v, float slope) {
 template <typename T>
 __device__ __forceinline__ void write_halo(T* ob, int osh, int osw, int h, int w, int H, int W,
                                            int pad, const typename Vec8<T>::type& o) {
-  // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d
-  int hh[2], ww[2];
-  int nh = 0, nw = 0;
-  if (h >= 1 && h <= pad) hh[nh++] = -h;
-  if (h <= H - 2 && h >= H - 1 - pad) hh[nh++] = 2 * (H - 1) - h;
-  if (w >= 1 && w <= pad) ww[nw++] = -w;
-  if (w <= W - 2 && w >= W - 1 - pad) ww[nw++] = 2 * (W - 1) - w;
-  for (int a = 0; a < nh; ++a) st16(ob + hh[a] * osh + w * osw, o);
-  for (int b = 0; b < nw; ++b) st16(ob + h * osh + ww[b] * osw, o);
-  for (int a = 0; a < nh; ++a)
-    for (int b = 0; b < nw; ++b) st16(ob + hh[a] * osh + ww[b] * osw, o);
+  // reflect halo: interior row d (1..pad) mirrors to row -d, row H-1-d to row H-1+d (scalars, no indexed arrays: those
+  // went to local memory)
+  constexpr int kNone = -(1 << 30);
+  const int h1 = (h >= 1 && h <= pad) ? -h : kNone;
+  const int h2 = (h <= H - 2 && h >= H - 1 - pad) ? 2 * (H - 1) - h : kNone;
+  const int w1 = (w >= 1 && w <= pad) ? -w : kNone;
+  const int w2 = (w <= W - 2 && w >= W - 1 - pad) ? 2 * (W - 1) - w : kNone;
+  if (h1 != kNone) {
+    st16(ob + h1 * osh + w * osw, o);
+    if (w1 != kNone) st16(ob + h1 * osh + w1 * osw, o);
+    if (w2 != kNone) st16(ob + h1 * osh + w2 * osw, o);
+  }
+  if (h2 != kNone) {
+    st16(ob + h2 * osh + w * osw, o);
+    if (w1 != kNone) st16(ob + h2 * osh + w1 * osw, o);
+    if (w2 != kNone) st16(ob + h2 * osh + w2 * osw, o);
+  }
+  if (w1 != kNone) st16(ob + h * osh + w1 * osw, o);
+  if (w2 != kNone) st16(ob + h * osh + w2 * osw, o);
 }
 
 template <typename T, int ACT, bool HAS_RES>
