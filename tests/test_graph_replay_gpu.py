@@ -123,6 +123,35 @@ def test_fused_adam_emits_the_packed_operands():
     assert ops._lib.lib().cdb_launch_count() - n0 == fwd_launches + 5   # only the invalidated run re-packs (5 filters)
 
 
+def test_fused_adam_packed_operands_of_the_resnet_generator():
+    """The tiled walk of adam_multi_kernel (32 x 32 filters x taps through shared memory) on every filter shape of the
+    ResNet generator: 3x3 stride-1 / stride-2 / transposed (d0 = Cin), channel counts below one tile, and the
+    row-packed 7x7 image layers that keep the element-order walk — every cached operand equals a fresh packing."""
+    from cycle_depth_estimation_b200 import networks as N, ops
+    from cycle_depth_estimation_b200.cycle_gan_model import FusedAdam
+    torch.manual_seed(2)
+    with quiet():
+        net = N.define_G(3, 3, 24, 'resnet_6blocks', 'instance', False, 'normal', 0.02, ['cuda'])
+    x = seeded_image(2, 3, 64, 64)
+    opt = FusedAdam(net.parameters(), lr=1e-2, betas=(0.5, 0.999))
+    for _ in range(2):                              # the second step updates operands the first one emitted
+        opt.zero_grad()
+        net(x).square().mean().backward()
+        opt.step()
+    checked = 0
+    for mod in net.modules():
+        w = getattr(mod, 'weight', None)
+        if w is None or w.dim() != 4 or '_cdb_packed' not in w.__dict__:
+            continue
+        for key, (ver, packed) in w.__dict__['_cdb_packed'].items():
+            if len(key) != 3 or not isinstance(key[0], bool) or key[2]:
+                continue
+            fresh, _, _ = ops.pack_conv_weight(w.detach().contiguous(), key[0], key[1])
+            assert torch.equal(packed[0], fresh), (type(mod).__name__, tuple(w.shape), key)
+            checked += 1
+    assert checked >= 20, checked
+
+
 def test_dropout_draws_a_new_mask_at_every_replay():
     """nn.Dropout inside the U-Net (models/networks.py:305-306): the seed lives in device memory and a node of the
     graph bumps it, so two replays of one captured forward differ; the backward regenerates the forward's mask."""
